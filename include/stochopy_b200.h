@@ -1,0 +1,180 @@
+/*
+ * stochopy_b200 -- C ABI of the B200 population engine.
+ *
+ * The reference (keurfonluu/stochopy v2.3.0) is pure Python and has no FFI; the
+ * entry points below are the functions a maintainer would bind (ctypes, see
+ * INTEGRATION.md) to run the per-generation hot path of
+ * stochopy.optimize.minimize() on a B200.  Each entry cites the reference code
+ * it replaces.  All pointers named d_* / inside the state structs are DEVICE
+ * pointers (row-major, leading dimension `ld` in elements, 16-byte aligned,
+ * ld a multiple of 16/sizeof(T)); everything is enqueued on `stream`
+ * (a cudaStream_t passed as void*, NULL = legacy default stream) and returns
+ * immediately.  Return value: 0 on success, <0 on error (sp_last_error()).
+ *
+ * No function here computes on the CPU: if no CUDA device / kernel image is
+ * usable the call fails.
+ */
+#ifndef STOCHOPY_B200_H
+#define STOCHOPY_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SP_ABI_VERSION 1
+
+/* error codes */
+#define SP_OK 0
+#define SP_ERR_ARG (-1)    /* bad argument (shape, enum, alignment) */
+#define SP_ERR_CUDA (-2)   /* CUDA runtime error, text in sp_last_error() */
+#define SP_ERR_SHAPE (-3)  /* ndim outside the compiled row shapes */
+
+/* ctrl.status while the optimiser has not terminated */
+#define SP_RUNNING (-1000)
+
+typedef enum { SP_F32 = 0, SP_F64 = 1 } sp_dtype;
+
+/* stochopy/factory/benchmark.py; SP_OBJ_HOST = fitness supplied by the caller
+ * (arbitrary Python fun(x): propose on device, evaluate on host, select on device) */
+typedef enum {
+  SP_OBJ_ACKLEY = 0,      /* benchmark.py:14-34  */
+  SP_OBJ_GRIEWANK = 1,    /* benchmark.py:37-56  */
+  SP_OBJ_QUARTIC = 2,     /* benchmark.py:59-76  */
+  SP_OBJ_RASTRIGIN = 3,   /* benchmark.py:79-97  */
+  SP_OBJ_ROSENBROCK = 4,  /* benchmark.py:100-118 */
+  SP_OBJ_SPHERE = 5,      /* benchmark.py:121-136 */
+  SP_OBJ_STYBLINSKI_TANG = 6, /* benchmark.py:139-156 */
+  SP_OBJ_HOST = 100
+} sp_objective;
+
+/* de/_strategy.py:41-46 */
+typedef enum { SP_DE_RAND1BIN = 0, SP_DE_RAND2BIN = 1, SP_DE_BEST1BIN = 2, SP_DE_BEST2BIN = 3 } sp_de_strategy;
+/* de/_constraints.py:31-34, cpso/_constraints.py:69-72, cmaes/_constraints.py:85-87 */
+typedef enum { SP_CONS_NONE = 0, SP_CONS_RANDOM = 1, SP_CONS_SHRINK = 2, SP_CONS_PENALIZE = 3 } sp_constraint;
+
+/* Device-resident control block shared by every generation kernel of one
+ * optimiser instance (64 bytes).  Kernels return at once when
+ * status != SP_RUNNING, so generations can be enqueued ahead of the host. */
+typedef struct {
+  int32_t status;        /* SP_RUNNING or the reference's status code (_common.py:12-24) */
+  int32_t nit;           /* generation that produced gbest/gfit */
+  uint32_t done_blocks;  /* last-block-done counter, self-resetting */
+  int32_t flag;          /* method specific (cpso: restart fired; es: hsig) */
+  int64_t gbest_row;     /* row of the current best in the population */
+  double gfit;           /* best objective value */
+  double dist;           /* |gbest_old - gbest_new| of the last generation */
+  double aux[3];         /* method specific (cpso: swarm radius, nw; es: sigma) */
+} sp_ctrl;
+
+/* ---- library ---------------------------------------------------------- */
+int sp_abi_version(void);
+const char* sp_last_error(void);
+/* SM count, L2 bytes, total HBM bytes, compute capability (major*10+minor) */
+int sp_device_info(int device, int* sm_count, int64_t* l2_bytes, int64_t* hbm_bytes, int* cc);
+/* kernels launched by this library since load (bench.py's gpu_launches) */
+int64_t sp_launch_count(void);
+/* scratch bytes every state struct needs behind `scratch` */
+int64_t sp_scratch_bytes(void);
+
+/* ---- a1+a2: batched objective  f[i] = fun(X[i] * scale + shift) ---------
+ * replaces optimizer.wrapper (stochopy/optimize/_common.py:79-80) calling
+ * stochopy/factory/benchmark.py once per row.  scale/shift may be NULL. */
+int sp_eval(int objective, int dtype, const void* d_X, int64_t P, int N, int64_t ld,
+            const void* d_scale, const void* d_shift, void* d_f, void* stream);
+
+/* ---- a3: Latin hypercube init (stochopy/optimize/_common.py:109-120) -----
+ * d_jitter (P x ld, U[0,1)) and d_perm (N x P int64, column permutations) may
+ * both be NULL: then draws are Philox/Feistel from `seed` on the device. */
+int sp_lhs_init(int dtype, void* d_X, int64_t P, int N, int64_t ld, const void* d_lower,
+                const void* d_upper, uint64_t seed, const void* d_jitter, const int64_t* d_perm,
+                void* stream);
+
+/* ---- a4: synchronous selection (stochopy/optimize/_common.py:123-160) ----
+ * rows with candfun < xfun: xfun = candfun and x = cand  (copy_when = 1), or,
+ * for ping-pong populations, rows that do NOT improve are copied from `cand`
+ * (the old population) into x (copy_when = 0).  Then argmin(xfun), distance to
+ * the previous best, status ladder; result in ctrl / d_gbest. */
+int sp_select_sync(int dtype, int it, int maxiter, double xtol, double ftol, const void* d_cand,
+                   const void* d_candfun, void* d_x, void* d_xfun, int64_t P, int N, int64_t ld,
+                   int copy_when, void* d_gbest, sp_ctrl* d_ctrl, void* d_scratch, void* stream);
+/* first evaluation of a population: xfun given, gbest = x[argmin], no status */
+int sp_best_init(int dtype, const void* d_x, const void* d_xfun, int64_t P, int N, int64_t ld,
+                 void* d_gbest, sp_ctrl* d_ctrl, void* d_scratch, void* stream);
+
+/* ---- a6-a10: differential evolution (stochopy/optimize/de/_de.py:314-351,
+ * de/_strategy.py, de/_constraints.py).  One call = one synchronous generation:
+ * donors, mutation, binomial crossover, bound repair, objective, selection,
+ * argmin and termination test, fused in one kernel. */
+typedef struct {
+  int32_t dtype, objective, strategy, constraint;
+  int64_t P;
+  int32_t N;
+  int32_t maxiter;
+  int64_t ld;
+  double F, CR, xtol, ftol;
+  uint64_t seed;
+  void* X[2];      /* ping-pong populations; generation `it` reads X[it&1], writes X[(it&1)^1] */
+  void* pbestfit;  /* (P) fitness of the population */
+  void* pfit;      /* (P) candidate fitness of the last generation (_de.py:349: pfit = candfun) */
+  void* gbest;     /* (ld) */
+  const void* lower;
+  const void* upper;
+  sp_ctrl* ctrl;
+  void* scratch;
+  /* explicit draws (rng="numpy"); all NULL => Philox in-kernel */
+  const void* r1;         /* (P x ld)  _de.py:250 */
+  const int64_t* donors;  /* (k x P)   _de.py:306,311 first k rows */
+  const int64_t* irand;   /* (P)       _de.py:340 */
+  const void* repair;     /* (P x ld)  de/_constraints.py:24 uniform(lower,upper) */
+} sp_de_state;
+int sp_de_generation(const sp_de_state* st, int it, void* stream);
+/* propose only: writes the trial population U into X[(it&1)^1] (SP_OBJ_HOST path) */
+int sp_de_propose(const sp_de_state* st, int it, void* stream);
+/* enqueue generations it_first .. it_first+n-1 (Philox draws only) */
+int sp_de_run(const sp_de_state* st, int it_first, int n, void* stream);
+
+/* ---- a11-a14: PSO / competitive PSO (stochopy/optimize/cpso/_cpso.py:324-361,
+ * 405-426, cpso/_constraints.py).  One call = velocity + position update with
+ * Shrink, objective, personal-best selection, argmin, termination. */
+typedef struct {
+  int32_t dtype, objective, constraint, pad_;
+  int64_t P;
+  int32_t N;
+  int32_t maxiter;
+  int64_t ld;
+  double w, c1, c2, xtol, ftol;
+  double gamma, delta;  /* competitivity (<0: plain PSO) and swarm radius threshold */
+  uint64_t seed;
+  void* X;
+  void* V;
+  void* pbest;
+  void* pbestfit;
+  void* pfit;
+  void* gbest;
+  const void* lower;
+  const void* upper;
+  sp_ctrl* ctrl;
+  void* scratch;
+  const void* r1;  /* (P x ld) _cpso.py:262 */
+  const void* r2;  /* (P x ld) _cpso.py:263 */
+} sp_pso_state;
+int sp_pso_generation(const sp_pso_state* st, int it, void* stream);
+int sp_pso_propose(const sp_pso_state* st, int it, void* stream);
+/* competitive restart (_cpso.py:405-426), split so host-drawn positions can be
+ * injected: plan = swarm radius, nw = rows to reset (ctrl->flag, 0 if the swarm is
+ * still wide), ascending stable rank of pbestfit into d_rank (P int32);
+ * apply = V=0, X=pbest=uniform(lower,upper), pbestfit=1e30 for the nw worst.
+ * d_fresh (nw x ld rows in the reference's reset order, worst first) may be NULL
+ * (Philox keyed by particle row). */
+int sp_cpso_restart_plan(const sp_pso_state* st, int it, int32_t* d_rank, void* stream);
+int sp_cpso_restart_apply(const sp_pso_state* st, int it, const int32_t* d_rank, const void* d_fresh, void* stream);
+int sp_cpso_restart(const sp_pso_state* st, int it, int32_t* d_rank, void* stream);
+/* enqueue generations it_first .. it_first+n-1 (+ restart when gamma >= 0) */
+int sp_pso_run(const sp_pso_state* st, int it_first, int n, int32_t* d_rank, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* STOCHOPY_B200_H */

@@ -1,0 +1,132 @@
+"""ctypes binding of libstochopy_b200.so (the C ABI in include/stochopy_b200.h).
+
+The shared library is built in-tree by ``__graft_entry__.build()`` (or
+``make -C stochopy_b200/csrc``).  There is no CPU fallback: if the library or a
+CUDA device is missing, loading / calling fails loudly.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libstochopy_b200.so")
+
+SP_RUNNING = -1000
+SP_F32, SP_F64 = 0, 1
+OBJECTIVES = {
+    "ackley": 0,
+    "griewank": 1,
+    "quartic": 2,
+    "rastrigin": 3,
+    "rosenbrock": 4,
+    "sphere": 5,
+    "styblinski_tang": 6,
+}
+SP_OBJ_HOST = 100
+DE_STRATEGIES = {"rand1bin": 0, "rand2bin": 1, "best1bin": 2, "best2bin": 3}
+DE_DONORS = {"rand1bin": 3, "rand2bin": 5, "best1bin": 2, "best2bin": 4}
+CONS_NONE, CONS_RANDOM, CONS_SHRINK, CONS_PENALIZE = 0, 1, 2, 3
+
+vp = C.c_void_p
+
+
+class Ctrl(C.Structure):
+    """sp_ctrl (64 bytes, device resident; this is its host mirror)."""
+
+    _fields_ = [
+        ("status", C.c_int32),
+        ("nit", C.c_int32),
+        ("done_blocks", C.c_uint32),
+        ("flag", C.c_int32),
+        ("gbest_row", C.c_int64),
+        ("gfit", C.c_double),
+        ("dist", C.c_double),
+        ("aux", C.c_double * 3),
+    ]
+
+
+class DeState(C.Structure):
+    _fields_ = [
+        ("dtype", C.c_int32), ("objective", C.c_int32), ("strategy", C.c_int32), ("constraint", C.c_int32),
+        ("P", C.c_int64), ("N", C.c_int32), ("maxiter", C.c_int32), ("ld", C.c_int64),
+        ("F", C.c_double), ("CR", C.c_double), ("xtol", C.c_double), ("ftol", C.c_double),
+        ("seed", C.c_uint64),
+        ("X", vp * 2), ("pbestfit", vp), ("pfit", vp), ("gbest", vp), ("lower", vp), ("upper", vp),
+        ("ctrl", vp), ("scratch", vp),
+        ("r1", vp), ("donors", vp), ("irand", vp), ("repair", vp),
+    ]
+
+
+class PsoState(C.Structure):
+    _fields_ = [
+        ("dtype", C.c_int32), ("objective", C.c_int32), ("constraint", C.c_int32), ("pad_", C.c_int32),
+        ("P", C.c_int64), ("N", C.c_int32), ("maxiter", C.c_int32), ("ld", C.c_int64),
+        ("w", C.c_double), ("c1", C.c_double), ("c2", C.c_double), ("xtol", C.c_double), ("ftol", C.c_double),
+        ("gamma", C.c_double), ("delta", C.c_double),
+        ("seed", C.c_uint64),
+        ("X", vp), ("V", vp), ("pbest", vp), ("pbestfit", vp), ("pfit", vp), ("gbest", vp),
+        ("lower", vp), ("upper", vp), ("ctrl", vp), ("scratch", vp),
+        ("r1", vp), ("r2", vp),
+    ]
+
+
+_i, _i64, _d, _u64 = C.c_int, C.c_int64, C.c_double, C.c_uint64
+
+# name -> (restype, argtypes); mirrors include/stochopy_b200.h one to one
+SIGNATURES = {
+    "sp_abi_version": (_i, []),
+    "sp_last_error": (C.c_char_p, []),
+    "sp_device_info": (_i, [_i, C.POINTER(_i), C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i)]),
+    "sp_launch_count": (_i64, []),
+    "sp_scratch_bytes": (_i64, []),
+    "sp_eval": (_i, [_i, _i, vp, _i64, _i, _i64, vp, vp, vp, vp]),
+    "sp_lhs_init": (_i, [_i, vp, _i64, _i, _i64, vp, vp, _u64, vp, vp, vp]),
+    "sp_select_sync": (_i, [_i, _i, _i, _d, _d, vp, vp, vp, vp, _i64, _i, _i64, _i, vp, vp, vp, vp]),
+    "sp_best_init": (_i, [_i, vp, vp, _i64, _i, _i64, vp, vp, vp, vp]),
+    "sp_de_generation": (_i, [C.POINTER(DeState), _i, vp]),
+    "sp_de_propose": (_i, [C.POINTER(DeState), _i, vp]),
+    "sp_de_run": (_i, [C.POINTER(DeState), _i, _i, vp]),
+    "sp_pso_generation": (_i, [C.POINTER(PsoState), _i, vp]),
+    "sp_pso_propose": (_i, [C.POINTER(PsoState), _i, vp]),
+    "sp_cpso_restart_plan": (_i, [C.POINTER(PsoState), _i, vp, vp]),
+    "sp_cpso_restart_apply": (_i, [C.POINTER(PsoState), _i, vp, vp, vp]),
+    "sp_cpso_restart": (_i, [C.POINTER(PsoState), _i, vp, vp]),
+    "sp_pso_run": (_i, [C.POINTER(PsoState), _i, _i, vp, vp]),
+}
+
+_lib = None
+
+
+class EngineError(RuntimeError):
+    """A call into libstochopy_b200.so failed."""
+
+
+def load():
+    """Load the shared library once; raises ImportError if it was not built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "or `make -C stochopy_b200/csrc` (there is no CPU fallback)"
+            )
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)  # AttributeError if the header and the library disagree
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        msg = load().sp_last_error().decode("utf-8", "replace")
+        raise EngineError(f"libstochopy_b200 error {rc}: {msg}")
+
+
+def call(name, *args):
+    check(getattr(load(), name)(*args))
+
+
+def launch_count():
+    return int(load().sp_launch_count())

@@ -1,0 +1,289 @@
+// Shared device/host helpers of the stochopy_b200 kernels (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <atomic>
+#include <cstdio>
+
+#include "../../include/stochopy_b200.h"
+
+namespace sp {
+
+// ---- host side -------------------------------------------------------------
+void set_error(const char* fmt, ...);
+extern std::atomic<long long> g_launches;
+int sm_count();
+
+#define SP_CHECK_ARG(cond, msg)                      \
+  do {                                               \
+    if (!(cond)) {                                   \
+      sp::set_error("%s: %s", __func__, msg);        \
+      return SP_ERR_ARG;                             \
+    }                                                \
+  } while (0)
+
+#define SP_CHECK_LAUNCH()                                                     \
+  do {                                                                        \
+    cudaError_t e_ = cudaGetLastError();                                      \
+    if (e_ != cudaSuccess) {                                                  \
+      sp::set_error("%s: CUDA launch failed: %s", __func__, cudaGetErrorString(e_)); \
+      return SP_ERR_CUDA;                                                     \
+    }                                                                         \
+    sp::g_launches.fetch_add(1, std::memory_order_relaxed);                   \
+  } while (0)
+
+constexpr int kThreads = 256;            // 8 warps per CTA
+constexpr int kMaxBlocks = 148 * 16;     // scratch is sized for this many per-CTA minima
+constexpr int kScratchBytes = kMaxBlocks * 16 + 256;
+
+// ---- numeric traits ----------------------------------------------------------
+template <typename T> struct Num;
+template <> struct Num<float> {
+  static constexpr int VEC = 4;
+  using vec_t = float4;
+  static __device__ __forceinline__ float inf() { return __int_as_float(0x7f800000); }
+};
+template <> struct Num<double> {
+  static constexpr int VEC = 2;
+  using vec_t = double2;
+  static __device__ __forceinline__ double inf() { return __longlong_as_double(0x7ff0000000000000LL); }
+};
+
+// Round-to-nearest ops that ptxas may not contract into FMAs: the update
+// formulas mirror numpy's separate multiply and add so trajectories stay on the
+// reference's path; objective evaluation is free to use FMA.
+__device__ __forceinline__ float add_rn(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float sub_rn(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ float mul_rn(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float div_rn(float a, float b) { return __fdiv_rn(a, b); }
+__device__ __forceinline__ double add_rn(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ double sub_rn(double a, double b) { return __dsub_rn(a, b); }
+__device__ __forceinline__ double mul_rn(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double div_rn(double a, double b) { return __ddiv_rn(a, b); }
+
+// ---- row tiles -----------------------------------------------------------------
+// A population row of N scalars is held by LPR lanes, CH chunks of VEC scalars
+// per lane (16-byte vector loads).  Column of element (c, e) on lane l:
+//   j = (c * LPR + l) * VEC + e
+// A warp carries 32 / LPR rows at once.
+template <typename T, int CH, int LPR>
+struct Tile {
+  static constexpr int VEC = Num<T>::VEC;
+  static constexpr int RPW = 32 / LPR;           // rows per warp
+  static constexpr int COLS = CH * LPR * VEC;    // widest row this shape holds
+  T v[CH][VEC];
+
+  static __device__ __forceinline__ int col(int c, int l, int e) { return (c * LPR + l) * VEC + e; }
+
+  // rows are padded to ld (multiple of VEC) so whole vectors are always in bounds
+  __device__ __forceinline__ void load(const T* __restrict__ row, int l, int ld) {
+    using V = typename Num<T>::vec_t;
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
+      int j0 = col(c, l, 0);
+      if (j0 < ld) {
+        V t = *reinterpret_cast<const V*>(row + j0);
+        const T* p = reinterpret_cast<const T*>(&t);
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) v[c][e] = p[e];
+      } else {
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) v[c][e] = T(0);
+      }
+    }
+  }
+  __device__ __forceinline__ void store(T* __restrict__ row, int l, int ld) const {
+    using V = typename Num<T>::vec_t;
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
+      int j0 = col(c, l, 0);
+      if (j0 < ld) {
+        V t;
+        T* p = reinterpret_cast<T*>(&t);
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) p[e] = v[c][e];
+        *reinterpret_cast<V*>(row + j0) = t;
+      }
+    }
+  }
+};
+
+// reductions over the LPR lanes that share a row (xor butterflies stay inside
+// an aligned group of LPR lanes)
+template <int LPR, typename T>
+__device__ __forceinline__ T group_sum(T x) {
+#pragma unroll
+  for (int o = LPR / 2; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+  return x;
+}
+template <int LPR, typename T>
+__device__ __forceinline__ T group_prod(T x) {
+#pragma unroll
+  for (int o = LPR / 2; o > 0; o >>= 1) x *= __shfl_xor_sync(0xffffffffu, x, o);
+  return x;
+}
+template <int LPR, typename T>
+__device__ __forceinline__ T group_min(T x) {
+#pragma unroll
+  for (int o = LPR / 2; o > 0; o >>= 1) {
+    T y = __shfl_xor_sync(0xffffffffu, x, o);
+    x = y < x ? y : x;
+  }
+  return x;
+}
+template <int LPR, typename T>
+__device__ __forceinline__ T group_max(T x) {
+#pragma unroll
+  for (int o = LPR / 2; o > 0; o >>= 1) {
+    T y = __shfl_xor_sync(0xffffffffu, x, o);
+    x = y > x ? y : x;
+  }
+  return x;
+}
+
+// (fitness, row) pairs ordered like np.argmin: smaller value, then smaller row
+struct Best {
+  double f;
+  long long row;
+};
+__device__ __forceinline__ bool better(double f, long long r, double g, long long s) {
+  return f < g || (f == g && r < s);
+}
+__device__ __forceinline__ Best warp_best(Best b) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    double f = __shfl_xor_sync(0xffffffffu, b.f, o);
+    long long r = __shfl_xor_sync(0xffffffffu, b.row, o);
+    if (better(f, r, b.f, b.row)) {
+      b.f = f;
+      b.row = r;
+    }
+  }
+  return b;
+}
+
+// Per-CTA minimum -> scratch[blockIdx]; the last CTA to arrive reduces all of
+// them.  Returns true (for every thread of that last CTA) with the global best.
+__device__ __forceinline__ bool grid_best(Best mine, Best* scratch, sp_ctrl* ctrl, Best* out) {
+  __shared__ Best s_best[kThreads / 32];
+  __shared__ bool s_last;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  mine = warp_best(mine);
+  if (lane == 0) s_best[warp] = mine;
+  __syncthreads();
+  if (warp == 0) {
+    Best b = lane < (blockDim.x >> 5) ? s_best[lane] : Best{1.0 / 0.0, 0x7fffffffffffffffLL};
+    b = warp_best(b);
+    if (lane == 0) {
+      scratch[blockIdx.x] = b;
+      __threadfence();
+      unsigned prev = atomicAdd(&ctrl->done_blocks, 1u);
+      s_last = (prev == gridDim.x - 1);
+    }
+  }
+  __syncthreads();
+  if (!s_last) return false;
+  __threadfence();
+  Best b{1.0 / 0.0, 0x7fffffffffffffffLL};
+  for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x) {
+    Best o{__ldcg(&scratch[i].f), __ldcg(&scratch[i].row)};
+    if (better(o.f, o.row, b.f, b.row)) b = o;
+  }
+  b = warp_best(b);
+  __syncthreads();
+  if (lane == 0) s_best[warp] = b;
+  __syncthreads();
+  b = s_best[0];
+  for (int w = 1; w < (int)(blockDim.x >> 5); ++w)
+    if (better(s_best[w].f, s_best[w].row, b.f, b.row)) b = s_best[w];
+  *out = b;
+  if (threadIdx.x == 0) ctrl->done_blocks = 0;  // ready for the next launch
+  return true;
+}
+
+// Last-CTA epilogue of every generation: new best row -> gbest, distance to
+// the previous best, status ladder of selection_sync (_common.py:135-158).
+// `it` < 0: initial population (no status test).
+template <typename T>
+__device__ __forceinline__ void finalize_generation(Best b, const T* __restrict__ xrows, int64_t ld, int N,
+                                                    T* gbest, sp_ctrl* ctrl, int it, int maxiter, double xtol,
+                                                    double ftol) {
+  __shared__ double s_part[kThreads / 32];
+  const T* src = xrows + b.row * ld;
+  double acc = 0.0;
+  for (int j = threadIdx.x; j < N; j += blockDim.x) {
+    T nv = src[j];
+    double d = (double)(T)(gbest[j] - nv);
+    acc += d * d;
+    gbest[j] = nv;
+  }
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double tot = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += s_part[w];
+    double dist = sqrt(tot);
+    ctrl->gbest_row = b.row;
+    ctrl->gfit = b.f;
+    ctrl->dist = dist;
+    if (it >= 0) {
+      ctrl->nit = it;
+      int st = SP_RUNNING;
+      if (dist <= xtol && b.f <= ftol) st = 0;
+      else if (b.f <= ftol) st = 1;
+      else if (it >= maxiter) st = -1;
+      ctrl->status = st;
+    }
+  }
+}
+
+__device__ __forceinline__ bool running(const sp_ctrl* ctrl) {
+  return *reinterpret_cast<const volatile int32_t*>(&ctrl->status) == SP_RUNNING;
+}
+
+// ---- launch shape ------------------------------------------------------------
+// Host-side choice of (CH, LPR) for a row of N scalars of type T; returns false
+// if N exceeds the compiled shapes.
+struct Shape {
+  int ch, lpr;
+};
+inline bool pick_shape(int N, int vec, Shape* s) {
+  const int lprs[] = {1, 4, 16, 32};
+  for (int l : lprs)
+    if (l * vec >= N) {
+      *s = {1, l};
+      return true;
+    }
+  const int chs[] = {2, 4, 8, 16};
+  for (int c : chs)
+    if (c * 32 * vec >= N) {
+      *s = {c, 32};
+      return true;
+    }
+  return false;
+}
+inline int grid_for_rows(int64_t P, int lpr, int blocks_per_sm) {
+  int64_t rows_per_block = (int64_t)(kThreads / 32) * (32 / lpr);
+  int64_t need = (P + rows_per_block - 1) / rows_per_block;
+  int64_t cap = (int64_t)sm_count() * blocks_per_sm;
+  if (cap > kMaxBlocks) cap = kMaxBlocks;
+  int64_t g = need < cap ? need : cap;
+  return (int)(g < 1 ? 1 : g);
+}
+
+// dispatch a functor templated on <T, CH, LPR>
+#define SP_DISPATCH_SHAPE(T, shape, CALL)                                   \
+  do {                                                                      \
+    if ((shape).lpr == 1) { CALL(T, 1, 1); }                                \
+    else if ((shape).lpr == 4) { CALL(T, 1, 4); }                           \
+    else if ((shape).lpr == 16) { CALL(T, 1, 16); }                         \
+    else if ((shape).ch == 1) { CALL(T, 1, 32); }                           \
+    else if ((shape).ch == 2) { CALL(T, 2, 32); }                           \
+    else if ((shape).ch == 4) { CALL(T, 4, 32); }                           \
+    else if ((shape).ch == 8) { CALL(T, 8, 32); }                           \
+    else { CALL(T, 16, 32); }                                               \
+  } while (0)
+
+}  // namespace sp

@@ -1,0 +1,120 @@
+// Counter-based random draws of the stochopy_b200 kernels.
+//
+// Philox4x32-10 (Salmon, Moraes, Dror, Shaw, SC'11) with
+//   key     = (seed & 0xffffffff, seed >> 32)
+//   counter = (block, row, generation, purpose)
+// A draw depends only on what it is for -- not on the launch shape nor on the
+// number of GPUs -- and is reproduced bit for bit by oracle/philox.py in the
+// tests.  One block = 4 x u32 = 4 fp32 columns or 2 fp64 columns, i.e. exactly
+// one 16-byte vector of a row tile.
+#pragma once
+#include <stdint.h>
+
+namespace sp {
+
+enum Purpose : uint32_t {
+  kLhsJitter = 1,
+  kDeCross = 2,
+  kDeIndex = 3,
+  kDeRepair = 4,
+  kPsoR1 = 5,
+  kPsoR2 = 6,
+  kPsoRestart = 7,
+  kEsZ = 8,
+  kVdInject = 9,
+  kEsMean0 = 10,
+  kVdV0 = 11,
+  kNaWalk = 12,
+};
+
+__device__ __forceinline__ uint4 philox4x32(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint64_t seed) {
+  uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+    c0 = n0;
+    c1 = lo1;
+    c2 = n2;
+    c3 = lo0;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  return make_uint4(c0, c1, c2, c3);
+}
+
+// U[0,1) for one vector of a row: fp32 -> 4 x 24-bit, fp64 -> 2 x 53-bit
+__device__ __forceinline__ void uniform_block(uint4 o, float (&u)[4]) {
+  u[0] = __uint2float_rn(o.x >> 8) * 5.9604644775390625e-08f;
+  u[1] = __uint2float_rn(o.y >> 8) * 5.9604644775390625e-08f;
+  u[2] = __uint2float_rn(o.z >> 8) * 5.9604644775390625e-08f;
+  u[3] = __uint2float_rn(o.w >> 8) * 5.9604644775390625e-08f;
+}
+__device__ __forceinline__ void uniform_block(uint4 o, double (&u)[2]) {
+  unsigned long long a = ((unsigned long long)o.x << 21) | (o.y >> 11);
+  unsigned long long b = ((unsigned long long)o.z << 21) | (o.w >> 11);
+  u[0] = __ull2double_rn(a) * 1.1102230246251565e-16;
+  u[1] = __ull2double_rn(b) * 1.1102230246251565e-16;
+}
+
+// N(0,1) by Box-Muller on the same block
+__device__ __forceinline__ void normal_block(uint4 o, float (&z)[4]) {
+  const float s = 5.9604644775390625e-08f;
+  float u1 = (__uint2float_rn(o.x >> 8) + 1.0f) * s, u2 = __uint2float_rn(o.y >> 8) * s;
+  float u3 = (__uint2float_rn(o.z >> 8) + 1.0f) * s, u4 = __uint2float_rn(o.w >> 8) * s;
+  float r0 = sqrtf(-2.0f * logf(u1)), r1 = sqrtf(-2.0f * logf(u3));
+  float sn, cs;
+  sincospif(2.0f * u2, &sn, &cs);
+  z[0] = r0 * cs;
+  z[1] = r0 * sn;
+  sincospif(2.0f * u4, &sn, &cs);
+  z[2] = r1 * cs;
+  z[3] = r1 * sn;
+}
+__device__ __forceinline__ void normal_block(uint4 o, double (&z)[2]) {
+  unsigned long long a = ((unsigned long long)o.x << 21) | (o.y >> 11);
+  unsigned long long b = ((unsigned long long)o.z << 21) | (o.w >> 11);
+  double u1 = (__ull2double_rn(a) + 1.0) * 1.1102230246251565e-16;
+  double u2 = __ull2double_rn(b) * 1.1102230246251565e-16;
+  double r = sqrt(-2.0 * log(u1));
+  double sn, cs;
+  sincospi(2.0 * u2, &sn, &cs);
+  z[0] = r * cs;
+  z[1] = r * sn;
+}
+
+// integer in [0, n) from one word (multiply-shift; bias < n / 2^32)
+__device__ __forceinline__ uint32_t bounded(uint32_t word, uint32_t n) { return __umulhi(word, n); }
+
+// ---- keyed permutation of [0, P) for the Latin hypercube ----------------------
+__device__ __forceinline__ uint32_t mix32(uint32_t h) {
+  h ^= h >> 16;
+  h *= 0x85EBCA6Bu;
+  h ^= h >> 13;
+  h *= 0xC2B2AE35u;
+  h ^= h >> 16;
+  return h;
+}
+// 4-round Feistel on 2*half bits + cycle walking (bijective on [0,P))
+__device__ __forceinline__ uint32_t lhs_permute(uint32_t i, uint32_t P, uint32_t col, uint64_t seed) {
+  uint32_t bits = 32 - __clz(P - 1);
+  if (bits < 2) bits = 2;
+  const uint32_t half = (bits + 1) >> 1, mask = (1u << half) - 1u;
+  const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32), colk = col * 0x9E3779B1u;
+  uint32_t v = i;
+  do {
+    uint32_t L = v >> half, R = v & mask;
+#pragma unroll
+    for (uint32_t rnd = 0; rnd < 4; ++rnd) {
+      uint32_t f = mix32(R ^ colk ^ ((rnd & 1u) ? k1 : k0) ^ ((rnd + 1u) * 0x7F4A7C15u));
+      uint32_t nr = (L ^ f) & mask;
+      L = R;
+      R = nr;
+    }
+    v = (L << half) | R;
+  } while (v >= P);
+  return v;
+}
+
+}  // namespace sp

@@ -1,0 +1,384 @@
+// PSO / competitive PSO: one fused kernel per synchronous generation.
+// Reference: stochopy/optimize/cpso/_cpso.py:324-361 (mutation, pso_sync),
+// cpso/_constraints.py (NoConstraint, Shrink), :405-426 (restart) and
+// selection_sync (_common.py:123-160) with cand = X, x = pbest.
+//
+// Per particle (row-local, in place): read X, V, pbest; write X, V and, on
+// improvement only, pbest.  Algorithmic HBM bytes per particle: 5 * N * s + 3 * s.
+#include "objectives.cuh"
+#include "philox.cuh"
+
+namespace sp {
+
+template <typename T>
+struct PsoArgs {
+  int objective, constraint, it, maxiter, N, propose_only;
+  int64_t P, ld;
+  T w, c1, c2;
+  double xtol, ftol;
+  uint64_t seed;
+  T* X;
+  T* V;
+  T* pbest;
+  T* pbestfit;
+  T* pfit;
+  T* gbest;
+  const T* lower;
+  const T* upper;
+  sp_ctrl* ctrl;
+  Best* scratch;
+  const T* r1;
+  const T* r2;
+};
+
+template <typename T, int CH, int LPR, bool PHILOX>
+__global__ void __launch_bounds__(kThreads)
+pso_generation_kernel(const PsoArgs<T> a) {
+  using TL = Tile<T, CH, LPR>;
+  constexpr int VEC = Num<T>::VEC;
+  if (!running(a.ctrl)) return;
+  const int lane = threadIdx.x & 31, l = lane % LPR, sub = lane / LPR;
+  const int64_t warp = (int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * (kThreads / 32);
+  const int64_t groups = (a.P + TL::RPW - 1) / TL::RPW;
+  const int ld = (int)a.ld;
+
+  TL gb;
+  gb.load(a.gbest, l, ld);
+
+  Best mine{1.0 / 0.0, 0x7fffffffffffffffLL};
+  for (int64_t g = warp; g < groups; g += nwarps) {
+    int64_t row = g * TL::RPW + sub;
+    const bool live = row < a.P;
+    if (!live) row = a.P - 1;
+
+    TL x, v;
+    {
+      TL pb;
+      x.load(a.X + row * a.ld, l, ld);
+      v.load(a.V + row * a.ld, l, ld);
+      pb.load(a.pbest + row * a.ld, l, ld);
+      // V = w V + c1 r1 (pbest - X) + c2 r2 (gbest - X), _cpso.py:326 (numpy's order)
+#pragma unroll
+      for (int c = 0; c < CH; ++c) {
+        const int j0 = TL::col(c, l, 0);
+        T r1[VEC], r2[VEC];
+        if (PHILOX) {
+          uniform_block(philox4x32((uint32_t)(j0 / VEC), (uint32_t)row, (uint32_t)a.it, kPsoR1, a.seed), r1);
+          uniform_block(philox4x32((uint32_t)(j0 / VEC), (uint32_t)row, (uint32_t)a.it, kPsoR2, a.seed), r2);
+        } else {
+#pragma unroll
+          for (int e = 0; e < VEC; ++e) {
+            const bool in = j0 + e < a.N;
+            r1[e] = in ? a.r1[row * a.ld + j0 + e] : T(0);
+            r2[e] = in ? a.r2[row * a.ld + j0 + e] : T(0);
+          }
+        }
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) {
+          const T xe = x.v[c][e];
+          T t = mul_rn(a.w, v.v[c][e]);
+          t = add_rn(t, mul_rn(mul_rn(a.c1, r1[e]), sub_rn(pb.v[c][e], xe)));
+          t = add_rn(t, mul_rn(mul_rn(a.c2, r2[e]), sub_rn(gb.v[c][e], xe)));
+          v.v[c][e] = (j0 + e < a.N) ? t : T(0);
+        }
+      }
+    }
+
+    if (a.constraint == SP_CONS_SHRINK) {  // cpso/_constraints.py:22-55
+      T beta = Num<T>::inf();
+#pragma unroll
+      for (int c = 0; c < CH; ++c)
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) {
+          const int j = TL::col(c, l, e);
+          if (j < a.N) {
+            const T trial = add_rn(x.v[c][e], v.v[c][e]);
+            const T lo = a.lower[j], hi = a.upper[j];
+            if (trial < lo) beta = fmin(beta, div_rn(sub_rn(lo, x.v[c][e]), v.v[c][e]));
+            if (trial > hi) beta = fmin(beta, div_rn(sub_rn(hi, x.v[c][e]), v.v[c][e]));
+          }
+        }
+      beta = group_min<LPR>(beta);
+      if (beta != Num<T>::inf()) {
+#pragma unroll
+        for (int c = 0; c < CH; ++c)
+#pragma unroll
+          for (int e = 0; e < VEC; ++e) v.v[c][e] = mul_rn(v.v[c][e], beta);
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < CH; ++c)
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) x.v[c][e] = add_rn(x.v[c][e], v.v[c][e]);
+
+    if (live) {
+      x.store(a.X + row * a.ld, l, ld);
+      v.store(a.V + row * a.ld, l, ld);
+    }
+    if (a.propose_only) continue;  // SP_OBJ_HOST: caller evaluates X, then sp_select_sync(copy_when=1)
+
+    const T f = evaluate_tile<T, CH, LPR>(a.objective, x, l, a.N);
+    T best = a.pbestfit[row];
+    const bool win = f < best;
+    if (win) best = f;
+    if (live) {
+      if (win) x.store(a.pbest + row * a.ld, l, ld);
+      if (l == 0) {
+        a.pbestfit[row] = best;
+        a.pfit[row] = f;
+        if (better((double)best, row, mine.f, mine.row)) mine = Best{(double)best, row};
+      }
+    }
+  }
+  if (a.propose_only) return;
+  Best top;
+  if (grid_best(mine, a.scratch, a.ctrl, &top))
+    finalize_generation<T>(top, a.pbest, a.ld, a.N, a.gbest, a.ctrl, a.it, a.maxiter, a.xtol, a.ftol);
+}
+
+// ---- competitive restart, _cpso.py:405-426 ------------------------------------
+// (1) max_i |X_i - gbest|^2 -> ctrl->aux[0] (bit pattern, atomicMax on non-negative doubles)
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+radius_kernel(const T* __restrict__ X, const T* __restrict__ gbest, int64_t P, int N, int64_t ld, sp_ctrl* ctrl) {
+  if (!running(ctrl)) return;
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * (kThreads / 32);
+  double worst = 0.0;
+  for (int64_t row = warp; row < P; row += nwarps) {
+    double acc = 0.0;
+    for (int j = lane; j < N; j += 32) {
+      double d = (double)(T)(X[row * ld + j] - gbest[j]);
+      acc += d * d;
+    }
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    worst = fmax(worst, acc);
+  }
+  __shared__ double s_w[kThreads / 32];
+  if (lane == 0) s_w[threadIdx.x >> 5] = worst;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < kThreads / 32; ++w) worst = fmax(worst, s_w[w]);
+    atomicMax(reinterpret_cast<unsigned long long*>(&ctrl->aux[0]), (unsigned long long)__double_as_longlong(worst));
+  }
+}
+
+// (2) decision: radius < delta -> nw rows to reset (ctrl->flag), ctrl->aux[1] = radius
+__global__ void restart_plan_kernel(sp_ctrl* ctrl, int64_t P, int N, int it, int maxiter, double gamma, double delta) {
+  if (!running(ctrl)) {
+    ctrl->flag = 0;
+    return;
+  }
+  const double radius = sqrt(ctrl->aux[0]) / sqrt(4.0 * (double)N);
+  int nw = 0;
+  if (radius < delta) {
+    const double inorm = (double)it / (double)maxiter;
+    nw = (int)(((double)P - 1.0) / (1.0 + exp(1.0 / 0.09 * (inorm - gamma + 0.5))));
+    if (nw < 0) nw = 0;
+  }
+  ctrl->flag = nw;
+  ctrl->aux[1] = radius;
+  ctrl->aux[0] = 0.0;
+}
+
+// (3) ascending stable rank of pbestfit (only when a restart fires)
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+rank_kernel(const T* __restrict__ fit, int64_t P, int32_t* __restrict__ rank, const sp_ctrl* ctrl) {
+  if (ctrl != nullptr && ctrl->flag <= 0) return;
+  __shared__ T s_f[kThreads];
+  const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  const T mine = i < P ? fit[i] : T(0);
+  int r = 0;
+  for (int64_t base = 0; base < P; base += kThreads) {
+    const int64_t j = base + threadIdx.x;
+    s_f[threadIdx.x] = j < P ? fit[j] : Num<T>::inf();
+    __syncthreads();
+    const int lim = (int)((P - base) < kThreads ? (P - base) : kThreads);
+#pragma unroll 8
+    for (int t = 0; t < lim; ++t) {
+      const T o = s_f[t];
+      r += (o < mine) || (o == mine && base + t < i);
+    }
+    __syncthreads();
+  }
+  if (i < P) rank[i] = r;
+}
+
+// (4) reset the nw worst: V = 0, X = U(lower, upper), pbest = X, pbestfit = 1e30
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+restart_apply_kernel(T* X, T* V, T* pbest, T* pbestfit, const int32_t* __restrict__ rank, const T* __restrict__ lower,
+                     const T* __restrict__ upper, int64_t P, int N, int64_t ld, int it, uint64_t seed,
+                     const T* __restrict__ fresh, const sp_ctrl* ctrl) {
+  constexpr int VEC = Num<T>::VEC;
+  const int nw = ctrl->flag;
+  if (nw <= 0) return;
+  const int64_t total = P * (int64_t)N;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = t / N;
+    const int j = (int)(t - i * N);
+    const int64_t r = rank[i];
+    if (r < P - nw) continue;
+    T val;
+    if (fresh != nullptr) {
+      val = fresh[(P - 1 - r) * ld + j];  // reset order: worst first (argsort()[:-nw-1:-1])
+    } else {
+      T blk[VEC];
+      uniform_block(philox4x32((uint32_t)(j / VEC), (uint32_t)i, (uint32_t)it, kPsoRestart, seed), blk);
+      val = add_rn(lower[j], mul_rn(sub_rn(upper[j], lower[j]), blk[j % VEC]));
+    }
+    X[i * ld + j] = val;
+    pbest[i * ld + j] = val;
+    V[i * ld + j] = T(0);
+    if (j == 0) pbestfit[i] = T(1.0e30);
+  }
+}
+
+template <typename T>
+static int pso_launch(const sp_pso_state* st, int it, int propose_only, cudaStream_t s) {
+  Shape sh;
+  if (!pick_shape(st->N, Num<T>::VEC, &sh)) {
+    set_error("sp_pso_generation: ndim %d exceeds the compiled row shapes", st->N);
+    return SP_ERR_SHAPE;
+  }
+  PsoArgs<T> a;
+  a.objective = st->objective;
+  a.constraint = st->constraint;
+  a.it = it;
+  a.maxiter = st->maxiter;
+  a.N = st->N;
+  a.propose_only = propose_only;
+  a.P = st->P;
+  a.ld = st->ld;
+  a.w = (T)st->w;
+  a.c1 = (T)st->c1;
+  a.c2 = (T)st->c2;
+  a.xtol = st->xtol;
+  a.ftol = st->ftol;
+  a.seed = st->seed;
+  a.X = (T*)st->X;
+  a.V = (T*)st->V;
+  a.pbest = (T*)st->pbest;
+  a.pbestfit = (T*)st->pbestfit;
+  a.pfit = (T*)st->pfit;
+  a.gbest = (T*)st->gbest;
+  a.lower = (const T*)st->lower;
+  a.upper = (const T*)st->upper;
+  a.ctrl = st->ctrl;
+  a.scratch = (Best*)st->scratch;
+  a.r1 = (const T*)st->r1;
+  a.r2 = (const T*)st->r2;
+  const bool philox = st->r1 == nullptr;
+  const int grid = grid_for_rows(st->P, sh.lpr, sh.ch >= 4 ? 2 : 4);
+#define SP_CALL(TT, C, L)                                                         \
+  do {                                                                            \
+    if (philox) pso_generation_kernel<TT, C, L, true><<<grid, kThreads, 0, s>>>(a); \
+    else pso_generation_kernel<TT, C, L, false><<<grid, kThreads, 0, s>>>(a);     \
+  } while (0)
+  SP_DISPATCH_SHAPE(T, sh, SP_CALL);
+#undef SP_CALL
+  SP_CHECK_LAUNCH();
+  return SP_OK;
+}
+
+static int pso_check(const sp_pso_state* st, int it) {
+  SP_CHECK_ARG(st != nullptr, "null state");
+  SP_CHECK_ARG(st->dtype == SP_F32 || st->dtype == SP_F64, "dtype");
+  SP_CHECK_ARG(st->constraint == SP_CONS_NONE || st->constraint == SP_CONS_SHRINK, "constraint");
+  SP_CHECK_ARG(st->N >= 1 && st->P >= 2 && st->P < (1LL << 31), "popsize / ndim");
+  const int vec = st->dtype == SP_F32 ? 4 : 2;
+  SP_CHECK_ARG(st->ld >= st->N && st->ld % vec == 0, "ld must be a multiple of 16/sizeof(T)");
+  SP_CHECK_ARG(st->X && st->V && st->pbest && st->pbestfit && st->pfit && st->gbest && st->ctrl && st->scratch,
+               "null buffer");
+  SP_CHECK_ARG(st->constraint == SP_CONS_NONE || (st->lower && st->upper), "bounds needed for Shrink");
+  SP_CHECK_ARG((st->r1 == nullptr) == (st->r2 == nullptr), "r1 and r2 must come together");
+  SP_CHECK_ARG(it >= 2, "generation index starts at 2 (_cpso.py:256-258)");
+  return SP_OK;
+}
+
+template <typename T>
+static int restart_plan_launch(const sp_pso_state* st, int it, int32_t* rank, cudaStream_t s) {
+  const int grid = grid_for_rows(st->P, 32, 8);
+  radius_kernel<T><<<grid, kThreads, 0, s>>>((const T*)st->X, (const T*)st->gbest, st->P, st->N, st->ld, st->ctrl);
+  SP_CHECK_LAUNCH();
+  restart_plan_kernel<<<1, 1, 0, s>>>(st->ctrl, st->P, st->N, it, st->maxiter, st->gamma, st->delta);
+  SP_CHECK_LAUNCH();
+  rank_kernel<T><<<(int)((st->P + kThreads - 1) / kThreads), kThreads, 0, s>>>((const T*)st->pbestfit, st->P, rank,
+                                                                                st->ctrl);
+  SP_CHECK_LAUNCH();
+  return SP_OK;
+}
+
+template <typename T>
+static int restart_apply_launch(const sp_pso_state* st, int it, const int32_t* rank, const void* fresh,
+                                cudaStream_t s) {
+  int64_t total = st->P * (int64_t)st->N;
+  int64_t need = (total + 255) / 256, cap = (int64_t)sm_count() * 8;
+  restart_apply_kernel<T><<<(int)(need < cap ? need : cap), 256, 0, s>>>(
+      (T*)st->X, (T*)st->V, (T*)st->pbest, (T*)st->pbestfit, rank, (const T*)st->lower, (const T*)st->upper, st->P,
+      st->N, st->ld, it, st->seed, (const T*)fresh, st->ctrl);
+  SP_CHECK_LAUNCH();
+  return SP_OK;
+}
+
+}  // namespace sp
+
+using namespace sp;
+
+extern "C" {
+
+int sp_pso_generation(const sp_pso_state* st, int it, void* stream) {
+  int rc = pso_check(st, it);
+  if (rc) return rc;
+  SP_CHECK_ARG(st->objective >= SP_OBJ_ACKLEY && st->objective <= SP_OBJ_STYBLINSKI_TANG,
+               "device objective required (use sp_pso_propose + sp_select_sync for host objectives)");
+  return st->dtype == SP_F32 ? pso_launch<float>(st, it, 0, (cudaStream_t)stream)
+                             : pso_launch<double>(st, it, 0, (cudaStream_t)stream);
+}
+
+int sp_pso_propose(const sp_pso_state* st, int it, void* stream) {
+  int rc = pso_check(st, it);
+  if (rc) return rc;
+  return st->dtype == SP_F32 ? pso_launch<float>(st, it, 1, (cudaStream_t)stream)
+                             : pso_launch<double>(st, it, 1, (cudaStream_t)stream);
+}
+
+int sp_cpso_restart_plan(const sp_pso_state* st, int it, int32_t* rank, void* stream) {
+  int rc = pso_check(st, it);
+  if (rc) return rc;
+  SP_CHECK_ARG(rank != nullptr && st->lower && st->upper && st->gamma >= 0.0, "rank scratch, bounds, competitivity");
+  return st->dtype == SP_F32 ? restart_plan_launch<float>(st, it, rank, (cudaStream_t)stream)
+                             : restart_plan_launch<double>(st, it, rank, (cudaStream_t)stream);
+}
+
+int sp_cpso_restart_apply(const sp_pso_state* st, int it, const int32_t* rank, const void* fresh, void* stream) {
+  int rc = pso_check(st, it);
+  if (rc) return rc;
+  SP_CHECK_ARG(rank != nullptr && st->lower && st->upper, "rank scratch and bounds");
+  return st->dtype == SP_F32 ? restart_apply_launch<float>(st, it, rank, fresh, (cudaStream_t)stream)
+                             : restart_apply_launch<double>(st, it, rank, fresh, (cudaStream_t)stream);
+}
+
+int sp_cpso_restart(const sp_pso_state* st, int it, int32_t* rank, void* stream) {
+  int rc = sp_cpso_restart_plan(st, it, rank, stream);
+  if (rc) return rc;
+  return sp_cpso_restart_apply(st, it, rank, nullptr, stream);
+}
+
+int sp_pso_run(const sp_pso_state* st, int it_first, int n, int32_t* rank, void* stream) {
+  SP_CHECK_ARG(st != nullptr && st->r1 == nullptr, "sp_pso_run needs in-kernel draws");
+  for (int g = 0; g < n; ++g) {
+    int rc = sp_pso_generation(st, it_first + g, stream);
+    if (rc) return rc;
+    if (st->gamma >= 0.0) {
+      rc = sp_cpso_restart(st, it_first + g, rank, stream);
+      if (rc) return rc;
+    }
+  }
+  return SP_OK;
+}
+
+}  // extern "C"

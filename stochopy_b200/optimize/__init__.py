@@ -1,0 +1,7 @@
+"""stochopy.optimize-compatible surface (stochopy/optimize/__init__.py:1-18)."""
+from ._helpers import OptimizeResult, minimize, register
+from ._cpso import minimize as cpso
+from ._de import minimize as de
+from ._pso import minimize as pso
+
+__all__ = ["OptimizeResult", "minimize", "register", "cpso", "de", "pso"]

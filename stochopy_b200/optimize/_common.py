@@ -1,0 +1,218 @@
+"""Host-side plumbing shared by the method front-ends.
+
+Mirrors the role of the reference's ``@optimizer`` decorator
+(stochopy/optimize/_common.py:27-106): it turns the per-individual ``fun(x)``
+contract into a population evaluation -- here either a device kernel (when
+``fun`` is one of the factory objectives) or a device->host->device round trip
+that calls the user's Python callable row by row (the exact reference contract).
+PyTorch is used for device buffers and streams only.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import torch
+
+from .. import _lib as L
+
+# stochopy/optimize/_common.py:12-24
+messages = {
+    -8: "TolX",
+    -7: "TolFun",
+    -6: "TolXUp",
+    -5: "EqualFunValues",
+    -4: "ConditionCov",
+    -3: "NoEffectCoord",
+    -2: "NoEffectAxis",
+    -1: "maximum number of iterations is reached",
+    0: "best solution changes less than xtol",
+    1: "best solution value is lower than ftol",
+}
+
+_TORCH_DT = {"float32": torch.float32, "float64": torch.float64}
+
+
+def resolve_dtype(dtype):
+    name = np.dtype(dtype).name
+    if name not in _TORCH_DT:
+        raise ValueError()
+    return np.dtype(name), _TORCH_DT[name], (L.SP_F32 if name == "float32" else L.SP_F64)
+
+
+def device_objective(fun, args):
+    """Objective id if ``fun`` is a factory objective (ours or the reference's), else None."""
+    if args:
+        return None
+    oid = getattr(fun, "_sp_objective", None)
+    if oid is not None:
+        return oid
+    mod = getattr(fun, "__module__", "") or ""
+    name = getattr(fun, "__name__", "")
+    if mod == "stochopy.factory.benchmark" and name in L.OBJECTIVES:
+        return L.OBJECTIVES[name]
+    return None
+
+
+def fresh_seed(seed):
+    if seed is None:
+        return int.from_bytes(os.urandom(8), "little")
+    return int(seed) & 0xFFFFFFFFFFFFFFFF
+
+
+class Engine:
+    """Device context of one optimiser run: device, dtype, stream, buffers."""
+
+    def __init__(self, dtype="float64", device=None):
+        L.load()
+        if not torch.cuda.is_available():
+            raise L.EngineError("stochopy_b200 needs a CUDA device (no CPU fallback)")
+        self.np_dt, self.t_dt, self.sp_dt = resolve_dtype(dtype)
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.vec = 16 // self.np_dt.itemsize
+        self._keep = []
+        self._ctrl_host = torch.empty(64, dtype=torch.uint8, pin_memory=True)
+
+    # -- buffers ----------------------------------------------------------------
+    def ld(self, n):
+        return (n + self.vec - 1) // self.vec * self.vec
+
+    def empty(self, *shape, dtype=None):
+        return torch.empty(shape, dtype=dtype or self.t_dt, device=self.device)
+
+    def zeros(self, *shape, dtype=None):
+        return torch.zeros(shape, dtype=dtype or self.t_dt, device=self.device)
+
+    def rows(self, p, n):
+        """Zero-filled (p, ld) row buffer."""
+        return self.zeros(p, self.ld(n))
+
+    def upload_rows(self, host, out=None):
+        """Host (p, n) array -> padded device rows (copy; the caller's array is never aliased)."""
+        host = np.ascontiguousarray(host, dtype=self.np_dt)
+        p, n = host.shape
+        out = self.rows(p, n) if out is None else out
+        out[:, :n].copy_(torch.from_numpy(host), non_blocking=False)
+        return out
+
+    def upload_vec(self, host, pad_to=None, dtype=None):
+        host = np.ascontiguousarray(host, dtype=dtype or self.np_dt)
+        n = host.shape[0]
+        out = torch.zeros(pad_to or n, dtype=torch.from_numpy(host).dtype, device=self.device)
+        out[:n].copy_(torch.from_numpy(host))
+        return out
+
+    def download_rows(self, dev, p, n):
+        return dev[:p, :n].to("cpu").numpy().astype(np.float64)
+
+    @property
+    def stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def sync(self):
+        torch.cuda.current_stream(self.device).synchronize()
+
+    # -- control block ------------------------------------------------------------
+    def new_ctrl(self):
+        host = L.Ctrl()
+        host.status = L.SP_RUNNING
+        raw = np.frombuffer(bytes(host), dtype=np.uint8).copy()
+        ctrl = torch.from_numpy(raw).to(self.device)
+        scratch = torch.zeros(int(L.load().sp_scratch_bytes()), dtype=torch.uint8, device=self.device)
+        return ctrl, scratch
+
+    def read_ctrl(self, ctrl):
+        """Device control block -> host mirror (one 64-byte D2H through pinned memory)."""
+        self._ctrl_host.copy_(ctrl, non_blocking=True)
+        self.sync()
+        return L.Ctrl.from_buffer_copy(self._ctrl_host.numpy().tobytes())
+
+    # -- population evaluation (the reference's `fun(X)` wrapper) -----------------------
+    def evaluate(self, fun, args, obj, X, p, n, out, scale=None, shift=None, to_user=None):
+        """out[:p] = fun(X[i]).  Device kernel for factory objectives; otherwise the
+        reference's per-individual Python contract via a host round trip."""
+        if obj is not None:
+            L.call("sp_eval", obj, self.sp_dt, X.data_ptr(), p, n, X.shape[1],
+                   None if scale is None else scale.data_ptr(), None if shift is None else shift.data_ptr(),
+                   out.data_ptr(), self.stream)
+            return
+        host = self.download_rows(X, p, n)
+        if to_user is not None:
+            host = to_user(host)
+        f = np.array([fun(row, *args) for row in host], dtype=np.float64)
+        out[:p].copy_(torch.from_numpy(f.astype(self.np_dt)))
+
+
+class NumpyStream:
+    """rng="numpy": draw from numpy's legacy MT19937 generator in the reference's
+    order so a fixed seed follows the reference's trajectory.
+    Host-side draws are uploaded; the kernels consume them instead of Philox."""
+
+    def __init__(self, seed):
+        self.rs = np.random.RandomState(seed)
+
+    def lhs(self, P, N):  # _common.py:111,113
+        jitter = self.rs.uniform(size=(P, N))
+        perm = np.stack([self.rs.permutation(P) for _ in range(N)], axis=0)  # (N, P)
+        return jitter, perm
+
+    def de(self, P, N, k, lower, upper, repair):  # _de.py:250, 306/311, 340; de/_constraints.py:24
+        r1 = self.rs.rand(P, N)
+        donors = np.empty((k, P), dtype=np.int64)
+        base = np.arange(P)
+        for i in range(P):
+            donors[:, i] = self.rs.permutation(np.delete(base, i))[:k]
+        irand = self.rs.randint(N, size=P).astype(np.int64)
+        rep = self.rs.uniform(lower, upper, (P, N)) if repair else None
+        return r1, donors, irand, rep
+
+    def pso(self, P, N):  # _cpso.py:262-263
+        return self.rs.rand(P, N), self.rs.rand(P, N)
+
+    def restart(self, nw, N, lower, upper):  # _cpso.py:422
+        return self.rs.uniform(lower, upper, (nw, N))
+
+    def mean0(self, N):  # _cmaes.py:180, _vdcma.py:181
+        return self.rs.uniform(-1.0, 1.0, N)
+
+    def normal(self, *shape):  # _cmaes.py:234, _vdcma.py:208,239,246
+        return self.rs.randn(*shape)
+
+
+class History:
+    """xall / funall of `return_all` (_de.py:221-234, 270-278)."""
+
+    def __init__(self, enabled, maxiter, P, N, verbosity):
+        self.enabled = bool(enabled)
+        if self.enabled:
+            self.nout = int(np.ceil(verbosity * P))
+            w = max(1, self.nout)
+            self.xall = np.empty((maxiter, w, N))
+            self.funall = np.empty((maxiter, w))
+
+    def put(self, it, X, pfit, gbest=None, gfit=None):
+        if not self.enabled:
+            return
+        if self.nout > 0:
+            self.xall[it - 1] = X[: self.nout]
+            self.funall[it - 1] = pfit[: self.nout]
+        elif gbest is not None:
+            self.xall[it - 1] = gbest
+            self.funall[it - 1] = gfit
+        else:
+            b = int(np.argmin(pfit))
+            self.xall[it - 1] = X[b]
+            self.funall[it - 1] = pfit[b]
+
+    def into(self, res, it):
+        if self.enabled:
+            res.update({"xall": self.xall[:it], "funall": self.funall[:it]})
+
+
+def validate_common(fun, bounds, callback):
+    """Checks shared by every front-end (same exception types as the reference)."""
+    if not hasattr(fun, "__call__"):
+        raise TypeError()
+    if np.ndim(bounds) != 2:
+        raise ValueError()
+    if callback is not None and not hasattr(callback, "__call__"):
+        raise ValueError()
