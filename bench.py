@@ -1,0 +1,342 @@
+#!/usr/bin/env python
+"""Headline benchmark: objective evaluations per second of the population hot path.
+
+Workload (BASELINE.json metric, SURVEY.md 8d "Headline"): differential evolution,
+strategy best1bin, Rosenbrock ndim=128, popsize=65536, fp32, bounds +-5.12,
+termination disabled (xtol=-1, ftol=-1e300).  One *step* = one generation = one
+launch of the fused DE kernel over the whole population (65536 evaluations).
+
+  value   device-resident throughput: K generations, each timed with CUDA events on
+          the launching stream, L2 flushed (256 MiB write) before every generation
+          so the population comes from HBM (the 2 x 32 MiB ping-pong state would
+          otherwise live in the 126 MB L2); `value_l2_resident` is the same loop
+          without the flush, i.e. what an actual run sees.
+  e2e     the same metric through the public API: minimize(fun, bounds, x0=<host
+          array>, method="de", options=...) -- host->device copy of x0, K
+          generations with device-side termination, device->host result.
+  roofline  the fused DE generation kernel against the measured HBM peak.
+  cpu_baseline  the oracle port of the reference algorithm on this box's host cores.
+
+N > 1 (torchrun): one independent seed per GPU (weak scaling), no data-path
+collective; barrier + max-over-ranks timing; value = total evals / s.
+
+--impl reference: the reference's CPU algorithm (oracle port; the reference is pure
+Python and cannot run DE at P=65536 -- its donor index matrix is O(P^2)) on a bounded
+population sample, rank 0 only.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "objective-evals/sec (popsize x iters / s), DE best1bin, Rosenbrock ndim=128"
+UNIT = "evals/s"
+P, N = 65536, 128
+BOUND = 5.12
+ALG_BYTES_PER_EVAL = (2 + 2) * N * 4 + 3 * 4  # (k+2) rows + 3 scalars, k=2 donors = 2060
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def traffic_from_profile():
+    """DRAM bytes per launch of the DE kernel from the committed ncu capture, if any."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
+            return float(json.load(f)["de_generation_kernel"]["dram_bytes_per_launch"])
+    except Exception:
+        return None
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc is not None:
+            time.sleep(0.25)
+            self.proc.terminate()
+            self.t.join(timeout=2)
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+                for n, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ---- reference arm / cpu baseline: the oracle port on host cores ---------------------
+def oracle_de_rate(p_sample, steps, warmup, seed=0):
+    """evals/s of the oracle's DE (reference algorithm, serial fun(x) loop) on a
+    population sample; steps timed after `warmup` generations via the callback."""
+    from oracle import de as ode
+    from oracle import objectives as oobj
+
+    rs = np.random.RandomState(seed)
+    x0 = rs.uniform(-BOUND, BOUND, (p_sample, N))
+    stamps = []
+    ode.minimize(oobj.rosenbrock, [[-BOUND, BOUND]] * N, x0=x0, maxiter=steps + warmup + 1, popsize=p_sample,
+                 mutation=0.5, recombination=0.9, strategy="best1bin", seed=seed, xtol=-1.0, ftol=-1.0e300,
+                 updating="deferred", callback=lambda X, s: stamps.append(time.perf_counter()))
+    # stamps[0] = initial population; stamps[i] = end of generation i+1
+    t = stamps[-1] - stamps[-1 - steps]
+    return p_sample * steps / t, t / steps
+
+
+def pick_sample(steps, warmup, budget_s):
+    """Largest population sample whose (steps+warmup) generations fit the time budget."""
+    rate, per = oracle_de_rate(256, 2, 1)
+    best = 256
+    for p in (512, 1024, 2048, 4096):
+        # reference cost per generation grows ~ p (evaluation) + p^2 (donor permutations)
+        est = per * (p / 256.0) * (1.0 + 0.35 * p / 1024.0)
+        if est * (steps + warmup + 1) <= budget_s:
+            best = p
+    return best
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    p_s = pick_sample(args.steps, args.warmup, 150.0)
+    rate, per = oracle_de_rate(p_s, args.steps, args.warmup)
+    sample = (f"oracle port of the reference DE (serial fun(x) loop, numpy MT19937 draws incl. its per-individual "
+              f"donor permutations); population sample {p_s} of {P} rows x {args.steps} generations "
+              f"(reference cannot allocate its (P-1)xP donor matrix at P={P})")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": per * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"DE best1bin, Rosenbrock ndim={N}, popsize={P} (sampled at {p_s}), bounds +-{BOUND}",
+                   "popsize": P, "ndim": N, "sample_popsize": p_s},
+        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample},
+        "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ---- our arm --------------------------------------------------------------------------
+def build_state(eng, L, x0, seed, maxiter):
+    import torch
+
+    ld = eng.ld(N)
+    X = [eng.rows(P, N), eng.rows(P, N)]
+    X[0][:, :N].copy_(torch.from_numpy(x0))
+    pbestfit, pfit, gbest = eng.empty(P), eng.empty(P), eng.zeros(ld)
+    lo = eng.upload_vec(np.full(N, -BOUND), ld)
+    hi = eng.upload_vec(np.full(N, BOUND), ld)
+    ctrl, scratch = eng.new_ctrl()
+    st = L.DeState()
+    st.dtype, st.objective, st.strategy, st.constraint = eng.sp_dt, L.OBJECTIVES["rosenbrock"], L.DE_STRATEGIES["best1bin"], 0
+    st.P, st.N, st.maxiter, st.ld = P, N, maxiter, ld
+    st.F, st.CR, st.xtol, st.ftol, st.seed = 0.5, 0.9, -1.0, -1.0e300, seed
+    st.X[0], st.X[1] = X[0].data_ptr(), X[1].data_ptr()
+    st.pbestfit, st.pfit, st.gbest = pbestfit.data_ptr(), pfit.data_ptr(), gbest.data_ptr()
+    st.lower, st.upper, st.ctrl, st.scratch = lo.data_ptr(), hi.data_ptr(), ctrl.data_ptr(), scratch.data_ptr()
+    L.call("sp_eval", st.objective, eng.sp_dt, X[0].data_ptr(), P, N, ld, None, None, pbestfit.data_ptr(), eng.stream)
+    pfit.copy_(pbestfit)
+    L.call("sp_best_init", eng.sp_dt, X[0].data_ptr(), pbestfit.data_ptr(), P, N, ld, gbest.data_ptr(), ctrl.data_ptr(),
+           scratch.data_ptr(), eng.stream)
+    keep = (X, pbestfit, pfit, gbest, lo, hi, ctrl, scratch)
+    return st, keep
+
+
+def our_arm(args):
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    import stochopy_b200 as sb
+    from stochopy_b200 import _lib as L
+    from stochopy_b200.optimize._common import Engine
+
+    eng = Engine("float32")
+    K, W = args.steps, args.warmup
+    seed = 1000 + rank  # one independent seed per GPU
+    rs = np.random.RandomState(seed)
+    x0 = rs.uniform(-BOUND, BOUND, (P, N)).astype(np.float32)
+    st, keep = build_state(eng, L, x0, seed, 2 * (K + W) + 10)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=eng.device)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device=eng.device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    it = 2
+    for _ in range(max(W, 3)):  # warm-up
+        flush.fill_(1)
+        L.call("sp_de_generation", C.byref(st), it, eng.stream)
+        it += 1
+
+    # (1) value: HBM-cold generations, one event pair per generation
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    barrier()
+    launches0 = L.launch_count()
+    with ClockSampler(local) as clocks:
+        wall0 = time.perf_counter()
+        for k in range(K):
+            flush.fill_(k & 1)
+            ev[k][0].record()
+            L.call("sp_de_generation", C.byref(st), it, eng.stream)
+            ev[k][1].record()
+            it += 1
+        barrier()
+        wall_cold = time.perf_counter() - wall0
+        launches = L.launch_count() - launches0
+        cold_ms = max_over_ranks(sum(a.elapsed_time(b) for a, b in ev))
+
+        # (2) the same loop as a real run sees it: no flush, state stays in L2
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        s.record()
+        L.call("sp_de_run", C.byref(st), it, K, eng.stream)
+        e.record()
+        barrier()
+        it += K
+        warm_ms = max_over_ranks(s.elapsed_time(e))
+
+        # (3) e2e through the public API with host buffers
+        x0_64 = x0.astype(np.float64)
+        opts = dict(maxiter=K + 1, popsize=P, mutation=0.5, recombination=0.9, strategy="best1bin", seed=seed,
+                    xtol=-1.0, ftol=-1.0e300, updating="deferred", dtype="float32")
+        sb.optimize.minimize(sb.factory.rosenbrock, [[-BOUND, BOUND]] * N, x0=x0, method="de",
+                             options=dict(opts, maxiter=max(W, 3) + 1))  # warm-up call
+        barrier()
+        t0 = time.perf_counter()
+        res = sb.optimize.minimize(sb.factory.rosenbrock, [[-BOUND, BOUND]] * N, x0=x0, method="de", options=opts)
+        torch.cuda.synchronize()
+        e2e_s = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([e2e_s], dtype=torch.float64, device=eng.device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e2e_s = float(t.item())
+    assert res.nit == K + 1 and res.status == -1, (res.nit, res.status)
+    c = eng.read_ctrl(keep[6])
+    assert c.status == L.SP_RUNNING and c.nit == it - 1, (c.status, c.nit, it)
+
+    # best over the independent seeds (the one exchange this sharding needs, outside the timed loop)
+    best_fun = float(res.fun)
+    if world > 1:
+        t = torch.tensor([best_fun], dtype=torch.float64, device=eng.device)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        best_fun = float(t.item())
+
+    if rank == 0:
+        peak, peak_src = peaks()
+        per_launch_s = cold_ms * 1e-3 / K
+        achieved = ALG_BYTES_PER_EVAL * P / per_launch_s / 1e9
+        value = world * P * K / (cold_ms * 1e-3)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": max(W, 3),
+            "ms_per_step": cold_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"DE best1bin, Rosenbrock ndim={N}, popsize={P} per GPU, fp32, bounds +-{BOUND}, "
+                                   "one independent seed per GPU, in-kernel Philox draws",
+                       "popsize": P, "ndim": N, "l2": "flushed (256 MiB write) before every timed generation",
+                       "timing": "CUDA events around each generation launch, summed; max over ranks",
+                       "best_fun_over_seeds": best_fun},
+            "value_l2_resident": world * P * K / (warm_ms * 1e-3),
+            "ms_per_step_l2_resident": warm_ms / K,
+            "wall_s_timed_loop": wall_cold,
+            "e2e": {"value": world * P * K / e2e_s, "unit": UNIT, "h2d_bytes_per_step": x0.nbytes / K,
+                    "d2h_bytes_per_step": (N * 4 + 64 * (K // 64 + 2)) / K, "seconds": e2e_s,
+                    "call": "stochopy_b200.optimize.minimize(rosenbrock, bounds, x0=<host fp32 array>, method='de')"},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic_from_profile(), "kernel": "de_generation_kernel<float,1,32,true>",
+                         "algorithmic_bytes_per_launch": ALG_BYTES_PER_EVAL * P, "peak_source": peak_src,
+                         "launch_us": per_launch_s * 1e6},
+            "clocks": clocks.summary(),
+        }
+        if world == 1 and not args.no_cpu:
+            p_s, gens = 4096, 24
+            t0 = time.perf_counter()
+            rate, per = oracle_de_rate(p_s, gens, 1)
+            line["cpu_baseline"] = {
+                "value": rate, "unit": UNIT, "cores": 1, "kind": "port",
+                "sample": f"oracle port of the reference DE on {p_s} of {P} rows x {gens} generations "
+                          f"({time.perf_counter() - t0:.1f} s); the reference's serial mode is its fastest (SURVEY.md 6)",
+                "host_cpus": os.cpu_count()}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=1000)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return reference_arm(args)
+    return our_arm(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

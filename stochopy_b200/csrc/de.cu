@@ -10,70 +10,14 @@
 //   write row of the next population, track argmin(pbestfit)
 // The last CTA refreshes gbest and evaluates the termination ladder.
 // Algorithmic HBM bytes per individual: (k + 2) * N * s + 3 * s.
-#include "objectives.cuh"
-#include "philox.cuh"
+#include <cstdlib>
+
+#include "de_common.cuh"
 
 namespace sp {
 
-template <typename T>
-struct DeArgs {
-  int objective, strategy, constraint, it, maxiter, N, propose_only;
-  int64_t P, ld;
-  T F, CR;
-  double xtol, ftol;
-  uint64_t seed;
-  const T* Xold;
-  T* Xnew;
-  T* pbestfit;
-  T* pfit;
-  T* gbest;
-  const T* lower;
-  const T* upper;
-  sp_ctrl* ctrl;
-  Best* scratch;
-  const T* r1;
-  const int64_t* donors;
-  const int64_t* irand;
-  const T* repair;
-};
-
-__host__ __device__ constexpr int de_donor_count(int strategy) {
-  return strategy == SP_DE_RAND1BIN ? 3 : strategy == SP_DE_RAND2BIN ? 5 : strategy == SP_DE_BEST1BIN ? 2 : 4;
-}
-
-// k distinct donors != row: draw from the shrinking range and step over the
-// excluded indices in ascending order (uniform over what is left; equals in
-// distribution the first k entries of the reference's permutation, _de.py:306).
-__device__ __forceinline__ void draw_donors(uint32_t row, uint32_t P, int k, int it, uint64_t seed, int N,
-                                            int64_t (&d)[5], int* irand) {
-  uint4 a = philox4x32(0u, row, (uint32_t)it, kDeIndex, seed);
-  uint32_t words[5] = {a.y, a.z, a.w, 0u, 0u};
-  if (k > 3) {
-    uint4 b = philox4x32(1u, row, (uint32_t)it, kDeIndex, seed);
-    words[3] = b.x;
-    words[4] = b.y;
-  }
-  *irand = (int)bounded(a.x, (uint32_t)N);
-  uint32_t excl[6] = {row, 0u, 0u, 0u, 0u, 0u};  // ascending; t + 1 entries valid at step t
-#pragma unroll
-  for (int t = 0; t < 5; ++t) {
-    if (t < k) {
-      uint32_t r = bounded(words[t], P - 1u - (uint32_t)t);
-#pragma unroll
-      for (int e = 0; e <= t; ++e)
-        if (r >= excl[e]) ++r;
-      d[t] = r;
-      excl[t + 1] = r;  // one backward bubble pass restores the order
-#pragma unroll
-      for (int e = t + 1; e > 0; --e)
-        if (excl[e - 1] > excl[e]) {
-          uint32_t tmp = excl[e - 1];
-          excl[e - 1] = excl[e];
-          excl[e] = tmp;
-        }
-    }
-  }
-}
+// test hook: SP_DE_DIRECT=1 keeps the direct-load kernel for every shape
+static const bool g_force_direct = getenv("SP_DE_DIRECT") != nullptr;
 
 template <typename T, int CH, int LPR, bool PHILOX>
 __global__ void __launch_bounds__(kThreads)
@@ -98,7 +42,7 @@ de_generation_kernel(const DeArgs<T> a) {
     const bool live = row < a.P;
     if (!live) row = a.P - 1;
 
-    int64_t d[5] = {0, 0, 0, 0, 0};
+    uint32_t d[5] = {0, 0, 0, 0, 0};
     int irand;
     if (PHILOX) {
       draw_donors((uint32_t)row, (uint32_t)a.P, k, a.it, a.seed, a.N, d, &irand);
@@ -106,15 +50,15 @@ de_generation_kernel(const DeArgs<T> a) {
       irand = (int)a.irand[row];
 #pragma unroll
       for (int t = 0; t < 5; ++t)
-        if (t < k) d[t] = a.donors[(int64_t)t * a.P + row];
+        if (t < k) d[t] = (uint32_t)a.donors[(int64_t)t * a.P + row];
     }
 
     TL xi, u;
     xi.load(a.Xold + row * a.ld, l, ld);
     {  // mutant, de/_strategy.py:1-38 (numpy's operation order, no FMA contraction)
       TL d0, d1;
-      d0.load(a.Xold + d[0] * a.ld, l, ld);
-      d1.load(a.Xold + d[1] * a.ld, l, ld);
+      d0.load(a.Xold + (int64_t)d[0] * a.ld, l, ld);
+      d1.load(a.Xold + (int64_t)d[1] * a.ld, l, ld);
       if (a.strategy == SP_DE_BEST1BIN) {
 #pragma unroll
         for (int c = 0; c < CH; ++c)
@@ -122,7 +66,7 @@ de_generation_kernel(const DeArgs<T> a) {
           for (int e = 0; e < VEC; ++e) u.v[c][e] = add_rn(gb.v[c][e], mul_rn(a.F, sub_rn(d0.v[c][e], d1.v[c][e])));
       } else {
         TL d2;
-        d2.load(a.Xold + d[2] * a.ld, l, ld);
+        d2.load(a.Xold + (int64_t)d[2] * a.ld, l, ld);
         if (a.strategy == SP_DE_RAND1BIN) {
 #pragma unroll
           for (int c = 0; c < CH; ++c)
@@ -130,7 +74,7 @@ de_generation_kernel(const DeArgs<T> a) {
             for (int e = 0; e < VEC; ++e) u.v[c][e] = add_rn(d0.v[c][e], mul_rn(a.F, sub_rn(d1.v[c][e], d2.v[c][e])));
         } else {
           TL d3;
-          d3.load(a.Xold + d[3] * a.ld, l, ld);
+          d3.load(a.Xold + (int64_t)d[3] * a.ld, l, ld);
           if (a.strategy == SP_DE_BEST2BIN) {
 #pragma unroll
             for (int c = 0; c < CH; ++c)
@@ -141,7 +85,7 @@ de_generation_kernel(const DeArgs<T> a) {
                     mul_rn(a.F, sub_rn(sub_rn(add_rn(d0.v[c][e], d1.v[c][e]), d2.v[c][e]), d3.v[c][e])));
           } else {  // rand2bin
             TL d4;
-            d4.load(a.Xold + d[4] * a.ld, l, ld);
+            d4.load(a.Xold + (int64_t)d[4] * a.ld, l, ld);
 #pragma unroll
             for (int c = 0; c < CH; ++c)
 #pragma unroll
@@ -222,6 +166,7 @@ de_generation_kernel(const DeArgs<T> a) {
     finalize_generation<T>(top, a.Xnew, a.ld, a.N, a.gbest, a.ctrl, a.it, a.maxiter, a.xtol, a.ftol);
 }
 
+
 template <typename T>
 static int de_launch(const sp_de_state* st, int it, int propose_only, cudaStream_t s) {
   Shape sh;
@@ -258,6 +203,17 @@ static int de_launch(const sp_de_state* st, int it, int propose_only, cudaStream
   a.irand = st->irand;
   a.repair = (const T*)st->repair;
   const bool philox = st->r1 == nullptr;
+  const int k = de_donor_count(st->strategy);
+  if (philox && sh.lpr == 32 && !g_force_direct && de_tma_fits(k, st->ld, sizeof(T))) {
+    a.cr_cut = crossover_cut<T>(st->CR);
+    cudaError_t e = de_tma_dispatch(a, sh.ch, s);
+    if (e != cudaSuccess) {
+      set_error("sp_de_generation: %s", cudaGetErrorString(e));
+      return SP_ERR_CUDA;
+    }
+    SP_CHECK_LAUNCH();
+    return SP_OK;
+  }
   const int grid = grid_for_rows(st->P, sh.lpr, sh.ch >= 4 ? 2 : 4);
 #define SP_CALL(TT, C, L)                                                        \
   do {                                                                           \

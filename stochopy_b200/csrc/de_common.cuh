@@ -1,0 +1,97 @@
+// Shared pieces of the DE kernels (direct-load and TMA-staged variants).
+#pragma once
+#include "objectives.cuh"
+#include "philox.cuh"
+
+namespace sp {
+
+template <typename T>
+struct DeArgs {
+  int objective, strategy, constraint, it, maxiter, N, propose_only;
+  int64_t P, ld;
+  T F, CR;
+  double xtol, ftol;
+  uint64_t seed;
+  const T* Xold;
+  T* Xnew;
+  T* pbestfit;
+  T* pfit;
+  T* gbest;
+  const T* lower;
+  const T* upper;
+  sp_ctrl* ctrl;
+  Best* scratch;
+  const T* r1;
+  const int64_t* donors;
+  const int64_t* irand;
+  const T* repair;
+  uint64_t cr_cut;  // integer form of `r <= CR` for the Philox words (crossover_cut)
+};
+
+__host__ __device__ constexpr int de_donor_count(int strategy) {
+  return strategy == SP_DE_RAND1BIN ? 3 : strategy == SP_DE_RAND2BIN ? 5 : strategy == SP_DE_BEST1BIN ? 2 : 4;
+}
+
+// k distinct donors != row: draw from the shrinking range and step over the
+// excluded indices in ascending order (uniform over what is left; equals in
+// distribution the first k entries of the reference's permutation, _de.py:306).
+__device__ __forceinline__ void draw_donors(uint32_t row, uint32_t P, int k, int it, uint64_t seed, int N,
+                                            uint32_t (&d)[5], int* irand) {
+  uint4 a = philox4x32(0u, row, (uint32_t)it, kDeIndex, seed);
+  uint32_t words[5] = {a.y, a.z, a.w, 0u, 0u};
+  if (k > 3) {
+    uint4 b = philox4x32(1u, row, (uint32_t)it, kDeIndex, seed);
+    words[3] = b.x;
+    words[4] = b.y;
+  }
+  *irand = (int)bounded(a.x, (uint32_t)N);
+  uint32_t excl[6] = {row, 0u, 0u, 0u, 0u, 0u};  // ascending; t + 1 entries valid at step t
+#pragma unroll
+  for (int t = 0; t < 5; ++t) {
+    if (t < k) {
+      uint32_t r = bounded(words[t], P - 1u - (uint32_t)t);
+#pragma unroll
+      for (int e = 0; e <= t; ++e)
+        if (r >= excl[e]) ++r;
+      d[t] = r;
+      excl[t + 1] = r;  // one backward bubble pass restores the order
+#pragma unroll
+      for (int e = t + 1; e > 0; --e)
+        if (excl[e - 1] > excl[e]) {
+          uint32_t tmp = excl[e - 1];
+          excl[e - 1] = excl[e];
+          excl[e] = tmp;
+        }
+    }
+  }
+}
+
+
+// `u <= CR` on the raw Philox words, bit-identical to comparing the converted
+// uniform: fp32 u = (w >> 8) * 2^-24  ->  w <= cut32;  fp64 u = m53 * 2^-53 -> m53 <= cut53.
+template <typename T>
+inline uint64_t crossover_cut(double CR);
+template <>
+inline uint64_t crossover_cut<float>(double CR) {
+  const double t = (double)(float)CR * 16777216.0;
+  if (t < 0.0) return 0;  // unreachable (CR is validated to [0,1]); word 0 still passes like u = 0 <= CR
+  const uint64_t thr = (uint64_t)t;
+  return thr >= (1ull << 24) ? 0xFFFFFFFFull : ((thr << 8) | 0xFFull);
+}
+template <>
+inline uint64_t crossover_cut<double>(double CR) {
+  const double t = CR * 9007199254740992.0;
+  return t < 0.0 ? 0 : (uint64_t)t;
+}
+
+// TMA-staged kernel (de_tma.cuh), one translation unit per (dtype, strategy)
+constexpr int kTmaWarps = 4;
+constexpr int kTmaStages = 4;
+inline size_t de_tma_smem(int k, int64_t ld, size_t elem) {
+  return 128 + (size_t)kTmaWarps * kTmaStages * (k + 1) * ld * elem;
+}
+inline bool de_tma_fits(int k, int64_t ld, size_t elem) { return de_tma_smem(k, ld, elem) <= 160 * 1024; }
+cudaError_t de_tma_dispatch(const DeArgs<float>& a, int ch, cudaStream_t s);
+cudaError_t de_tma_dispatch(const DeArgs<double>& a, int ch, cudaStream_t s);
+
+}  // namespace sp

@@ -1,0 +1,7 @@
+// DE TMA kernel instantiations: dtype double, strategy 0 (one unit per pair so the build parallelises)
+#include <cstdlib>
+
+#include "de_tma.cuh"
+namespace sp {
+cudaError_t de_tma_double_s0(const DeArgs<double>& a, int ch, cudaStream_t s) { return de_tma_by_ch<double, 0>(a, ch, s); }
+}  // namespace sp

@@ -63,9 +63,8 @@ __device__ __forceinline__ T evaluate_tile(int objective, const Tile<T, CH, LPR>
             s2 += b * b;
           }
         }
-      s1 = group_sum<LPR>(s1);
-      s2 = group_sum<LPR>(s2);
-      return T(100) * s1 + s2;
+      // one butterfly for both sums: sum_l (100 s1_l + s2_l) == 100 sum s1 + sum s2
+      return group_sum<LPR>(T(100) * s1 + s2);
     }
     case SP_OBJ_RASTRIGIN: {  // benchmark.py:79-97
       T s = 0;

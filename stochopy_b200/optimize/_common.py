@@ -30,6 +30,7 @@ messages = {
 }
 
 _TORCH_DT = {"float32": torch.float32, "float64": torch.float64}
+_PINNED = {}  # one pinned 64-byte landing pad for the control block per device
 
 
 def resolve_dtype(dtype):
@@ -69,8 +70,10 @@ class Engine:
         self.np_dt, self.t_dt, self.sp_dt = resolve_dtype(dtype)
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.vec = 16 // self.np_dt.itemsize
-        self._keep = []
-        self._ctrl_host = torch.empty(64, dtype=torch.uint8, pin_memory=True)
+        key = (self.device.type, self.device.index)
+        if key not in _PINNED:
+            _PINNED[key] = torch.empty(64, dtype=torch.uint8, pin_memory=True)
+        self._ctrl_host = _PINNED[key]
 
     # -- buffers ----------------------------------------------------------------
     def ld(self, n):
@@ -87,11 +90,15 @@ class Engine:
         return self.zeros(p, self.ld(n))
 
     def upload_rows(self, host, out=None):
-        """Host (p, n) array -> padded device rows (copy; the caller's array is never aliased)."""
-        host = np.ascontiguousarray(host, dtype=self.np_dt)
+        """Host (p, n) array -> padded device rows (copy; the caller's array is never
+        aliased).  fp32/fp64 sources travel as they are and are cast on the device."""
+        host = np.asarray(host)
+        if host.dtype not in (np.float32, np.float64):
+            host = host.astype(np.float64)
+        host = np.ascontiguousarray(host)
         p, n = host.shape
         out = self.rows(p, n) if out is None else out
-        out[:, :n].copy_(torch.from_numpy(host), non_blocking=False)
+        out[:, :n].copy_(torch.from_numpy(host).to(self.device))
         return out
 
     def upload_vec(self, host, pad_to=None, dtype=None):

@@ -102,7 +102,7 @@ def minimize(
     st.ctrl, st.scratch = ctrl.data_ptr(), scratch.data_ptr()
 
     if x0 is not None:
-        eng.upload_rows(np.asarray(x0, dtype=np.float64), out=X)
+        eng.upload_rows(x0, out=X)
     elif stream is not None:
         jitter, perm = stream.lhs(P, N)
         d_j, d_p = eng.upload_rows(jitter), torch.from_numpy(perm).to(eng.device)

@@ -96,7 +96,7 @@ def minimize(
 
     # initial population: x0 (copied, the caller's array is not aliased) or LHS, _de.py:208
     if x0 is not None:
-        eng.upload_rows(np.asarray(x0, dtype=np.float64), out=X[0])
+        eng.upload_rows(x0, out=X[0])
     elif stream is not None:
         jitter, perm = stream.lhs(P, N)
         d_j, d_p = eng.upload_rows(jitter), torch.from_numpy(perm).to(eng.device)

@@ -309,9 +309,9 @@ def test_cpso_restart_philox_and_wide_swarm():
     fresh = PhiloxStream(42).pso_restart(20, hit, N, lower, upper)
     assert np.array_equal(out["X"][hit], fresh) and np.array_equal(out["pbest"][hit], fresh)
     assert np.all(out["V"][hit] == 0) and np.array_equal(np.delete(out["X"], hit, 0), np.delete(X, hit, 0))
-    # a wide swarm must not restart
+    # a wide swarm must not restart (long run -> small threshold, _cpso.py:216)
     rig2 = PsoRig(rs.uniform(-5, 5, (P, N)), X, X, pbestfit, gbest, "sphere", None, 0.7, 1.5, 1.5, lower, upper,
-                  maxiter=100, gamma=1.2, delta=delta)
+                  maxiter=100000, gamma=1.2, delta=opso.swarm_delta(P, 100000))
     assert rig2.restart(20) == 0
 
 
