@@ -174,6 +174,91 @@ int sp_cpso_restart(const sp_pso_state* st, int it, int32_t* d_rank, void* strea
 /* enqueue generations it_first .. it_first+n-1 (+ restart when gamma >= 0) */
 int sp_pso_run(const sp_pso_state* st, int it_first, int n, int32_t* d_rank, void* stream);
 
+
+/* ---- counter-based draws as a buffer: out[row][j] = U[0,1) (normal = 0) or N(0,1)
+ * (normal = 1) of Philox counter (j / (16/sizeof(T)), row, it, purpose); the same
+ * streams the generation kernels consume in place (csrc/philox.cuh). */
+int sp_random_fill(int dtype, void* d_out, int64_t P, int N, int64_t ld, int it, int purpose, uint64_t seed,
+                   int normal, void* stream);
+
+/* ---- fitness ranking (np.argsort(arfitness), _cmaes.py:272 / _vdcma.py:290) ----
+ * d_rank[i] = number of individuals that sort before i (ascending, ties by
+ * index = a stable argsort); O(P^2) counting, P <= 2^31. */
+int sp_fitness_rank(int dtype, const void* d_fit, int64_t P, int32_t* d_rank, void* stream);
+
+/* ---- dense symmetric eigendecomposition (np.linalg.eigh, _cmaes.py:304) -------
+ * d_C (N x N, ld = N) is symmetrised from its upper triangle in place
+ * (_cmaes.py:303); eigenvalues ascending into d_w (N), eigenvectors into the
+ * columns of d_B (N x N).  Cyclic one-sided Jacobi on the device; every
+ * eigenvector is normalised so that its largest-magnitude component is positive
+ * (LAPACK's sign is implementation defined).  d_work: 2*N*N scalars. */
+int sp_sym_eigh(int dtype, void* d_C, int N, void* d_w, void* d_B, void* d_work, void* stream);
+
+/* ---- a15-a17: (mu,lambda)-CMA-ES generation (stochopy/optimize/cmaes/_cmaes.py:228-343,
+ * converge :360-434, Penalize cmaes/_constraints.py:4-82).  Works in the space
+ * standardised to [-1,1]; the objective sees x * xscale + xshift. */
+typedef struct {
+  sp_ctrl base;          /* status / nit / gfit (best of the last generation) / gbest_row */
+  double sigma;          /* step size */
+  double sigma_gen;      /* sigma the current population was sampled with */
+  double ps_norm;
+  double vd_ps;          /* vdcma: scalar evolution path */
+  int64_t nfev;
+  int64_t eigeneval;
+  int32_t hsig;          /* cond of _cmaes.py:283 / _vdcma.py:303 */
+  int32_t do_eig;        /* eigendecomposition due this generation */
+  int32_t inject;        /* vdcma flg_injection */
+  int32_t validfitval;   /* Penalize state */
+  int32_t iniphase;
+  int32_t hist_len;      /* Penalize dfithist length */
+  int32_t sweeps;        /* Jacobi sweeps of the last decomposition */
+  int32_t pad_;
+  double aux[16];
+} sp_es_ctrl;
+
+typedef struct {
+  int32_t dtype, objective, constraint, N;
+  int64_t P, ld;
+  int32_t mu, maxiter, ilim, hist_cap;
+  double cc, cs, c1, cmu, damps, chind, mueff, xtol, ftol, insigma;
+  uint64_t seed;
+  void* xmean;     /* (N) */
+  void* xold;      /* (N) */
+  void* pc;        /* (N) */
+  void* ps;        /* (N) */
+  void* C;         /* (N x N) */
+  void* B;         /* (N x N) eigenvectors in columns */
+  void* D;         /* (N) sqrt of eigenvalues */
+  void* BD;        /* reserved (unused) */
+  void* invsqrtC;  /* (N x N) */
+  void* arx;       /* (P x ld) population (standardised, unclipped) */
+  void* arfit;     /* (P) fitness (penalised when constraint = Penalize) */
+  void* Z;         /* (P x ld) N(0,I) draws of the generation */
+  void* weights;   /* (mu) */
+  void* xscale;    /* (ld) 0.5 (upper - lower) */
+  void* xshift;    /* (ld) 0.5 (upper + lower) */
+  void* besthist;  /* (maxiter) arbestfitness, zero initialised */
+  void* work;      /* workspace, sp_cma_work_scalars(N, P) scalars */
+  int32_t* rank;   /* (P) */
+  void* bnd_weights; /* (N)      Penalize */
+  void* dfithist;    /* (hist_cap) Penalize */
+  sp_es_ctrl* ctrl;
+  void* scratch;
+  int32_t host_z;    /* 1: Z was filled by the caller (rng="numpy"), 0: Philox in-kernel */
+  int32_t host_eigh; /* 1: the caller decomposes C itself when ctrl->do_eig (compat mode) */
+} sp_cma_state;
+int64_t sp_cma_work_scalars(int N, int64_t P);
+/* one generation; with host_eigh the call stops after the covariance update when a
+ * decomposition is due and sp_cma_finish_generation must follow once B, D are uploaded */
+int sp_cma_generation(const sp_cma_state* st, int it, void* stream);
+/* the generation in two halves around an external evaluation (host objectives):
+ * sample = draws + sampling GEMM into arx; the caller fills arfit with fun(clip?(arx)
+ * * xscale + xshift); update = penalty, selection, paths, covariance, eigenbasis, status */
+int sp_cma_sample(const sp_cma_state* st, int it, void* stream);
+int sp_cma_update(const sp_cma_state* st, int it, void* stream);
+int sp_cma_finish_generation(const sp_cma_state* st, int it, void* stream);
+int sp_cma_run(const sp_cma_state* st, int it_first, int n, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

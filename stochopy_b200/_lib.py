@@ -25,6 +25,8 @@ SP_OBJ_HOST = 100
 DE_STRATEGIES = {"rand1bin": 0, "rand2bin": 1, "best1bin": 2, "best2bin": 3}
 DE_DONORS = {"rand1bin": 3, "rand2bin": 5, "best1bin": 2, "best2bin": 4}
 CONS_NONE, CONS_RANDOM, CONS_SHRINK, CONS_PENALIZE = 0, 1, 2, 3
+# Philox purpose tags (csrc/philox.cuh)
+PURPOSE_ES_MEAN0, PURPOSE_VD_V0 = 10, 11
 
 vp = C.c_void_p
 
@@ -69,6 +71,36 @@ class PsoState(C.Structure):
     ]
 
 
+class EsCtrl(C.Structure):
+    """sp_es_ctrl: control block of the evolution-strategy methods (cmaes, vdcma)."""
+
+    _fields_ = [
+        ("base", Ctrl),
+        ("sigma", C.c_double), ("sigma_gen", C.c_double), ("ps_norm", C.c_double), ("vd_ps", C.c_double),
+        ("nfev", C.c_int64), ("eigeneval", C.c_int64),
+        ("hsig", C.c_int32), ("do_eig", C.c_int32), ("inject", C.c_int32), ("validfitval", C.c_int32),
+        ("iniphase", C.c_int32), ("hist_len", C.c_int32), ("sweeps", C.c_int32), ("pad_", C.c_int32),
+        ("aux", C.c_double * 16),
+    ]
+
+
+class CmaState(C.Structure):
+    _fields_ = [
+        ("dtype", C.c_int32), ("objective", C.c_int32), ("constraint", C.c_int32), ("N", C.c_int32),
+        ("P", C.c_int64), ("ld", C.c_int64),
+        ("mu", C.c_int32), ("maxiter", C.c_int32), ("ilim", C.c_int32), ("hist_cap", C.c_int32),
+        ("cc", C.c_double), ("cs", C.c_double), ("c1", C.c_double), ("cmu", C.c_double), ("damps", C.c_double),
+        ("chind", C.c_double), ("mueff", C.c_double), ("xtol", C.c_double), ("ftol", C.c_double),
+        ("insigma", C.c_double),
+        ("seed", C.c_uint64),
+        ("xmean", vp), ("xold", vp), ("pc", vp), ("ps", vp), ("C", vp), ("B", vp), ("D", vp), ("BD", vp),
+        ("invsqrtC", vp), ("arx", vp), ("arfit", vp), ("Z", vp), ("weights", vp), ("xscale", vp), ("xshift", vp),
+        ("besthist", vp), ("work", vp), ("rank", vp), ("bnd_weights", vp), ("dfithist", vp), ("ctrl", vp),
+        ("scratch", vp),
+        ("host_z", C.c_int32), ("host_eigh", C.c_int32),
+    ]
+
+
 _i, _i64, _d, _u64 = C.c_int, C.c_int64, C.c_double, C.c_uint64
 
 # name -> (restype, argtypes); mirrors include/stochopy_b200.h one to one
@@ -91,6 +123,15 @@ SIGNATURES = {
     "sp_cpso_restart_apply": (_i, [C.POINTER(PsoState), _i, vp, vp, vp]),
     "sp_cpso_restart": (_i, [C.POINTER(PsoState), _i, vp, vp]),
     "sp_pso_run": (_i, [C.POINTER(PsoState), _i, _i, vp, vp]),
+    "sp_random_fill": (_i, [_i, vp, _i64, _i, _i64, _i, _i, _u64, _i, vp]),
+    "sp_fitness_rank": (_i, [_i, vp, _i64, vp, vp]),
+    "sp_sym_eigh": (_i, [_i, vp, _i, vp, vp, vp, vp]),
+    "sp_cma_work_scalars": (_i64, [_i, _i64]),
+    "sp_cma_generation": (_i, [C.POINTER(CmaState), _i, vp]),
+    "sp_cma_sample": (_i, [C.POINTER(CmaState), _i, vp]),
+    "sp_cma_update": (_i, [C.POINTER(CmaState), _i, vp]),
+    "sp_cma_finish_generation": (_i, [C.POINTER(CmaState), _i, vp]),
+    "sp_cma_run": (_i, [C.POINTER(CmaState), _i, _i, vp]),
 }
 
 _lib = None

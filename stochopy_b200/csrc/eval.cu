@@ -6,8 +6,8 @@
 #include <cstdarg>
 #include <cstring>
 
-#include "objectives.cuh"
-#include "philox.cuh"
+#include "linalg.cuh"
+#include "rows.cuh"
 
 namespace sp {
 
@@ -31,37 +31,6 @@ int sm_count() {
     cached[dev] = n;
   }
   return cached[dev];
-}
-
-// ---- a1/a2 --------------------------------------------------------------------
-template <typename T, int CH, int LPR>
-__global__ void __launch_bounds__(kThreads)
-eval_kernel(int objective, const T* __restrict__ X, int64_t P, int N, int64_t ld, const T* __restrict__ scale,
-            const T* __restrict__ shift, T* __restrict__ f) {
-  using TL = Tile<T, CH, LPR>;
-  constexpr int VEC = Num<T>::VEC;
-  const int lane = threadIdx.x & 31, l = lane % LPR, sub = lane / LPR;
-  const int64_t warp = (int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
-  const int64_t nwarps = (int64_t)gridDim.x * (kThreads / 32);
-  const int64_t groups = (P + TL::RPW - 1) / TL::RPW;
-  for (int64_t g = warp; g < groups; g += nwarps) {
-    int64_t row = g * TL::RPW + sub;
-    const bool live = row < P;
-    if (!live) row = P - 1;
-    TL x;
-    x.load(X + row * ld, l, (int)ld);
-    if (scale != nullptr) {  // un-standardise: x * xstd + xm (_cmaes.py:168-173)
-#pragma unroll
-      for (int c = 0; c < CH; ++c)
-#pragma unroll
-        for (int e = 0; e < VEC; ++e) {
-          int j = TL::col(c, l, e);
-          if (j < N) x.v[c][e] = add_rn(mul_rn(x.v[c][e], scale[j]), shift[j]);
-        }
-    }
-    T val = evaluate_tile<T, CH, LPR>(objective, x, l, N);
-    if (live && l == 0) f[row] = val;
-  }
 }
 
 // ---- a3 -----------------------------------------------------------------------
@@ -142,24 +111,6 @@ best_init_kernel(const T* __restrict__ x, const T* __restrict__ xfun, int64_t P,
 }
 
 template <typename T>
-static int eval_launch(int objective, const void* X, int64_t P, int N, int64_t ld, const void* scale,
-                       const void* shift, void* f, cudaStream_t s) {
-  Shape sh;
-  if (!pick_shape(N, Num<T>::VEC, &sh)) {
-    set_error("sp_eval: ndim %d exceeds the compiled row shapes", N);
-    return SP_ERR_SHAPE;
-  }
-  const int grid = grid_for_rows(P, sh.lpr, 8);
-#define SP_CALL(TT, C, L)                                                                                     \
-  eval_kernel<TT, C, L><<<grid, kThreads, 0, s>>>(objective, (const TT*)X, P, N, ld, (const TT*)scale,        \
-                                                  (const TT*)shift, (TT*)f)
-  SP_DISPATCH_SHAPE(T, sh, SP_CALL);
-#undef SP_CALL
-  SP_CHECK_LAUNCH();
-  return SP_OK;
-}
-
-template <typename T>
 static int select_launch(int it, int maxiter, double xtol, double ftol, const void* cand, const void* candfun, void* x,
                          void* xfun, int64_t P, int N, int64_t ld, int copy_when, void* gbest, sp_ctrl* ctrl,
                          void* scratch, cudaStream_t s) {
@@ -215,8 +166,8 @@ int sp_eval(int objective, int dtype, const void* X, int64_t P, int N, int64_t l
   const int vec = dtype == SP_F32 ? 4 : 2;
   SP_CHECK_ARG(ld >= N && ld % vec == 0 && aligned16(X), "rows must be 16-byte aligned (ld multiple of 16/sizeof(T))");
   cudaStream_t s = (cudaStream_t)stream;
-  return dtype == SP_F32 ? eval_launch<float>(objective, X, P, N, ld, scale, shift, f, s)
-                         : eval_launch<double>(objective, X, P, N, ld, scale, shift, f, s);
+  return dtype == SP_F32 ? eval_launch<float>(objective, X, P, N, ld, scale, shift, f, 0, s)
+                         : eval_launch<double>(objective, X, P, N, ld, scale, shift, f, 0, s);
 }
 
 int sp_lhs_init(int dtype, void* X, int64_t P, int N, int64_t ld, const void* lower, const void* upper,
@@ -266,6 +217,48 @@ int sp_best_init(int dtype, const void* x, const void* xfun, int64_t P, int N, i
   else
     best_init_kernel<double><<<grid, kThreads, 0, s>>>((const double*)x, (const double*)xfun, P, N, ld, (double*)gbest,
                                                        ctrl, (Best*)scratch);
+  SP_CHECK_LAUNCH();
+  return SP_OK;
+}
+
+int sp_random_fill(int dtype, void* out, int64_t P, int N, int64_t ld, int it, int purpose, uint64_t seed, int normal,
+                   void* stream) {
+  SP_CHECK_ARG(out && P >= 1 && N >= 1 && ld >= N, "null pointer or bad shape");
+  SP_CHECK_ARG(dtype == SP_F32 || dtype == SP_F64, "dtype");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int vec = dtype == SP_F32 ? 4 : 2;
+  int64_t need = (P * (int64_t)((N + vec - 1) / vec) + 255) / 256, cap = (int64_t)sm_count() * 8;
+  const int grid = (int)(need < cap ? need : cap);
+  if (dtype == SP_F32)
+    random_fill_kernel<float><<<grid, 256, 0, s>>>((float*)out, P, N, ld, it, seed, (uint32_t)purpose, normal);
+  else
+    random_fill_kernel<double><<<grid, 256, 0, s>>>((double*)out, P, N, ld, it, seed, (uint32_t)purpose, normal);
+  SP_CHECK_LAUNCH();
+  return SP_OK;
+}
+
+int sp_fitness_rank(int dtype, const void* fit, int64_t P, int32_t* rank, void* stream) {
+  SP_CHECK_ARG(fit && rank && P >= 1 && P < (1LL << 31), "null pointer or bad popsize");
+  SP_CHECK_ARG(dtype == SP_F32 || dtype == SP_F64, "dtype");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int grid = (int)((P + kThreads - 1) / kThreads);
+  if (dtype == SP_F32) rank_kernel<float><<<grid, kThreads, 0, s>>>((const float*)fit, P, rank, nullptr);
+  else rank_kernel<double><<<grid, kThreads, 0, s>>>((const double*)fit, P, rank, nullptr);
+  SP_CHECK_LAUNCH();
+  return SP_OK;
+}
+
+int sp_sym_eigh(int dtype, void* C, int N, void* w, void* B, void* work, void* stream) {
+  SP_CHECK_ARG(C && w && B && work && N >= 1 && N <= 1024, "null pointer or N outside [1, 1024]");
+  SP_CHECK_ARG(dtype == SP_F32 || dtype == SP_F64, "dtype");
+  cudaStream_t s = (cudaStream_t)stream;
+  cudaError_t e = dtype == SP_F32
+                      ? jacobi_launch<float>((float*)C, N, (float*)w, (float*)B, (float*)work, 0, nullptr, nullptr, nullptr, s)
+                      : jacobi_launch<double>((double*)C, N, (double*)w, (double*)B, (double*)work, 0, nullptr, nullptr, nullptr, s);
+  if (e != cudaSuccess) {
+    set_error("sp_sym_eigh: %s", cudaGetErrorString(e));
+    return SP_ERR_CUDA;
+  }
   SP_CHECK_LAUNCH();
   return SP_OK;
 }

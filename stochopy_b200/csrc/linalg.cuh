@@ -1,0 +1,290 @@
+// Small dense linear algebra for the CMA-ES path: tiled GEMMs with fused
+// prologues/epilogues and a one-sided Jacobi symmetric eigensolver.
+// CMA-ES matrices are N x N with N <= ~1024 and the GEMMs are <= 1 GFLOP, fp64 by
+// default (tcgen05 has no f64 kind), so these are CUDA-core DFMA/FFMA kernels.
+#pragma once
+#include "common.cuh"
+
+namespace sp {
+
+constexpr int kGemmTile = 64;  // output tile edge
+constexpr int kGemmK = 16;     // k-chunk
+// 256 threads, each owns a 4 x 4 block of the 64 x 64 tile.
+
+// C[m][n] = epi(sum_k A(m,k) * B(n,k))        ("NT": both operands k-contiguous)
+// LoadA / LoadB: functors (row, k) -> T (0 outside bounds handled here); Epi: (m, n, acc).
+template <typename T, typename LoadA, typename LoadB, typename Epi>
+__device__ __forceinline__ void gemm_nt_tile(int M, int Nn, int K, int m0, int n0, LoadA la, LoadB lb, Epi epi) {
+  __shared__ T As[kGemmK][kGemmTile + 4];
+  __shared__ T Bs[kGemmK][kGemmTile + 4];
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  T acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = T(0);
+  for (int k0 = 0; k0 < K; k0 += kGemmK) {
+    // 64 x 16 elements per operand, 4 per thread; k fastest so global reads are contiguous
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const int e = tid + t * 256, r = e >> 4, kk = e & 15;
+      const int m = m0 + r, n = n0 + r, k = k0 + kk;
+      As[kk][r] = (m < M && k < K) ? la(m, k) : T(0);
+      Bs[kk][r] = (n < Nn && k < K) ? lb(n, k) : T(0);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < kGemmK; ++kk) {
+      T a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = As[kk][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = Bs[kk][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] += a[i] * b[j];
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int m = m0 + ty * 4 + i, n = n0 + tx * 4 + j;
+      if (m < M && n < Nn) epi(m, n, acc[i][j]);
+    }
+}
+
+// C[r][c] = sum_i A(i, r) * B(i, c) over i in [i0, i1)   ("TN": reduction over rows)
+template <typename T, typename LoadA, typename LoadB, typename Epi>
+__device__ __forceinline__ void gemm_tn_tile(int R, int Cc, int i0, int i1, int r0, int c0, LoadA la, LoadB lb, Epi epi) {
+  __shared__ T As[kGemmK][kGemmTile + 4];
+  __shared__ T Bs[kGemmK][kGemmTile + 4];
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  T acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = T(0);
+  for (int ib = i0; ib < i1; ib += kGemmK) {
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const int e = tid + t * 256, kk = e >> 6, cc = e & 63;  // column fastest: contiguous row reads
+      const int i = ib + kk;
+      As[kk][cc] = (i < i1 && r0 + cc < R) ? la(i, r0 + cc) : T(0);
+      Bs[kk][cc] = (i < i1 && c0 + cc < Cc) ? lb(i, c0 + cc) : T(0);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < kGemmK; ++kk) {
+      T a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = As[kk][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = Bs[kk][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] += a[i] * b[j];
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int r = r0 + ty * 4 + i, c = c0 + tx * 4 + j;
+      if (r < R && c < Cc) epi(r, c, acc[i][j]);
+    }
+}
+
+// ---- symmetric eigendecomposition: cyclic one-sided Jacobi on rows -----------------
+// W = Q C is driven to mutually orthogonal rows by plane rotations applied to the
+// rows of W and Q alike (Hestenes).  At convergence row j of Q is an eigenvector
+// q_j and row j of W equals lambda_j q_j, so lambda_j = w_j . q_j (signed).
+// One CTA of 1024 threads; a warp owns one (p, q) pair of the round-robin round.
+// W and Q live in shared memory when 2 N^2 scalars fit, otherwise in global (L2).
+// warm != 0: start from Q = previous eigenvectors (rows), W = Q C -- the covariance
+// moves little per generation, so 2-3 sweeps instead of ~8 from the identity.
+template <typename T>
+struct JacobiEps;
+template <>
+struct JacobiEps<double> {
+  static __device__ double eps() { return 2.220446049250313e-16; }
+};
+template <>
+struct JacobiEps<float> {
+  static __device__ float eps() { return 1.1920929e-7f; }
+};
+
+constexpr int kJacobiThreads = 1024;
+
+template <typename T>
+__global__ void __launch_bounds__(kJacobiThreads, 1)
+jacobi_eigh_kernel(T* __restrict__ C, int N, T* __restrict__ w_out, T* __restrict__ B, T* __restrict__ Wg,
+                   T* __restrict__ Qg, int use_smem, int warm, const int* __restrict__ gate,
+                   const int* __restrict__ status_gate, int* __restrict__ sweeps_out) {
+  extern __shared__ __align__(16) unsigned char jsm[];
+  __shared__ unsigned int s_off;
+  __shared__ int s_rank_tmp;
+  if (gate != nullptr && *gate == 0) return;
+  if (status_gate != nullptr && *status_gate != SP_RUNNING) return;
+  T* W = use_smem ? reinterpret_cast<T*>(jsm) : Wg;
+  T* Q = use_smem ? reinterpret_cast<T*>(jsm) + (size_t)N * N : Qg;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = kJacobiThreads / 32;
+
+  // symmetrise from the upper triangle (_cmaes.py:303): C = triu(C) + triu(C,1)^T
+  for (int e = tid; e < N * N; e += kJacobiThreads) {
+    const int r = e / N, c = e - r * N;
+    if (r > c) C[e] = C[c * N + r];
+  }
+  __syncthreads();
+  if (warm) {  // Q rows = previous eigenvectors (columns of B); W = Q C
+    for (int e = tid; e < N * N; e += kJacobiThreads) {
+      const int j = e / N, r = e - j * N;
+      Q[e] = B[r * N + j];
+    }
+    __syncthreads();
+    for (int e = tid; e < N * N; e += kJacobiThreads) {
+      const int j = e / N, c = e - j * N;
+      T acc = 0;
+      for (int k = 0; k < N; ++k) acc += Q[j * N + k] * C[k * N + c];
+      W[e] = acc;
+    }
+  } else {
+    for (int e = tid; e < N * N; e += kJacobiThreads) {
+      const int r = e / N, c = e - r * N;
+      W[e] = C[e];
+      Q[e] = r == c ? T(1) : T(0);
+    }
+  }
+  __syncthreads();
+
+  // rotate while |w_p.w_q| exceeds the rounding noise of a length-N dot product
+  const T tol = T(4) * JacobiEps<T>::eps() * sqrt((T)(N < 16 ? 16 : N));
+  const int n = N + (N & 1);  // even player count; index N (if any) is a bye
+  const int half = n / 2;
+  int sweep = 0;
+  for (; sweep < 60; ++sweep) {
+    if (tid == 0) s_off = 0u;
+    __syncthreads();
+    for (int r = 0; r < n - 1; ++r) {
+      for (int i = warp; i < half; i += nwarps) {
+        int p, q;
+        if (i == 0) {
+          p = n - 1;
+          q = r;
+        } else {
+          p = (r + i) % (n - 1);
+          q = (r - i + (n - 1)) % (n - 1);
+        }
+        if (p >= N || q >= N) continue;
+        T* wp = W + (size_t)p * N;
+        T* wq = W + (size_t)q * N;
+        T al = 0, be = 0, ga = 0;
+        for (int k = lane; k < N; k += 32) {
+          const T a = wp[k], b = wq[k];
+          al += a * a;
+          be += b * b;
+          ga += a * b;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          al += __shfl_xor_sync(0xffffffffu, al, o);
+          be += __shfl_xor_sync(0xffffffffu, be, o);
+          ga += __shfl_xor_sync(0xffffffffu, ga, o);
+        }
+        const T lim = tol * sqrt(al * be);
+        if (fabs(ga) > lim && al > T(0) && be > T(0)) {
+          if (lane == 0) s_off = 1u;
+          const T zeta = (be - al) / (T(2) * ga);
+          const T t = (zeta >= T(0) ? T(1) : T(-1)) / (fabs(zeta) + sqrt(T(1) + zeta * zeta));
+          const T cs = T(1) / sqrt(T(1) + t * t), sn = cs * t;
+          T* qp = Q + (size_t)p * N;
+          T* qq = Q + (size_t)q * N;
+          for (int k = lane; k < N; k += 32) {
+            const T a = wp[k], b = wq[k];
+            wp[k] = cs * a - sn * b;
+            wq[k] = sn * a + cs * b;
+            const T c = qp[k], d = qq[k];
+            qp[k] = cs * c - sn * d;
+            qq[k] = sn * c + cs * d;
+          }
+        }
+      }
+      __syncthreads();
+    }
+    const unsigned int off = s_off;
+    __syncthreads();
+    if (off == 0u) break;
+  }
+  if (tid == 0 && sweeps_out != nullptr) *sweeps_out = sweep + 1;
+
+  // eigenvalues (Rayleigh product), ascending stable rank, canonical sign, scatter
+  T* lam = w_out;  // temporarily unsorted in global scratch: reuse Wg tail? keep simple: two passes
+  __shared__ T s_lam[1024];
+  for (int j = warp; j < N; j += nwarps) {
+    T acc = 0;
+    for (int k = lane; k < N; k += 32) acc += W[(size_t)j * N + k] * Q[(size_t)j * N + k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) s_lam[j] = acc;
+  }
+  __syncthreads();
+  (void)s_rank_tmp;
+  for (int j = warp; j < N; j += nwarps) {
+    const T mine = s_lam[j];
+    int rk = 0;
+    for (int k = lane; k < N; k += 32) {
+      const T o = s_lam[k];
+      rk += (o < mine) || (o == mine && k < j);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) rk += __shfl_xor_sync(0xffffffffu, rk, o);
+    // sign: largest |component| positive (first one on ties)
+    T best = T(-1);
+    int bidx = 0;
+    for (int k = lane; k < N; k += 32) {
+      const T a = fabs(Q[(size_t)j * N + k]);
+      if (a > best) {
+        best = a;
+        bidx = k;
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const T ob = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bidx, o);
+      if (ob > best || (ob == best && oi < bidx)) {
+        best = ob;
+        bidx = oi;
+      }
+    }
+    const T sgn = Q[(size_t)j * N + bidx] < T(0) ? T(-1) : T(1);
+    if (lane == 0) lam[rk] = mine;
+    for (int k = lane; k < N; k += 32) B[(size_t)k * N + rk] = sgn * Q[(size_t)j * N + k];
+  }
+}
+
+template <typename T>
+inline cudaError_t jacobi_launch(T* C, int N, T* w, T* B, T* work, int warm, const int* gate,
+                                 const int* status_gate, int* sweeps, cudaStream_t s) {
+  const size_t need = 2 * (size_t)N * N * sizeof(T);
+  const int use_smem = need <= 200 * 1024 ? 1 : 0;
+  auto kern = jacobi_eigh_kernel<T>;
+  static thread_local bool configured[64];
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) dev = 0;
+  if (!configured[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return e;
+    configured[dev] = true;
+  }
+  kern<<<1, kJacobiThreads, use_smem ? need : 0, s>>>(C, N, w, B, work, work + (size_t)N * N, use_smem, warm, gate,
+                                                       status_gate, sweeps);
+  return cudaSuccess;
+}
+
+}  // namespace sp

@@ -5,8 +5,7 @@
 //
 // Per particle (row-local, in place): read X, V, pbest; write X, V and, on
 // improvement only, pbest.  Algorithmic HBM bytes per particle: 5 * N * s + 3 * s.
-#include "objectives.cuh"
-#include "philox.cuh"
+#include "rows.cuh"
 
 namespace sp {
 
@@ -183,30 +182,6 @@ __global__ void restart_plan_kernel(sp_ctrl* ctrl, int64_t P, int N, int it, int
   ctrl->aux[0] = 0.0;
 }
 
-// (3) ascending stable rank of pbestfit (only when a restart fires)
-template <typename T>
-__global__ void __launch_bounds__(kThreads)
-rank_kernel(const T* __restrict__ fit, int64_t P, int32_t* __restrict__ rank, const sp_ctrl* ctrl) {
-  if (ctrl != nullptr && ctrl->flag <= 0) return;
-  __shared__ T s_f[kThreads];
-  const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
-  const T mine = i < P ? fit[i] : T(0);
-  int r = 0;
-  for (int64_t base = 0; base < P; base += kThreads) {
-    const int64_t j = base + threadIdx.x;
-    s_f[threadIdx.x] = j < P ? fit[j] : Num<T>::inf();
-    __syncthreads();
-    const int lim = (int)((P - base) < kThreads ? (P - base) : kThreads);
-#pragma unroll 8
-    for (int t = 0; t < lim; ++t) {
-      const T o = s_f[t];
-      r += (o < mine) || (o == mine && base + t < i);
-    }
-    __syncthreads();
-  }
-  if (i < P) rank[i] = r;
-}
-
 // (4) reset the nw worst: V = 0, X = U(lower, upper), pbest = X, pbestfit = 1e30
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
@@ -307,7 +282,7 @@ static int restart_plan_launch(const sp_pso_state* st, int it, int32_t* rank, cu
   restart_plan_kernel<<<1, 1, 0, s>>>(st->ctrl, st->P, st->N, it, st->maxiter, st->gamma, st->delta);
   SP_CHECK_LAUNCH();
   rank_kernel<T><<<(int)((st->P + kThreads - 1) / kThreads), kThreads, 0, s>>>((const T*)st->pbestfit, st->P, rank,
-                                                                                st->ctrl);
+                                                                                &st->ctrl->flag);
   SP_CHECK_LAUNCH();
   return SP_OK;
 }

@@ -72,7 +72,7 @@ class Engine:
         self.vec = 16 // self.np_dt.itemsize
         key = (self.device.type, self.device.index)
         if key not in _PINNED:
-            _PINNED[key] = torch.empty(64, dtype=torch.uint8, pin_memory=True)
+            _PINNED[key] = torch.empty(512, dtype=torch.uint8, pin_memory=True)
         self._ctrl_host = _PINNED[key]
 
     # -- buffers ----------------------------------------------------------------
@@ -127,11 +127,17 @@ class Engine:
         scratch = torch.zeros(int(L.load().sp_scratch_bytes()), dtype=torch.uint8, device=self.device)
         return ctrl, scratch
 
-    def read_ctrl(self, ctrl):
-        """Device control block -> host mirror (one 64-byte D2H through pinned memory)."""
-        self._ctrl_host.copy_(ctrl, non_blocking=True)
+    def read_ctrl(self, ctrl, cls=L.Ctrl):
+        """Device control block -> host mirror (one small D2H through pinned memory)."""
+        n = C.sizeof(cls)
+        self._ctrl_host[:n].copy_(ctrl[:n], non_blocking=True)
         self.sync()
-        return L.Ctrl.from_buffer_copy(self._ctrl_host.numpy().tobytes())
+        return cls.from_buffer_copy(self._ctrl_host[:n].numpy().tobytes())
+
+    def new_struct(self, host):
+        """Upload a ctypes struct as a device byte buffer."""
+        raw = np.frombuffer(bytes(host), dtype=np.uint8).copy()
+        return torch.from_numpy(raw).to(self.device)
 
     # -- population evaluation (the reference's `fun(X)` wrapper) -----------------------
     def evaluate(self, fun, args, obj, X, p, n, out, scale=None, shift=None, to_user=None):
