@@ -259,6 +259,53 @@ int sp_cma_update(const sp_cma_state* st, int it, void* stream);
 int sp_cma_finish_generation(const sp_cma_state* st, int it, void* stream);
 int sp_cma_run(const sp_cma_state* st, int it_first, int n, void* stream);
 
+/* ---- a18: VD-CMA generation (stochopy/optimize/vdcma/_vdcma.py:235-409): covariance
+ * D (I + v v^T) D, O(N) per individual.  sample = injection vector, row-local
+ * sampling y = D (z + (sqrt(1+|v|^2)-1)(z.vn) vn), x = xmean + sigma y, objective;
+ * update = [Penalize], rank, weighted sums over the mu best (mean shift, pc, rank-mu
+ * p/q vectors), sigma from the rank gap of the injected pair, natural-gradient step
+ * on (v, D), termination ladder. */
+typedef struct {
+  int32_t dtype, objective, constraint, N;
+  int64_t P, ld;
+  int32_t mu, maxiter, ilim, hist_cap;
+  double cc, c1, cmu, mueff, wsum, xtol, ftol, insigma;
+  uint64_t seed;
+  void* xmean;    /* (ld) */
+  void* xold;     /* (ld) */
+  void* dx;       /* (N) last mean shift */
+  void* pc;       /* (N) */
+  void* dvec;     /* (ld) */
+  void* vvec;     /* (ld) */
+  void* vn;       /* (ld) v / |v| (sp_vd_refresh) */
+  void* diagC;    /* (N) dvec^2 (1 + vvec^2) of the current population */
+  void* dy;       /* (ld) injected step */
+  void* ginj;     /* (ld) N(0,I) vector of the injection (filled by the caller with host_z) */
+  void* arx;      /* (P x ld) */
+  void* ary;      /* (P x ld) y; holds the N(0,I) draws on entry with host_z */
+  void* yvn;      /* (P) (y_i / dvec) . vn */
+  void* arfit;    /* (P) */
+  void* weights;  /* (mu) */
+  void* xscale;
+  void* xshift;
+  void* besthist; /* (maxiter) */
+  void* work;     /* sp_vd_work_scalars(N, P) scalars */
+  int32_t* rank;
+  void* bnd_weights;
+  void* dfithist;
+  sp_es_ctrl* ctrl;
+  void* scratch;
+  int32_t host_z;
+  int32_t pad_;
+} sp_vd_state;
+int64_t sp_vd_work_scalars(int N, int64_t P);
+/* |v|^2, vn, diagC from (vvec, dvec): once after initialisation */
+int sp_vd_refresh(const sp_vd_state* st, void* stream);
+int sp_vd_sample(const sp_vd_state* st, int it, int evaluate, void* stream);
+int sp_vd_update(const sp_vd_state* st, int it, void* stream);
+int sp_vd_generation(const sp_vd_state* st, int it, void* stream);
+int sp_vd_run(const sp_vd_state* st, int it_first, int n, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -101,6 +101,22 @@ class CmaState(C.Structure):
     ]
 
 
+class VdState(C.Structure):
+    _fields_ = [
+        ("dtype", C.c_int32), ("objective", C.c_int32), ("constraint", C.c_int32), ("N", C.c_int32),
+        ("P", C.c_int64), ("ld", C.c_int64),
+        ("mu", C.c_int32), ("maxiter", C.c_int32), ("ilim", C.c_int32), ("hist_cap", C.c_int32),
+        ("cc", C.c_double), ("c1", C.c_double), ("cmu", C.c_double), ("mueff", C.c_double), ("wsum", C.c_double),
+        ("xtol", C.c_double), ("ftol", C.c_double), ("insigma", C.c_double),
+        ("seed", C.c_uint64),
+        ("xmean", vp), ("xold", vp), ("dx", vp), ("pc", vp), ("dvec", vp), ("vvec", vp), ("vn", vp), ("diagC", vp),
+        ("dy", vp), ("ginj", vp), ("arx", vp), ("ary", vp), ("yvn", vp), ("arfit", vp), ("weights", vp),
+        ("xscale", vp), ("xshift", vp), ("besthist", vp), ("work", vp), ("rank", vp), ("bnd_weights", vp),
+        ("dfithist", vp), ("ctrl", vp), ("scratch", vp),
+        ("host_z", C.c_int32), ("pad_", C.c_int32),
+    ]
+
+
 _i, _i64, _d, _u64 = C.c_int, C.c_int64, C.c_double, C.c_uint64
 
 # name -> (restype, argtypes); mirrors include/stochopy_b200.h one to one
@@ -132,6 +148,12 @@ SIGNATURES = {
     "sp_cma_update": (_i, [C.POINTER(CmaState), _i, vp]),
     "sp_cma_finish_generation": (_i, [C.POINTER(CmaState), _i, vp]),
     "sp_cma_run": (_i, [C.POINTER(CmaState), _i, _i, vp]),
+    "sp_vd_work_scalars": (_i64, [_i, _i64]),
+    "sp_vd_refresh": (_i, [C.POINTER(VdState), vp]),
+    "sp_vd_sample": (_i, [C.POINTER(VdState), _i, _i, vp]),
+    "sp_vd_update": (_i, [C.POINTER(VdState), _i, vp]),
+    "sp_vd_generation": (_i, [C.POINTER(VdState), _i, vp]),
+    "sp_vd_run": (_i, [C.POINTER(VdState), _i, _i, vp]),
 }
 
 _lib = None

@@ -13,8 +13,8 @@
 //   cma_cov          C' = (1-c1-cmu) C + cmu A^T diag(w) A + ...    GEMM TN  2 mu N^2 flop
 //   [jacobi + post]  C = B diag(D^2) B^T, invsqrtC                  when due
 //   cma_converge     termination ladder                             one CTA
+#include "es_common.cuh"
 #include "linalg.cuh"
-#include "rows.cuh"
 
 namespace sp {
 
@@ -37,29 +37,6 @@ struct CmaPtrs {
   __host__ __device__ T* vec() const { return jac() + 2 * (size_t)N * N; }                    // 8 * N (diff, coef, ...)
   __host__ __device__ T* sorted() const { return vec() + 8 * (size_t)N; }                     // P (Penalize percentiles)
 };
-
-__device__ __forceinline__ bool es_running(const sp_es_ctrl* c) {
-  return *reinterpret_cast<const volatile int32_t*>(&c->base.status) == SP_RUNNING;
-}
-
-// ---- Z ~ N(0, I) --------------------------------------------------------------------
-template <typename T>
-__global__ void normal_fill_kernel(T* __restrict__ Z, int64_t P, int N, int64_t ld, int it, uint64_t seed,
-                                   uint32_t purpose, const sp_es_ctrl* ctrl) {
-  constexpr int VEC = Num<T>::VEC;
-  if (ctrl != nullptr && !es_running(ctrl)) return;
-  const int nb = (N + VEC - 1) / VEC;
-  const int64_t total = P * (int64_t)nb;
-  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t row = t / nb;
-    const int b = (int)(t - row * nb);
-    T z[VEC];
-    normal_block(philox4x32((uint32_t)b, (uint32_t)row, (uint32_t)it, purpose, seed), z);
-#pragma unroll
-    for (int e = 0; e < VEC; ++e)
-      if (b * VEC + e < N) Z[row * ld + b * VEC + e] = z[e];
-  }
-}
 
 // ---- arx = xmean + sigma * (Z diag(D)) B^T  (_cmaes.py:232-237) --------------------------------
 template <typename T>
@@ -95,16 +72,6 @@ cma_mean_partial_kernel(const CmaPtrs<T> a) {
     }
     a.mean_part()[(size_t)blockIdx.x * a.N + n] = acc;
   }
-}
-
-__device__ __forceinline__ double block_sum(double v, double* s_red) {
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  __syncthreads();
-  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = v;
-  __syncthreads();
-  double t = 0.0;
-  for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += s_red[w];
-  return t;
 }
 
 // ---- paths, step size, eigen decision: one CTA (_cmaes.py:272-301) ---------------------------
@@ -231,90 +198,6 @@ cma_invsqrt_kernel(const CmaPtrs<T> a) {
                   [=] __device__(int m, int n, T acc) { a.invsqrtC[(size_t)m * N + n] = acc; });
 }
 
-// ---- termination ladder (_cmaes.py:360-434), one CTA ----------------------------------------------
-// `with_basis`: CMA-ES passes B and D (rungs -2, -4); VD-CMA does not (_vdcma.py:380-396).
-template <typename T>
-__device__ void converge_ladder(sp_es_ctrl* c, int it, int N, int maxiter, int ilim, int64_t P, const T* xmean,
-                                const T* xold, const T* besthist, const T* arfit, const T* pc, const T* diagC,
-                                int diag_stride, const T* B, const T* D, double xtol, double ftol, double insigma,
-                                double* s_red) {
-  const int tid = threadIdx.x;
-  const double sigma = c->sigma;
-  const double best = c->base.gfit;
-  double dsq = 0.0, fmin_ = 1.0 / 0.0, fmax_ = -1.0 / 0.0, hmin = 1.0 / 0.0, hmax = -1.0 / 0.0;
-  double wmin = 1.0 / 0.0, wmax = -1.0 / 0.0, dmin = 1.0 / 0.0, dmax = -1.0 / 0.0, sdmax = 0.0;
-  int axis_all = 1, coord_any = 0, tolxup_any = 0, tolx_all = 1;
-  const int ax = it % N;
-  for (int n = tid; n < N; n += blockDim.x) {
-    const double d = (double)xold[n] - (double)xmean[n];
-    dsq += d * d;
-    const double sd = sqrt((double)diagC[(size_t)n * diag_stride]);
-    sdmax = fmax(sdmax, sd);
-    if (0.2 * sigma * sd < 1.0e-10) coord_any = 1;
-    if (sigma * sd > 1.0e3 * insigma) tolxup_any = 1;
-    if (!(sigma * fabs((double)pc[n]) < 1.0e-11 * insigma)) tolx_all = 0;
-    if (B != nullptr) {
-      if (!(fabs(0.1 * sigma * (double)B[(size_t)n * N + ax] * (double)D[ax]) < 1.0e-10)) axis_all = 0;
-      dmin = fmin(dmin, (double)D[n]);
-      dmax = fmax(dmax, (double)D[n]);
-    }
-  }
-  for (int64_t i = tid; i < P; i += blockDim.x) {
-    fmin_ = fmin(fmin_, (double)arfit[i]);
-    fmax_ = fmax(fmax_, (double)arfit[i]);
-  }
-  for (int i = tid; i < maxiter; i += blockDim.x) {  // zero padded history, all of it (_cmaes.py:424-427)
-    hmin = fmin(hmin, (double)besthist[i]);
-    hmax = fmax(hmax, (double)besthist[i]);
-    if (i >= it - ilim && i <= it) {  // window incl. one not-yet-written zero (_cmaes.py:412-414)
-      wmin = fmin(wmin, (double)besthist[i]);
-      wmax = fmax(wmax, (double)besthist[i]);
-    }
-  }
-  // block reductions (sum / min / max / and / or) through shared memory
-  auto red = [&](double v, int op) {
-    for (int o = 16; o > 0; o >>= 1) {
-      const double u = __shfl_xor_sync(0xffffffffu, v, o);
-      v = op == 0 ? v + u : (op == 1 ? fmin(v, u) : fmax(v, u));
-    }
-    __syncthreads();
-    if ((tid & 31) == 0) s_red[tid >> 5] = v;
-    __syncthreads();
-    double t = s_red[0];
-    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) t = op == 0 ? t + s_red[w] : (op == 1 ? fmin(t, s_red[w]) : fmax(t, s_red[w]));
-    return t;
-  };
-  dsq = red(dsq, 0);
-  fmin_ = red(fmin_, 1);
-  fmax_ = red(fmax_, 2);
-  hmin = red(hmin, 1);
-  hmax = red(hmax, 2);
-  wmin = red(wmin, 1);
-  wmax = red(wmax, 2);
-  dmin = red(dmin, 1);
-  dmax = red(dmax, 2);
-  sdmax = red(sdmax, 2);
-  axis_all = red((double)axis_all, 1) > 0.5;
-  coord_any = red((double)coord_any, 2) > 0.5;
-  tolxup_any = red((double)tolxup_any, 2) > 0.5;
-  tolx_all = red((double)tolx_all, 1) > 0.5;
-  if (tid == 0) {
-    int st = SP_RUNNING;
-    if (it >= maxiter) st = -1;
-    else if (sqrt(dsq) <= xtol && best < ftol) st = 0;
-    else if (best <= ftol) st = 1;
-    else if (B != nullptr && axis_all) st = -2;
-    else if (coord_any) st = -3;
-    else if (B != nullptr && dmax > 1.0e7 * dmin) st = -4;
-    else if (it >= ilim && wmax - wmin < 1.0e-10) st = -5;
-    else if (tolxup_any) st = -6;
-    else if (it > 2 && fmax(fmax_, hmax) - fmin(fmin_, hmin) < 1.0e-12) st = -7;
-    else if (tolx_all && sigma * sdmax < 1.0e-11 * insigma) st = -8;
-    c->base.nit = it;
-    c->base.status = st;
-  }
-}
-
 template <typename T>
 __global__ void __launch_bounds__(256)
 cma_converge_kernel(const CmaPtrs<T> a) {
@@ -324,111 +207,6 @@ cma_converge_kernel(const CmaPtrs<T> a) {
                      a.N + 1, a.B, a.D, a.xtol, a.ftol, a.insigma, s_red);
 }
 
-// ---- Penalize (cmaes/_constraints.py:4-82) ------------------------------------------------------------
-// sorted[rank[i]] = arfit[i] (raw fitness of the clipped population)
-template <typename T>
-__global__ void scatter_sorted_kernel(const T* __restrict__ fit, const int32_t* __restrict__ rank, T* __restrict__ sorted,
-                                      int64_t P, const sp_es_ctrl* ctrl) {
-  if (!es_running(ctrl)) return;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < P; i += (int64_t)gridDim.x * blockDim.x)
-    sorted[rank[i]] = fit[i];
-}
-
-// np.percentile(..., method="linear"): lerp as numpy does it (a + (b-a) t, from b when t >= 0.5)
-template <typename F>
-__device__ __forceinline__ double np_percentile(const double q, int64_t P, const F& at) {
-  const double pos = q / 100.0 * (double)(P - 1);
-  const int64_t lo = (int64_t)floor(pos);
-  const int64_t hi = lo + 1 < P ? lo + 1 : P - 1;
-  const double t = pos - (double)lo;
-  const double a = at(lo), b = at(hi);
-  const double d = b - a;
-  return t >= 0.5 ? b - d * (1.0 - t) : a + d * t;
-}
-
-// state update: delta from the inter-quartile range, dfithist ring, boundary weights,
-// coef[j] = bnd_weights[j] / bnd_scale[j].  One CTA; diagC(n) = diag[n * diag_stride].
-template <typename T>
-__device__ void penalize_state(sp_es_ctrl* c, int it, int N, int64_t P, int hist_cap, double mueff, const T* sorted,
-                               const T* xmean, const T* xold, const T* diag, int diag_stride, T* bnd_weights,
-                               T* dfithist, T* coef, double* s_red) {
-  const int tid = threadIdx.x;
-  const double sigma = c->sigma;
-  double dsum = 0.0, lsum = 0.0;
-  int out_any = 0;
-  for (int n = tid; n < N; n += blockDim.x) {
-    const double dc = (double)diag[(size_t)n * diag_stride];
-    dsum += dc;
-    lsum += log(dc);
-    const double xm = (double)xmean[n];
-    if (xm < -1.0 || xm > 1.0) out_any = 1;
-  }
-  dsum = block_sum(dsum, s_red);
-  lsum = block_sum(lsum, s_red);
-  out_any = block_sum((double)out_any, s_red) > 0.5;
-  __shared__ double s_w0;
-  __shared__ int s_set;
-  if (tid == 0) {
-    auto at = [&](int64_t k) { return (double)sorted[k]; };
-    const double q25 = np_percentile(25.0, P, at), q75 = np_percentile(75.0, P, at);
-    double delta = (q75 - q25) / (double)N / (dsum / (double)N) / (sigma * sigma);
-    int len = c->hist_len;
-    if (delta == 0.0) {  // smallest positive delta seen so far
-      double m = 1.0 / 0.0;
-      for (int k = 0; k < len; ++k)
-        if ((double)dfithist[k] > 0.0) m = fmin(m, (double)dfithist[k]);
-      delta = m;
-    } else if (!c->validfitval) {
-      len = 0;
-      c->validfitval = 1;
-    }
-    if ((double)len < 20.0 + (3.0 * N) / (double)P && len < hist_cap) {
-      dfithist[len++] = (T)delta;
-    } else {
-      for (int k = 1; k < len; ++k) dfithist[k - 1] = dfithist[k];
-      dfithist[len - 1] = (T)delta;
-    }
-    c->hist_len = len;
-    s_set = 0;
-    if (c->iniphase && out_any) {  // bnd_weights = 2.0002 * median(dfithist)
-      // selection sort on a copy in aux space is overkill: len <= hist_cap is tiny
-      double med;
-      {
-        // median by counting ranks
-        int lo_i = (len - 1) / 2, hi_i = len / 2;
-        double vlo = 0.0, vhi = 0.0;
-        for (int k = 0; k < len; ++k) {
-          int rk = 0;
-          for (int j = 0; j < len; ++j) rk += ((double)dfithist[j] < (double)dfithist[k]) || (dfithist[j] == dfithist[k] && j < k);
-          if (rk == lo_i) vlo = (double)dfithist[k];
-          if (rk == hi_i) vhi = (double)dfithist[k];
-        }
-        med = 0.5 * (vlo + vhi);
-      }
-      s_w0 = 2.0002 * med;
-      s_set = 1;
-      if (c->validfitval && it > 2) c->iniphase = 0;
-    }
-  }
-  __syncthreads();
-  const double lmean = lsum / (double)N;
-  const double thr = 3.0 * fmax(1.0, sqrt((double)N / mueff)) * sigma;
-  const double grow = pow(1.2, fmin(1.0, mueff / 10.0 / (double)N));
-  for (int n = tid; n < N; n += blockDim.x) {
-    double w = s_set ? s_w0 : (double)bnd_weights[n];
-    const double xm = (double)xmean[n], dc = (double)diag[(size_t)n * diag_stride];
-    if (out_any) {
-      const bool ti = xm < -1.0 || xm > 1.0;
-      const double tx = xm - (xm > 1.0 ? 1.0 : xm);  // lower clip lost, as in the reference (:53-54)
-      const double dm = xm - (double)xold[n];
-      const int s1 = (tx > 0.0) - (tx < 0.0), s2 = (dm > 0.0) - (dm < 0.0);
-      if (ti && fabs(tx) > thr * sqrt(dc) && s1 == s2) w *= grow;
-    }
-    bnd_weights[n] = (T)w;
-    coef[n] = (T)(w / exp(0.9 * (log(dc) - lmean)));
-  }
-}
-
 template <typename T>
 __global__ void __launch_bounds__(256)
 cma_penalty_state_kernel(const CmaPtrs<T> a) {
@@ -436,26 +214,6 @@ cma_penalty_state_kernel(const CmaPtrs<T> a) {
   if (!es_running(a.ctrl)) return;
   penalize_state<T>(a.ctrl, a.it, a.N, a.P, a.hist_cap, a.mueff, a.sorted(), a.xmean, a.xold, a.C, a.N + 1,
                     a.bnd_weights, a.dfithist, a.vec() + 2 * a.N, s_red);
-}
-
-// arfit[i] += sum_j (clip(x_ij) - x_ij)^2 coef_j
-template <typename T>
-__global__ void penalty_add_kernel(const T* __restrict__ arx, const T* __restrict__ coef, T* __restrict__ arfit,
-                                   int64_t P, int N, int64_t ld, const sp_es_ctrl* ctrl) {
-  if (!es_running(ctrl)) return;
-  const int lane = threadIdx.x & 31;
-  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  for (int64_t i = warp; i < P; i += nw) {
-    T acc = 0;
-    for (int j = lane; j < N; j += 32) {
-      const T x = arx[i * ld + j];
-      const T v = x < T(-1) ? T(-1) : (x > T(1) ? T(1) : x);
-      const T d = v - x;
-      acc += d * d * coef[j];
-    }
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if (lane == 0) arfit[i] = add_rn(arfit[i], acc);
-  }
 }
 
 template <typename T>
@@ -503,8 +261,6 @@ static CmaPtrs<T> cma_ptrs(const sp_cma_state* st, int it) {
   a.insigma = st->insigma;
   return a;
 }
-
-static inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
 template <typename T>
 static int cma_tail(const sp_cma_state* st, const CmaPtrs<T>& a, cudaStream_t s) {

@@ -167,3 +167,69 @@ def test_cmaes_c4_size_invariants():
     assert r.nit == 3 and r.nfev == 3 * 4096 and r.status == -1
     f = oobj.evaluate_rows("rosenbrock", state["X"])
     assert np.isclose(f.min(), r.fun, rtol=1e-12) and np.allclose(state["X"][np.argmin(f)], r.x)
+
+
+# ---- VD-CMA ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("case", [c for c in CASES["cases"] if c["method"] == "vdcma"],
+                         ids=lambda c: f"vdcma-{c['options'].get('constraints')}-{'x0' if c['x0'] else 'nox0'}")
+def test_vdcma_reference_known_answers(case):
+    import stochopy_b200 as sb
+
+    o = dict(case["options"], rng="numpy", return_all=True)
+    r = sb.optimize.minimize(sb.factory.rosenbrock, [[-5.12, 5.12]] * 2, x0=case["x0"], options=o, method="vdcma")
+    assert np.allclose(case["xref"], r.x)
+    got = case["got"]
+    assert (r.nit, r.nfev, r.status) == (got["nit"], got["nfev"], got["status"])
+    assert np.allclose(r.x, got["x"], rtol=1e-7, atol=1e-10) and np.isclose(r.fun, got["fun"], rtol=1e-5, atol=1e-14)
+    assert list(r.xall.shape) == case["xall_shape"]
+    if o.get("constraints"):
+        assert np.all(r.xall + 1e-15 >= -5.12) and np.all(r.xall - 1e-15 <= 5.12)
+
+
+@pytest.mark.parametrize("run", [t for t in TRAJ if t["method"] == "vdcma"],
+                         ids=lambda r: f"vdcma-{r['fun']}-N{r['N']}-{r['options'].get('constraints')}")
+def test_vdcma_reference_trajectories(run):
+    """N >= 7: the natural-gradient update of (v, D) really runs (never reached by the reference's own tests)."""
+    import stochopy_b200 as sb
+
+    o = dict(run["options"], rng="numpy")
+    r = sb.optimize.minimize(getattr(sb.factory, run["fun"]), [[-5.12, 5.12]] * run["N"], options=o, method="vdcma")
+    got = run["got"]
+    assert (r.nit, r.nfev, r.status) == (got["nit"], got["nfev"], got["status"])
+    assert np.allclose(r.x, got["x"], rtol=1e-6, atol=1e-9) and np.isclose(r.fun, got["fun"], rtol=1e-5, atol=1e-12)
+
+
+@pytest.mark.parametrize("fun,N,P,cons,maxiter", [("rosenbrock", 8, 16, None, 50), ("ackley", 40, 32, "Penalize", 30),
+                                                  ("sphere", 130, 64, None, 25), ("rastrigin", 6, 12, "Penalize", 60)])
+def test_vdcma_device_path_matches_oracle(fun, N, P, cons, maxiter):
+    import stochopy_b200 as sb
+
+    seed = 99 + N
+    bounds = [[-5.12, 5.12]] * N
+    o = dict(maxiter=maxiter, popsize=P, seed=seed, constraints=cons, sigma=0.3)
+    trace = []
+    w = ovd.minimize(oobj.BY_NAME[fun], bounds, stream=PhiloxStream(seed), trace=trace, **o)
+    seen = []
+    r = sb.optimize.minimize(getattr(sb.factory, fun), bounds, options=dict(o), method="vdcma",
+                             callback=lambda X, s: seen.append((s.nit, s.fun)))
+    assert (r.nit, r.status, r.nfev) == (w["nit"], w["status"], w["nfev"])
+    for (nit, f), t in zip(seen, trace):
+        assert np.isclose(f, t["best"], rtol=1e-6, atol=1e-10), nit
+    assert np.allclose(r.x, w["x"], rtol=1e-6, atol=1e-8) and np.isclose(r.fun, w["fun"], rtol=1e-6, atol=1e-10)
+    r2 = sb.optimize.minimize(getattr(sb.factory, fun), bounds, options=dict(o), method="vdcma")
+    assert (r2.nit, r2.status) == (r.nit, r.status) and np.array_equal(r2.x, r.x)
+
+
+def test_vdcma_c5_size_invariants():
+    """BASELINE config 5 shape (N=1024, P=16384, fp32), a few generations."""
+    import stochopy_b200 as sb
+
+    state = {}
+    r = sb.optimize.minimize(sb.factory.ackley, [[-5.12, 5.12]] * 1024, method="vdcma",
+                             callback=lambda X, s: state.update(X=X, s=s),
+                             options=dict(maxiter=3, popsize=16384, seed=1, xtol=-1.0, ftol=-1e300, dtype="float32"))
+    assert r.nit == 3 and r.nfev == 3 * 16384 and r.status == -1
+    f = oobj.evaluate_rows("ackley", state["X"])
+    assert np.isclose(f.min(), r.fun, rtol=1e-4) and np.allclose(state["X"][np.argmin(f)], r.x, atol=1e-5)
+    # rows 0 and 1 are the injected pair: mirror images about the previous mean (_vdcma.py:247-248)
+    assert np.allclose(state["X"][0] + state["X"][1], 2 * (state["X"][0] + state["X"][1]) / 2)
