@@ -306,6 +306,23 @@ int sp_vd_update(const sp_vd_state* st, int it, void* stream);
 int sp_vd_generation(const sp_vd_state* st, int it, void* stream);
 int sp_vd_run(const sp_vd_state* st, int it_first, int n, void* stream);
 
+/* ---- a19: Neighbourhood Algorithm resampling (stochopy/optimize/na/_na.py:265-305).
+ * The archive of every model ever evaluated lives on the device TRANSPOSED
+ * (d_archT[j * cap + m], unit-cube coordinates) so the per-axis Voronoi scan reads
+ * contiguous memory.  One CTA per new individual: Gibbs walk inside the cell of one
+ * of the nr best archived models, axis after axis, limits by block reductions. */
+/* append P rows (row-major, ld) at archive positions [M, M+P) */
+int sp_na_append(int dtype, void* d_archT, int64_t cap, int64_t M, const void* d_X, int64_t P, int N, int64_t ld,
+                 void* stream);
+/* d_cells[r] = archive index of the model with fitness rank r, r < nr (d_rank from sp_fitness_rank) */
+int sp_na_cells(const int32_t* d_rank, int64_t M, int32_t nr, int32_t* d_cells, void* stream);
+/* d_X (P x ld) = new population.  d_u (P x ld) U[0,1) draws or NULL (Philox, seed/it);
+ * d_mask (N int32, 0 = zero-span axis: coordinate fixed to 0 and skipped);
+ * d_work: P * M scalars. */
+int sp_na_resample(int dtype, const void* d_archT, int64_t cap, int64_t M, const int32_t* d_cells, int32_t nr,
+                   void* d_X, int64_t P, int N, int64_t ld, const int32_t* d_mask, const void* d_u, uint64_t seed,
+                   int it, void* d_work, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

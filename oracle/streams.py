@@ -125,3 +125,7 @@ class PhiloxStream:
 
     def vd_inject(self, it, N):
         return px.normal([0], N, it, px.VD_INJECT, self.seed, self.dtype)[0]
+
+    def na_uniform(self, it, i, j, low, high):
+        u = px.uniform([i], j + 1, it, px.NA_WALK, self.seed, self.dtype)[0][j]
+        return low + (high - low) * u

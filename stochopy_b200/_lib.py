@@ -148,6 +148,9 @@ SIGNATURES = {
     "sp_cma_update": (_i, [C.POINTER(CmaState), _i, vp]),
     "sp_cma_finish_generation": (_i, [C.POINTER(CmaState), _i, vp]),
     "sp_cma_run": (_i, [C.POINTER(CmaState), _i, _i, vp]),
+    "sp_na_append": (_i, [_i, vp, _i64, _i64, vp, _i64, _i, _i64, vp]),
+    "sp_na_cells": (_i, [vp, _i64, C.c_int32, vp, vp]),
+    "sp_na_resample": (_i, [_i, vp, _i64, _i64, vp, C.c_int32, vp, _i64, _i, _i64, vp, vp, _u64, _i, vp, vp]),
     "sp_vd_work_scalars": (_i64, [_i, _i64]),
     "sp_vd_refresh": (_i, [C.POINTER(VdState), vp]),
     "sp_vd_sample": (_i, [C.POINTER(VdState), _i, _i, vp]),

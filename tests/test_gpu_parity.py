@@ -394,7 +394,7 @@ def test_host_objective_follows_the_same_path():
     assert set(calls) == {(3,)}
 
 
-@pytest.mark.parametrize("method", ["de", "pso", "cpso"])
+@pytest.mark.parametrize("method", ["de", "pso", "cpso", "na", "cmaes", "vdcma"])
 def test_callback_contract(method):
     """callback(X, state) once per iteration incl. the initial population (tests/test_optimize.py:135-152)."""
     import stochopy_b200 as sb
@@ -402,7 +402,7 @@ def test_callback_contract(method):
     seen = []
     r = sb.optimize.minimize(sb.factory.rosenbrock, [[-5.12, 5.12]] * 2, method=method, options={"maxiter": 7, "seed": 1},
                              callback=lambda X, s: seen.append((X.shape, s.nit, s.nfev)))
-    assert len(seen) == 7 and seen[0] == ((10, 2), 1, 10) and seen[-1][1] == r.nit
+    assert len(seen) == 7 and seen[0] == ((10, 2), 1, 10) and seen[-1][1] == r.nit == 7
 
 
 def test_termination_codes():
@@ -414,3 +414,43 @@ def test_termination_codes():
     r = sb.optimize.minimize(sb.factory.sphere, b, method="pso", options=dict(maxiter=5, popsize=20, seed=0, ftol=-1.0))
     assert r.status == -1 and not r.success and r.nit == 5 and r.nfev == 100
     assert r.message == "maximum number of iterations is reached"
+
+
+# ---- a19 NA -----------------------------------------------------------------------------------
+def test_na_reference_known_answer():
+    import stochopy_b200 as sb
+
+    case = [c for c in CASES["cases"] if c["method"] == "na"][0]
+    o = dict(case["options"], rng="numpy", return_all=True)
+    r = sb.optimize.minimize(sb.factory.rosenbrock, [[-5.12, 5.12]] * 2, options=o, method="na")
+    assert np.allclose(case["xref"], r.x)
+    got = case["got"]
+    assert (r.nit, r.nfev, r.status) == (got["nit"], got["nfev"], got["status"])
+    assert np.allclose(r.x, got["x"], rtol=1e-9) and np.isclose(r.fun, got["fun"], rtol=1e-7)
+    assert list(r.xall.shape) == case["xall_shape"] and np.allclose(r.funall[-1], case["funall_last"], rtol=1e-7)
+
+
+def test_na_reference_trajectory_and_philox():
+    import stochopy_b200 as sb
+    from oracle import na as ona
+
+    run = [t for t in TRAJ if t["method"] == "na"][0]
+    r = sb.optimize.minimize(getattr(sb.factory, run["fun"]), [[-5.12, 5.12]] * run["N"],
+                             options=dict(run["options"], rng="numpy"), method="na")
+    got = run["got"]
+    assert (r.nit, r.status) == (got["nit"], got["status"]) and np.allclose(r.x, got["x"], rtol=1e-8)
+    # in-kernel Philox draws vs the oracle fed with the same stream; one fixed (zero-span) axis
+    bounds = [[-5.12, 5.12], [1.5, 1.5], [-2.0, 3.0], [-5.12, 5.12]]
+    o = dict(maxiter=10, popsize=12, seed=77, nrperc=0.4)
+    w = ona.minimize(oobj.sphere, bounds, stream=PhiloxStream(77), **o)
+    r = sb.optimize.minimize(sb.factory.sphere, bounds, options=dict(o), method="na")
+    assert (r.nit, r.status) == (w["nit"], w["status"])
+    assert np.allclose(r.x, w["x"], rtol=1e-9, atol=1e-12) and np.isclose(r.fun, w["fun"], rtol=1e-9)
+    assert r.x[1] == 1.5
+
+
+def test_na_direct_call_default_callback_quirk():
+    import stochopy_b200 as sb
+
+    with pytest.raises(ValueError):  # callback=True default is not callable (_na.py:26,113-114)
+        sb.optimize.na(sb.factory.sphere, [[-1, 1]] * 2)
