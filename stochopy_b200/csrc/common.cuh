@@ -166,7 +166,7 @@ __device__ __forceinline__ Best warp_best(Best b) {
 // Per-CTA minimum -> scratch[blockIdx]; the last CTA to arrive reduces all of
 // them.  Returns true (for every thread of that last CTA) with the global best.
 __device__ __forceinline__ bool grid_best(Best mine, Best* scratch, sp_ctrl* ctrl, Best* out) {
-  __shared__ Best s_best[kThreads / 32];
+  __shared__ Best s_best[32];  // up to 1024 threads
   __shared__ bool s_last;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   mine = warp_best(mine);
@@ -209,7 +209,7 @@ template <typename T>
 __device__ __forceinline__ void finalize_generation(Best b, const T* __restrict__ xrows, int64_t ld, int N,
                                                     T* gbest, sp_ctrl* ctrl, int it, int maxiter, double xtol,
                                                     double ftol) {
-  __shared__ double s_part[kThreads / 32];
+  __shared__ double s_part[32];
   const T* src = xrows + b.row * ld;
   double acc = 0.0;
   for (int j = threadIdx.x; j < N; j += blockDim.x) {

@@ -204,7 +204,7 @@ static int de_launch(const sp_de_state* st, int it, int propose_only, cudaStream
   a.repair = (const T*)st->repair;
   const bool philox = st->r1 == nullptr;
   const int k = de_donor_count(st->strategy);
-  if (philox && sh.lpr == 32 && !g_force_direct && de_tma_fits(k, st->ld, sizeof(T))) {
+  if (philox && sh.lpr == 32 && !g_force_direct && de_tma_fits(sh.ch, st->P, k, st->ld, sizeof(T))) {
     a.cr_cut = crossover_cut<T>(st->CR);
     cudaError_t e = de_tma_dispatch(a, sh.ch, s);
     if (e != cudaSuccess) {

@@ -84,13 +84,8 @@ inline uint64_t crossover_cut<double>(double CR) {
   return t < 0.0 ? 0 : (uint64_t)t;
 }
 
-// TMA-staged kernel (de_tma.cuh), one translation unit per (dtype, strategy)
-constexpr int kTmaWarps = 4;
-constexpr int kTmaStages = 4;
-inline size_t de_tma_smem(int k, int64_t ld, size_t elem) {
-  return 128 + (size_t)kTmaWarps * kTmaStages * (k + 1) * ld * elem;
-}
-inline bool de_tma_fits(int k, int64_t ld, size_t elem) { return de_tma_smem(k, ld, elem) <= 160 * 1024; }
+// pool kernel (de_tma.cuh), one translation unit per (dtype, strategy)
+bool de_tma_fits(int ch, int64_t P, int K, int64_t ld, size_t elem);
 cudaError_t de_tma_dispatch(const DeArgs<float>& a, int ch, cudaStream_t s);
 cudaError_t de_tma_dispatch(const DeArgs<double>& a, int ch, cudaStream_t s);
 

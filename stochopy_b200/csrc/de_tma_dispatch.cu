@@ -1,6 +1,7 @@
 // Strategy dispatch of the TMA-staged DE kernels (instantiated in de_tma_<dtype>_s<k>.cu).
-#include "de_common.cuh"
+#include "de_tma.cuh"
 namespace sp {
+bool de_tma_fits(int ch, int64_t P, int K, int64_t ld, size_t elem) { return de_pool_fits(ch, P, K, ld, elem); }
 #define SP_DECL(T)                                                              \
   cudaError_t de_tma_##T##_s0(const DeArgs<T>&, int, cudaStream_t);             \
   cudaError_t de_tma_##T##_s1(const DeArgs<T>&, int, cudaStream_t);             \
