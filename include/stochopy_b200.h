@@ -91,6 +91,10 @@ int sp_lhs_init(int dtype, void* d_X, int64_t P, int N, int64_t ld, const void* 
                 const void* d_upper, uint64_t seed, const void* d_jitter, const int64_t* d_perm,
                 void* stream);
 
+/* LHS rows [row0, row0 + P_local) of a population of P_total (sharded swarm; Philox draws) */
+int sp_lhs_init_shard(int dtype, void* d_X, int64_t P_local, int N, int64_t ld, const void* d_lower,
+                      const void* d_upper, uint64_t seed, int64_t P_total, int64_t row0, void* stream);
+
 /* ---- a4: synchronous selection (stochopy/optimize/_common.py:123-160) ----
  * rows with candfun < xfun: xfun = candfun and x = cand  (copy_when = 1), or,
  * for ping-pong populations, rows that do NOT improve are copied from `cand`
@@ -102,6 +106,12 @@ int sp_select_sync(int dtype, int it, int maxiter, double xtol, double ftol, con
 /* first evaluation of a population: xfun given, gbest = x[argmin], no status */
 int sp_best_init(int dtype, const void* d_x, const void* d_xfun, int64_t P, int N, int64_t ld,
                  void* d_gbest, sp_ctrl* d_ctrl, void* d_scratch, void* stream);
+
+/* gbest exchange of a sharded swarm: d_recs = world records of rec_ld scalars,
+ * [fit, x_0 .. x_{N-1}], all-gathered from the ranks; every rank picks the first minimum,
+ * refreshes d_gbest and evaluates the status ladder exactly like selection_sync. */
+int sp_gbest_reduce(int dtype, const void* d_recs, int world, int N, int64_t rec_ld, void* d_gbest, sp_ctrl* d_ctrl,
+                    int it, int maxiter, double xtol, double ftol, void* stream);
 
 /* ---- a6-a10: differential evolution (stochopy/optimize/de/_de.py:314-351,
  * de/_strategy.py, de/_constraints.py).  One call = one synchronous generation:
@@ -159,6 +169,15 @@ typedef struct {
   void* scratch;
   const void* r1;  /* (P x ld) _cpso.py:262 */
   const void* r2;  /* (P x ld) _cpso.py:263 */
+  /* one swarm sharded over GPUs (shard != 0): this rank holds rows [row0, row0 + P) of a
+   * swarm of P_total; draws are keyed by the global row, so the run does not depend on the
+   * GPU count.  The generation kernel then leaves gbest / status alone and writes its
+   * local best [fit, x_0 .. x_{N-1}] into xch for the exchange (sp_gbest_reduce). */
+  int64_t row0;
+  int64_t P_total;
+  void* xch;       /* (ld + 1) */
+  int32_t shard;
+  int32_t pad2_;
 } sp_pso_state;
 int sp_pso_generation(const sp_pso_state* st, int it, void* stream);
 int sp_pso_propose(const sp_pso_state* st, int it, void* stream);
@@ -171,6 +190,10 @@ int sp_pso_propose(const sp_pso_state* st, int it, void* stream);
 int sp_cpso_restart_plan(const sp_pso_state* st, int it, int32_t* d_rank, void* stream);
 int sp_cpso_restart_apply(const sp_pso_state* st, int it, const int32_t* d_rank, const void* d_fresh, void* stream);
 int sp_cpso_restart(const sp_pso_state* st, int it, int32_t* d_rank, void* stream);
+/* the same in pieces for a sharded swarm: local max |X_i - gbest|^2 into ctrl->aux[0]
+ * (the caller max-reduces it over the ranks), then the decision from the global radius */
+int sp_cpso_radius(const sp_pso_state* st, int it, void* stream);
+int sp_cpso_decide(const sp_pso_state* st, int it, void* stream);
 /* enqueue generations it_first .. it_first+n-1 (+ restart when gamma >= 0) */
 int sp_pso_run(const sp_pso_state* st, int it_first, int n, int32_t* d_rank, void* stream);
 

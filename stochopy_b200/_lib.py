@@ -68,6 +68,7 @@ class PsoState(C.Structure):
         ("X", vp), ("V", vp), ("pbest", vp), ("pbestfit", vp), ("pfit", vp), ("gbest", vp),
         ("lower", vp), ("upper", vp), ("ctrl", vp), ("scratch", vp),
         ("r1", vp), ("r2", vp),
+        ("row0", C.c_int64), ("P_total", C.c_int64), ("xch", vp), ("shard", C.c_int32), ("pad2_", C.c_int32),
     ]
 
 
@@ -128,6 +129,8 @@ SIGNATURES = {
     "sp_scratch_bytes": (_i64, []),
     "sp_eval": (_i, [_i, _i, vp, _i64, _i, _i64, vp, vp, vp, vp]),
     "sp_lhs_init": (_i, [_i, vp, _i64, _i, _i64, vp, vp, _u64, vp, vp, vp]),
+    "sp_lhs_init_shard": (_i, [_i, vp, _i64, _i, _i64, vp, vp, _u64, _i64, _i64, vp]),
+    "sp_gbest_reduce": (_i, [_i, vp, _i, _i, _i64, vp, vp, _i, _i, _d, _d, vp]),
     "sp_select_sync": (_i, [_i, _i, _i, _d, _d, vp, vp, vp, vp, _i64, _i, _i64, _i, vp, vp, vp, vp]),
     "sp_best_init": (_i, [_i, vp, vp, _i64, _i, _i64, vp, vp, vp, vp]),
     "sp_de_generation": (_i, [C.POINTER(DeState), _i, vp]),
@@ -138,6 +141,8 @@ SIGNATURES = {
     "sp_cpso_restart_plan": (_i, [C.POINTER(PsoState), _i, vp, vp]),
     "sp_cpso_restart_apply": (_i, [C.POINTER(PsoState), _i, vp, vp, vp]),
     "sp_cpso_restart": (_i, [C.POINTER(PsoState), _i, vp, vp]),
+    "sp_cpso_radius": (_i, [C.POINTER(PsoState), _i, vp]),
+    "sp_cpso_decide": (_i, [C.POINTER(PsoState), _i, vp]),
     "sp_pso_run": (_i, [C.POINTER(PsoState), _i, _i, vp, vp]),
     "sp_random_fill": (_i, [_i, vp, _i64, _i, _i64, _i, _i, _u64, _i, vp]),
     "sp_fitness_rank": (_i, [_i, vp, _i64, vp, vp]),

@@ -177,9 +177,10 @@ de_pool_kernel(const DeArgs<T> a, int nb, const PhiloxKeys keys) {
   __syncthreads();
 
   // ---- phase 1: claim / fetch / process ----------------------------------------------------
-  auto claim = [&]() {
+  const uint32_t s_next_addr = smem_u32(s_next);
+  auto claim = [&]() {  // raw atom.shared: one lane claims, no warp-aggregation preamble
     int r = 0;
-    if (lane == 0) r = atomicAdd(s_next, 1);
+    if (lane == 0) asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(r) : "r"(s_next_addr) : "memory");
     return __shfl_sync(0xffffffffu, r, 0);
   };
   auto issue = [&](int st, int r) {  // one elected lane fills stage `st` with the donors of row r

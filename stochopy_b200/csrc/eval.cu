@@ -39,7 +39,7 @@ int sm_count() {
 template <typename T>
 __global__ void lhs_kernel(T* __restrict__ X, int64_t P, int N, int64_t ld, const T* __restrict__ lower,
                            const T* __restrict__ upper, uint64_t seed, const T* __restrict__ jitter,
-                           const int64_t* __restrict__ perm) {
+                           const int64_t* __restrict__ perm, int64_t Ptot, int64_t row0) {
   constexpr int VEC = Num<T>::VEC;
   const int64_t total = P * (int64_t)N;
   for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
@@ -51,13 +51,13 @@ __global__ void lhs_kernel(T* __restrict__ X, int64_t P, int N, int64_t ld, cons
       p = perm[(int64_t)j * P + i];
       u = jitter[p * ld + j];
     } else {
-      p = lhs_permute((uint32_t)i, (uint32_t)P, (uint32_t)j, seed);
+      p = lhs_permute((uint32_t)(row0 + i), (uint32_t)Ptot, (uint32_t)j, seed);
       T blk[VEC];
       uniform_block(philox4x32((uint32_t)(j / VEC), (uint32_t)p, 0u, kLhsJitter, seed), blk);
       u = blk[j % VEC];
     }
     // linspace(-1, 1, P, endpoint=False)[p] = -1 + p * (2/P)
-    T cell = add_rn(div_rn(u, (T)P), (T)__dadd_rn(__dmul_rn((double)p, 2.0 / (double)P), -1.0));
+    T cell = add_rn(div_rn(u, (T)Ptot), (T)__dadd_rn(__dmul_rn((double)p, 2.0 / (double)Ptot), -1.0));
     T half = mul_rn((T)0.5, sub_rn(upper[j], lower[j]));
     T mid = mul_rn((T)0.5, add_rn(upper[j], lower[j]));
     X[i * ld + j] = add_rn(mul_rn(cell, half), mid);
@@ -108,6 +108,22 @@ best_init_kernel(const T* __restrict__ x, const T* __restrict__ xfun, int64_t P,
   }
   Best top;
   if (grid_best(mine, scratch, ctrl, &top)) finalize_generation<T>(top, x, ld, N, gbest, ctrl, -1, 0, 0.0, 0.0);
+}
+
+// Sharded swarm: every rank holds the records [fit, x_0 .. x_{N-1}] of all ranks' local
+// bests (all-gathered); pick the first minimum (ranks own ascending row ranges, so this
+// is np.argmin's tie rule), then distance to the previous gbest and the status ladder.
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+gbest_reduce_kernel(const T* __restrict__ recs, int world, int N, int64_t rec_ld, T* gbest, sp_ctrl* ctrl, int it,
+                    int maxiter, double xtol, double ftol) {
+  if (!running(ctrl)) return;
+  int best = 0;
+  for (int r = 1; r < world; ++r)
+    if (recs[r * rec_ld] < recs[best * rec_ld]) best = r;
+  // finalize_generation reads the winning row from `xrows + row * ld`
+  Best b{(double)recs[best * rec_ld], (long long)best};
+  finalize_generation<T>(b, recs + 1, rec_ld, N, gbest, ctrl, it, maxiter, xtol, ftol);
 }
 
 template <typename T>
@@ -181,10 +197,43 @@ int sp_lhs_init(int dtype, void* X, int64_t P, int N, int64_t ld, const void* lo
   int grid = (int)((total + 255) / 256 < (int64_t)sm_count() * 8 ? (total + 255) / 256 : (int64_t)sm_count() * 8);
   if (dtype == SP_F32)
     lhs_kernel<float><<<grid, 256, 0, s>>>((float*)X, P, N, ld, (const float*)lower, (const float*)upper, seed,
-                                           (const float*)jitter, perm);
+                                           (const float*)jitter, perm, P, 0);
   else
     lhs_kernel<double><<<grid, 256, 0, s>>>((double*)X, P, N, ld, (const double*)lower, (const double*)upper, seed,
-                                            (const double*)jitter, perm);
+                                            (const double*)jitter, perm, P, 0);
+  SP_CHECK_LAUNCH();
+  return SP_OK;
+}
+
+int sp_lhs_init_shard(int dtype, void* X, int64_t P_local, int N, int64_t ld, const void* lower, const void* upper,
+                      uint64_t seed, int64_t P_total, int64_t row0, void* stream) {
+  SP_CHECK_ARG(X && lower && upper && P_local >= 1 && N >= 1 && ld >= N, "null pointer or bad shape");
+  SP_CHECK_ARG(row0 >= 0 && row0 + P_local <= P_total && P_total < (1LL << 31), "shard outside the population");
+  SP_CHECK_ARG(dtype == SP_F32 || dtype == SP_F64, "dtype");
+  cudaStream_t s = (cudaStream_t)stream;
+  int64_t total = P_local * (int64_t)N;
+  int grid = (int)((total + 255) / 256 < (int64_t)sm_count() * 8 ? (total + 255) / 256 : (int64_t)sm_count() * 8);
+  if (dtype == SP_F32)
+    lhs_kernel<float><<<grid, 256, 0, s>>>((float*)X, P_local, N, ld, (const float*)lower, (const float*)upper, seed,
+                                           nullptr, nullptr, P_total, row0);
+  else
+    lhs_kernel<double><<<grid, 256, 0, s>>>((double*)X, P_local, N, ld, (const double*)lower, (const double*)upper,
+                                            seed, nullptr, nullptr, P_total, row0);
+  SP_CHECK_LAUNCH();
+  return SP_OK;
+}
+
+int sp_gbest_reduce(int dtype, const void* recs, int world, int N, int64_t rec_ld, void* gbest, sp_ctrl* ctrl, int it,
+                    int maxiter, double xtol, double ftol, void* stream) {
+  SP_CHECK_ARG(recs && gbest && ctrl && world >= 1 && N >= 1 && rec_ld >= N + 1, "null pointer or bad shape");
+  SP_CHECK_ARG(dtype == SP_F32 || dtype == SP_F64, "dtype");
+  cudaStream_t s = (cudaStream_t)stream;
+  if (dtype == SP_F32)
+    gbest_reduce_kernel<float><<<1, kThreads, 0, s>>>((const float*)recs, world, N, rec_ld, (float*)gbest, ctrl, it,
+                                                      maxiter, xtol, ftol);
+  else
+    gbest_reduce_kernel<double><<<1, kThreads, 0, s>>>((const double*)recs, world, N, rec_ld, (double*)gbest, ctrl, it,
+                                                       maxiter, xtol, ftol);
   SP_CHECK_LAUNCH();
   return SP_OK;
 }

@@ -28,6 +28,9 @@ struct PsoArgs {
   Best* scratch;
   const T* r1;
   const T* r2;
+  int64_t row0, P_total;  // sharded swarm: global index of local row 0, whole swarm size
+  T* xch;                  // shard mode: [fit, x_0..x_{N-1}] of the local best for the exchange
+  int shard;
 };
 
 template <typename T, int CH, int LPR, bool PHILOX>
@@ -63,8 +66,8 @@ pso_generation_kernel(const PsoArgs<T> a) {
         const int j0 = TL::col(c, l, 0);
         T r1[VEC], r2[VEC];
         if (PHILOX) {
-          uniform_block(philox4x32((uint32_t)(j0 / VEC), (uint32_t)row, (uint32_t)a.it, kPsoR1, a.seed), r1);
-          uniform_block(philox4x32((uint32_t)(j0 / VEC), (uint32_t)row, (uint32_t)a.it, kPsoR2, a.seed), r2);
+          uniform_block(philox4x32((uint32_t)(j0 / VEC), (uint32_t)(a.row0 + row), (uint32_t)a.it, kPsoR1, a.seed), r1);
+          uniform_block(philox4x32((uint32_t)(j0 / VEC), (uint32_t)(a.row0 + row), (uint32_t)a.it, kPsoR2, a.seed), r2);
         } else {
 #pragma unroll
           for (int e = 0; e < VEC; ++e) {
@@ -132,8 +135,15 @@ pso_generation_kernel(const PsoArgs<T> a) {
   }
   if (a.propose_only) return;
   Best top;
-  if (grid_best(mine, a.scratch, a.ctrl, &top))
-    finalize_generation<T>(top, a.pbest, a.ld, a.N, a.gbest, a.ctrl, a.it, a.maxiter, a.xtol, a.ftol);
+  if (grid_best(mine, a.scratch, a.ctrl, &top)) {
+    if (a.shard) {  // local best -> exchange record; gbest/status come from sp_gbest_reduce on every rank
+      const T* src = a.pbest + top.row * a.ld;
+      for (int j = threadIdx.x; j < a.N; j += blockDim.x) a.xch[1 + j] = src[j];
+      if (threadIdx.x == 0) a.xch[0] = (T)top.f;
+    } else {
+      finalize_generation<T>(top, a.pbest, a.ld, a.N, a.gbest, a.ctrl, a.it, a.maxiter, a.xtol, a.ftol);
+    }
+  }
 }
 
 // ---- competitive restart, _cpso.py:405-426 ------------------------------------
@@ -165,7 +175,7 @@ radius_kernel(const T* __restrict__ X, const T* __restrict__ gbest, int64_t P, i
 }
 
 // (2) decision: radius < delta -> nw rows to reset (ctrl->flag), ctrl->aux[1] = radius
-__global__ void restart_plan_kernel(sp_ctrl* ctrl, int64_t P, int N, int it, int maxiter, double gamma, double delta) {
+__global__ void restart_plan_kernel(sp_ctrl* ctrl, int64_t P, int N, int it, int maxiter, double gamma, double delta) {  // P = whole swarm
   if (!running(ctrl)) {
     ctrl->flag = 0;
     return;
@@ -187,7 +197,7 @@ template <typename T>
 __global__ void __launch_bounds__(kThreads)
 restart_apply_kernel(T* X, T* V, T* pbest, T* pbestfit, const int32_t* __restrict__ rank, const T* __restrict__ lower,
                      const T* __restrict__ upper, int64_t P, int N, int64_t ld, int it, uint64_t seed,
-                     const T* __restrict__ fresh, const sp_ctrl* ctrl) {
+                     const T* __restrict__ fresh, const sp_ctrl* ctrl, int64_t Ptot, int64_t row0) {
   constexpr int VEC = Num<T>::VEC;
   const int nw = ctrl->flag;
   if (nw <= 0) return;
@@ -196,13 +206,13 @@ restart_apply_kernel(T* X, T* V, T* pbest, T* pbestfit, const int32_t* __restric
     const int64_t i = t / N;
     const int j = (int)(t - i * N);
     const int64_t r = rank[i];
-    if (r < P - nw) continue;
+    if (r < Ptot - nw) continue;
     T val;
     if (fresh != nullptr) {
-      val = fresh[(P - 1 - r) * ld + j];  // reset order: worst first (argsort()[:-nw-1:-1])
+      val = fresh[(Ptot - 1 - r) * ld + j];  // reset order: worst first (argsort()[:-nw-1:-1])
     } else {
       T blk[VEC];
-      uniform_block(philox4x32((uint32_t)(j / VEC), (uint32_t)i, (uint32_t)it, kPsoRestart, seed), blk);
+      uniform_block(philox4x32((uint32_t)(j / VEC), (uint32_t)(row0 + i), (uint32_t)it, kPsoRestart, seed), blk);
       val = add_rn(lower[j], mul_rn(sub_rn(upper[j], lower[j]), blk[j % VEC]));
     }
     X[i * ld + j] = val;
@@ -246,6 +256,10 @@ static int pso_launch(const sp_pso_state* st, int it, int propose_only, cudaStre
   a.scratch = (Best*)st->scratch;
   a.r1 = (const T*)st->r1;
   a.r2 = (const T*)st->r2;
+  a.row0 = st->shard ? st->row0 : 0;
+  a.P_total = st->shard ? st->P_total : st->P;
+  a.xch = (T*)st->xch;
+  a.shard = st->shard;
   const bool philox = st->r1 == nullptr;
   const int grid = grid_for_rows(st->P, sh.lpr, sh.ch >= 4 ? 2 : 4);
 #define SP_CALL(TT, C, L)                                                         \
@@ -270,6 +284,8 @@ static int pso_check(const sp_pso_state* st, int it) {
                "null buffer");
   SP_CHECK_ARG(st->constraint == SP_CONS_NONE || (st->lower && st->upper), "bounds needed for Shrink");
   SP_CHECK_ARG((st->r1 == nullptr) == (st->r2 == nullptr), "r1 and r2 must come together");
+  SP_CHECK_ARG(!st->shard || (st->xch && st->r1 == nullptr && st->row0 >= 0 && st->row0 + st->P <= st->P_total),
+               "shard mode needs the exchange record, in-kernel draws and a row range inside the swarm");
   SP_CHECK_ARG(it >= 2, "generation index starts at 2 (_cpso.py:256-258)");
   return SP_OK;
 }
@@ -294,7 +310,7 @@ static int restart_apply_launch(const sp_pso_state* st, int it, const int32_t* r
   int64_t need = (total + 255) / 256, cap = (int64_t)sm_count() * 8;
   restart_apply_kernel<T><<<(int)(need < cap ? need : cap), 256, 0, s>>>(
       (T*)st->X, (T*)st->V, (T*)st->pbest, (T*)st->pbestfit, rank, (const T*)st->lower, (const T*)st->upper, st->P,
-      st->N, st->ld, it, st->seed, (const T*)fresh, st->ctrl);
+      st->N, st->ld, it, st->seed, (const T*)fresh, st->ctrl, st->shard ? st->P_total : st->P, st->shard ? st->row0 : 0);
   SP_CHECK_LAUNCH();
   return SP_OK;
 }
@@ -327,6 +343,28 @@ int sp_cpso_restart_plan(const sp_pso_state* st, int it, int32_t* rank, void* st
   SP_CHECK_ARG(rank != nullptr && st->lower && st->upper && st->gamma >= 0.0, "rank scratch, bounds, competitivity");
   return st->dtype == SP_F32 ? restart_plan_launch<float>(st, it, rank, (cudaStream_t)stream)
                              : restart_plan_launch<double>(st, it, rank, (cudaStream_t)stream);
+}
+
+int sp_cpso_radius(const sp_pso_state* st, int it, void* stream) {
+  int rc = pso_check(st, it);
+  if (rc) return rc;
+  cudaStream_t s = (cudaStream_t)stream;
+  const int grid = grid_for_rows(st->P, 32, 8);
+  if (st->dtype == SP_F32)
+    radius_kernel<float><<<grid, kThreads, 0, s>>>((const float*)st->X, (const float*)st->gbest, st->P, st->N, st->ld, st->ctrl);
+  else
+    radius_kernel<double><<<grid, kThreads, 0, s>>>((const double*)st->X, (const double*)st->gbest, st->P, st->N, st->ld, st->ctrl);
+  SP_CHECK_LAUNCH();
+  return SP_OK;
+}
+
+int sp_cpso_decide(const sp_pso_state* st, int it, void* stream) {
+  int rc = pso_check(st, it);
+  if (rc) return rc;
+  restart_plan_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(st->ctrl, st->shard ? st->P_total : st->P, st->N, it,
+                                                         st->maxiter, st->gamma, st->delta);
+  SP_CHECK_LAUNCH();
+  return SP_OK;
 }
 
 int sp_cpso_restart_apply(const sp_pso_state* st, int it, const int32_t* rank, const void* fresh, void* stream) {

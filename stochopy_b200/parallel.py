@@ -1,0 +1,210 @@
+"""Multi-GPU use of the engine, one process per GPU.
+
+Two ways the population path spreads over GPUs:
+
+* ``minimize_seeds``: independent restarts / seeds.  Each rank runs its share of the
+  seeds on its own GPU with no data-path collective; one all-gather of
+  ``(fun, x[N])`` per seed at the end, then a local argmin (NCCL has no MINLOC).
+  This is what ``bench.py --gpus N`` scales.
+* ``cpso_sharded``: ONE swarm row-sharded over the ranks (reference analogue: the mpi
+  backend that splits a population's evaluation over ranks, ``_common.py:53-72``).
+  Per generation the ranks exchange their local best ``[fit, x]`` (N+1 scalars,
+  latency bound) and every rank reduces them with ``sp_gbest_reduce``; the
+  competitive restart needs a max-reduce of the swarm radius and the global rank of
+  ``pbestfit``.  Draws are Philox keyed by the *global* row index, so a sharded run is
+  identical, bit for bit, to the single-GPU run of the same seed.
+
+``torch.distributed`` (NCCL on GPUs, gloo in the CPU tests of the host logic) is the
+plumbing; the collectives carry device tensors.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+__all__ = ["shard_range", "shard_seeds", "reduce_best", "minimize_seeds", "cpso_sharded"]
+
+
+def _all_gather_flat(out, part, group):
+    """out (world * k) <- concatenation of every rank's `part` (k); list form on gloo."""
+    if dist.get_backend(group) == "nccl":
+        dist.all_gather_into_tensor(out, part, group=group)
+    else:
+        world = dist.get_world_size(group)
+        chunks = list(out.view(world, -1).unbind(0))
+        dist.all_gather(chunks, part, group=group)
+
+
+def shard_range(total, rank, world):
+    """Contiguous, balanced [start, stop) of `total` items for `rank` (first ranks get the extras)."""
+    q, r = divmod(int(total), int(world))
+    start = rank * q + min(rank, r)
+    return start, start + q + (1 if rank < r else 0)
+
+
+def shard_seeds(seeds, rank, world):
+    """Seeds handled by `rank`: contiguous blocks in seed order."""
+    seeds = list(seeds)
+    a, b = shard_range(len(seeds), rank, world)
+    return seeds[a:b]
+
+
+def reduce_best(funs, xs, group=None, device=None):
+    """All-gather per-seed results and pick the best on every rank.
+
+    funs: (k,) local objective values, xs: (k, N) local solutions (k may differ by rank).
+    Returns (best_fun, best_x, all_funs) with ties resolved to the lowest global seed
+    position, like np.argmin."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    funs = np.atleast_1d(np.asarray(funs, dtype=np.float64))
+    xs = np.atleast_2d(np.asarray(xs, dtype=np.float64))
+    if world == 1:
+        b = int(np.argmin(funs))
+        return float(funs[b]), xs[b].copy(), funs.copy()
+    device = device or (torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else "cpu")
+    n = xs.shape[1]
+    counts = torch.zeros(world, dtype=torch.int64, device=device)
+    counts[rank] = len(funs)
+    dist.all_reduce(counts, group=group)
+    kmax = int(counts.max().item())
+    rec = torch.full((kmax, n + 1), float("inf"), dtype=torch.float64, device=device)
+    rec[: len(funs), 0] = torch.from_numpy(funs).to(device)
+    rec[: len(funs), 1:] = torch.from_numpy(xs).to(device)
+    out = torch.empty((world, kmax, n + 1), dtype=torch.float64, device=device)
+    _all_gather_flat(out.view(-1), rec.view(-1), group)
+    out = out.cpu().numpy()
+    rows = np.concatenate([out[r, : int(counts[r].item())] for r in range(world)], axis=0)
+    b = int(np.argmin(rows[:, 0]))
+    return float(rows[b, 0]), rows[b, 1:].copy(), rows[:, 0].copy()
+
+
+def minimize_seeds(fun, bounds, seeds, method="de", options=None, group=None, runner=None):
+    """Run one optimisation per seed, seeds sharded over the ranks; returns the best
+    OptimizeResult-like dict plus every seed's final value (identical on all ranks)."""
+    from .optimize import minimize
+
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    runner = runner or (lambda seed: minimize(fun, bounds, method=method, options=dict(options or {}, seed=seed)))
+    mine = [runner(s) for s in shard_seeds(seeds, rank, world)]
+    n = len(bounds)
+    funs = [r["fun"] for r in mine]
+    xs = [r["x"] for r in mine] if mine else np.empty((0, n))
+    best_fun, best_x, all_funs = reduce_best(funs, xs, group)
+    return dict(x=best_x, fun=best_fun, funs=all_funs, seeds=list(seeds), local=mine)
+
+
+def cpso_sharded(fun, bounds, maxiter=100, popsize=10, inertia=0.7298, cognitivity=1.49618, sociability=1.49618,
+                 competitivity=1.0, seed=None, xtol=1.0e-8, ftol=1.0e-8, constraints=None, dtype="float64",
+                 group=None):
+    """One (C)PSO swarm of `popsize` particles row-sharded over the process group.
+
+    Same algorithm, options and result as ``optimize.cpso`` (reference
+    ``cpso/_cpso.py:182-321``, synchronous); device objectives only; every rank returns
+    the same result.  With world size 1 it is exactly ``optimize.cpso``'s Philox path."""
+    from . import _lib as L
+    from .optimize._common import Engine, device_objective, fresh_seed, messages
+    from .optimize._helpers import OptimizeResult
+
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    obj = device_objective(fun, ())
+    if obj is None:
+        raise ValueError("cpso_sharded needs one of the factory objectives")
+    cons = {None: L.CONS_NONE, "Shrink": L.CONS_SHRINK}[constraints]
+    if seed is None:
+        raise ValueError("a sharded swarm needs an explicit seed (all ranks must draw the same stream)")
+
+    eng = Engine(dtype)
+    bounds = np.asarray(bounds, dtype=np.float64)
+    N, Ptot = len(bounds), int(popsize)
+    row0, row1 = shard_range(Ptot, rank, world)
+    P = row1 - row0
+    if P < 1:
+        raise ValueError("more ranks than particles")
+    lower, upper = bounds[:, 0].copy(), bounds[:, 1].copy()
+    restart = bool(competitivity)
+    ld = eng.ld(N)
+    X, V, pbest = eng.rows(P, N), eng.rows(P, N), eng.rows(P, N)
+    pbestfit, pfit = eng.empty(P), eng.empty(P)
+    gbest = eng.zeros(ld)
+    d_lower, d_upper = eng.upload_vec(lower, ld), eng.upload_vec(upper, ld)
+    ctrl, scratch = eng.new_ctrl()
+    rec_ld = ld + 2  # [fit, x_0..x_{N-1}] padded
+    xch = eng.zeros(rec_ld)
+    recs = eng.zeros(world, rec_ld)
+    rank_all = eng.zeros(Ptot, dtype=torch.int32)
+    fit_all = eng.zeros(Ptot)
+
+    st = L.PsoState()
+    st.dtype, st.objective, st.constraint = eng.sp_dt, obj, cons
+    st.P, st.N, st.maxiter, st.ld = P, N, int(maxiter), ld
+    st.w, st.c1, st.c2 = float(inertia), float(cognitivity), float(sociability)
+    st.xtol, st.ftol = float(xtol), float(ftol)
+    st.gamma = float(competitivity) if restart else -1.0
+    st.delta = float(np.log(1.0 + 0.003 * Ptot) / np.max((0.2, np.log(0.01 * maxiter)))) if restart else 0.0
+    st.seed = fresh_seed(seed)
+    st.X, st.V, st.pbest = X.data_ptr(), V.data_ptr(), pbest.data_ptr()
+    st.pbestfit, st.pfit, st.gbest = pbestfit.data_ptr(), pfit.data_ptr(), gbest.data_ptr()
+    st.lower, st.upper = d_lower.data_ptr(), d_upper.data_ptr()
+    st.ctrl, st.scratch = ctrl.data_ptr(), scratch.data_ptr()
+    st.row0, st.P_total, st.xch, st.shard = row0, Ptot, xch.data_ptr(), 1
+
+    def exchange(it):
+        """all-gather the local bests, reduce on every rank (status from the global best)."""
+        if world > 1:
+            _all_gather_flat(recs.view(-1), xch, group)
+        else:
+            recs[0].copy_(xch)
+        L.call("sp_gbest_reduce", eng.sp_dt, recs.data_ptr(), world, N, rec_ld, gbest.data_ptr(), ctrl.data_ptr(), it,
+               int(maxiter), float(xtol), float(ftol), eng.stream)
+
+    L.call("sp_lhs_init_shard", eng.sp_dt, X.data_ptr(), P, N, ld, st.lower, st.upper, st.seed, Ptot, row0, eng.stream)
+    pbest.copy_(X)
+    L.call("sp_eval", obj, eng.sp_dt, X.data_ptr(), P, N, ld, None, None, pbestfit.data_ptr(), eng.stream)
+    pfit.copy_(pbestfit)
+    # initial best: local argmin -> record -> exchange (no status test: it = -1)
+    b = int(torch.argmin(pbestfit).item())
+    xch[0] = pbestfit[b]
+    xch[1:1 + N] = X[b, :N]
+    exchange(-1)
+
+    ctrl64 = ctrl.view(torch.float64)  # aux[0] (local max squared radius) sits at byte 40
+    it = 1
+    c = eng.read_ctrl(ctrl)
+    while c.status == L.SP_RUNNING:
+        it += 1
+        L.call("sp_pso_generation", C.byref(st), it, eng.stream)
+        exchange(it)
+        c = eng.read_ctrl(ctrl)
+        if c.status == L.SP_RUNNING and restart:  # _cpso.py:304-307, 405-426
+            L.call("sp_cpso_radius", C.byref(st), it, eng.stream)
+            if world > 1:
+                dist.all_reduce(ctrl64[5:6], op=dist.ReduceOp.MAX, group=group)
+            L.call("sp_cpso_decide", C.byref(st), it, eng.stream)
+            if eng.read_ctrl(ctrl).flag > 0:
+                if world > 1:
+                    counts = [shard_range(Ptot, r, world) for r in range(world)]
+                    if len({b - a for a, b in counts}) == 1:
+                        _all_gather_flat(fit_all, pbestfit, group)
+                    else:
+                        parts = [eng.empty(b - a) for a, b in counts]
+                        dist.all_gather(parts, pbestfit, group=group)
+                        fit_all.copy_(torch.cat(parts))
+                else:
+                    fit_all.copy_(pbestfit)
+                L.call("sp_fitness_rank", eng.sp_dt, fit_all.data_ptr(), Ptot, rank_all.data_ptr(), eng.stream)
+                L.call("sp_cpso_restart_apply", C.byref(st), it, rank_all[row0:].data_ptr(), None, eng.stream)
+
+    it = c.nit
+    return OptimizeResult(
+        x=gbest[:N].to("cpu").numpy().astype(np.float64),
+        success=c.status >= 0,
+        status=int(c.status),
+        message=messages[int(c.status)],
+        fun=float(c.gfit),
+        nfev=it * Ptot,
+        nit=it,
+    )

@@ -1,0 +1,103 @@
+"""Multi-rank logic.  CPU: world_size-2 gloo tests of the host side
+(seed sharding, final min-loc gather).  GPU: a 2-rank sharded swarm on one device over
+gloo must equal the single-process run bit for bit (draws are keyed by global rows)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from stochopy_b200 import parallel
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _spawn(fn, world, *args):
+    port = _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.SimpleQueue()
+    procs = [ctx.Process(target=_entry, args=(fn, r, world, port, q) + args) for r in range(world)]
+    for p in procs:
+        p.start()
+    out = [q.get() for _ in range(world)]
+    for p in procs:
+        p.join(60)
+    errs = [o for o in out if isinstance(o, str)]
+    assert not errs, errs
+    return sorted(out, key=lambda o: o[0])
+
+
+def _entry(fn, rank, world, port, q, *args):
+    try:
+        os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+        q.put((rank, fn(rank, world, *args)))
+        dist.destroy_process_group()
+    except Exception as e:  # pragma: no cover
+        import traceback
+
+        q.put(f"rank {rank}: {e}\n{traceback.format_exc()}")
+
+
+def test_shard_range_covers_everything():
+    for total in (1, 7, 8, 64, 65536, 100003):
+        for world in (1, 2, 3, 8):
+            spans = [parallel.shard_range(total, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == total
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [b - a for a, b in spans]
+            assert max(sizes) - min(sizes) <= 1
+    assert parallel.shard_seeds(range(5), 1, 2) == [3, 4] and parallel.shard_seeds(range(5), 0, 2) == [0, 1, 2]
+
+
+def _fake_run(rank, world, seeds):
+    # objective value and solution are a pure function of the seed: every rank must agree on the winner
+    def runner(seed):
+        rs = np.random.RandomState(seed)
+        return dict(fun=float(rs.uniform(0, 10)), x=rs.uniform(-1, 1, 4))
+
+    r = parallel.minimize_seeds(None, [[-1, 1]] * 4, seeds, runner=runner)
+    return r["fun"], r["x"].tolist(), r["funs"].tolist(), len(r["local"])
+
+
+@pytest.mark.parametrize("nseeds", [1, 5, 8])
+def test_minimize_seeds_gloo_world2(nseeds):
+    seeds = list(range(100, 100 + nseeds))
+    out = _spawn(_fake_run, 2, seeds)
+    want = [np.random.RandomState(s).uniform(0, 10) for s in seeds]
+    for rank, (fun, x, funs, nlocal) in out:
+        assert np.allclose(funs, want) and np.isclose(fun, min(want))
+        rs = np.random.RandomState(seeds[int(np.argmin(want))])
+        rs.uniform(0, 10)
+        assert np.allclose(x, rs.uniform(-1, 1, 4))
+    assert sum(o[1][3] for o in out) == nseeds
+
+
+def _sharded(rank, world, opts):
+    import stochopy_b200 as sb
+
+    torch.cuda.set_device(0)
+    r = parallel.cpso_sharded(sb.factory.styblinski_tang, [[-5.12, 5.12]] * 10, **opts)
+    return r.x.tolist(), r.fun, r.nit, r.status
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("opts", [dict(competitivity=None, constraints="Shrink"), dict(competitivity=1.0),
+                                  dict(competitivity=1.2, dtype="float32")])
+def test_sharded_swarm_equals_single_process(opts):
+    import stochopy_b200 as sb
+
+    o = dict(opts, maxiter=60, popsize=101, seed=11)
+    one = sb.optimize.minimize(sb.factory.styblinski_tang, [[-5.12, 5.12]] * 10, method="cpso",
+                               options=dict(o, updating="deferred"))
+    solo = parallel.cpso_sharded(sb.factory.styblinski_tang, [[-5.12, 5.12]] * 10, **o)
+    assert np.array_equal(solo.x, one.x) and solo.fun == one.fun and (solo.nit, solo.status) == (one.nit, one.status)
+    for rank, (x, fun, nit, status) in _spawn(_sharded, 2, o):  # two ranks, odd split 51 + 50
+        assert np.array_equal(np.array(x), one.x) and fun == one.fun and (nit, status) == (one.nit, one.status)
