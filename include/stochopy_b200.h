@@ -214,7 +214,10 @@ int sp_fitness_rank(int dtype, const void* d_fit, int64_t P, int32_t* d_rank, vo
  * (_cmaes.py:303); eigenvalues ascending into d_w (N), eigenvectors into the
  * columns of d_B (N x N).  Cyclic one-sided Jacobi on the device; every
  * eigenvector is normalised so that its largest-magnitude component is positive
- * (LAPACK's sign is implementation defined).  d_work: 2*N*N scalars. */
+ * (LAPACK's sign is implementation defined).  One CTA with the problem in shared memory
+ * when 2 N^2 scalars fit, otherwise a cooperative multi-CTA kernel (one pair per warp,
+ * grid barriers between rounds).  d_work: sp_sym_eigh_work_scalars(N) scalars. */
+int64_t sp_sym_eigh_work_scalars(int N);
 int sp_sym_eigh(int dtype, void* d_C, int N, void* d_w, void* d_B, void* d_work, void* stream);
 
 /* ---- a15-a17: (mu,lambda)-CMA-ES generation (stochopy/optimize/cmaes/_cmaes.py:228-343,

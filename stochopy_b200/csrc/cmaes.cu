@@ -33,8 +33,8 @@ struct CmaPtrs {
   // workspace slices
   __host__ __device__ T* mean_part() const { return work; }                                  // kMeanChunks * N
   __host__ __device__ T* cov_part() const { return work + (size_t)kMeanChunks * N; }          // kCovSplits * N * N
-  __host__ __device__ T* jac() const { return cov_part() + (size_t)kCovSplits * N * N; }      // 2 * N * N
-  __host__ __device__ T* vec() const { return jac() + 2 * (size_t)N * N; }                    // 8 * N (diff, coef, ...)
+  __host__ __device__ T* jac() const { return cov_part() + (size_t)kCovSplits * N * N; }      // 2 N^2 + N + 64
+  __host__ __device__ T* vec() const { return jac() + 2 * (size_t)N * N + N + 64; }           // 8 * N (diff, coef, ...)
   __host__ __device__ T* sorted() const { return vec() + 8 * (size_t)N; }                     // P (Penalize percentiles)
 };
 
@@ -303,10 +303,9 @@ static int cma_update(const sp_cma_state* st, int it, cudaStream_t s) {
   const CmaPtrs<T> a = cma_ptrs<T>(st, it);
   const int N = st->N, tiles = cdiv(N, kGemmTile);
   const int64_t P = st->P;
-  const int rank_grid = cdiv(P, kThreads);
   if (st->constraint == SP_CONS_PENALIZE) {
-    rank_kernel<T><<<rank_grid, kThreads, 0, s>>>(a.arfit, P, a.rank, nullptr);
-    SP_CHECK_LAUNCH();
+    if (rank_launch<T>(a.arfit, P, a.rank, nullptr, s) != cudaSuccess) return SP_ERR_CUDA;
+    g_launches.fetch_add(2);
     scatter_sorted_kernel<T><<<cdiv(P, 256) < 1024 ? cdiv(P, 256) : 1024, 256, 0, s>>>(a.arfit, a.rank, a.sorted(), P, st->ctrl);
     SP_CHECK_LAUNCH();
     cma_penalty_state_kernel<T><<<1, 256, 0, s>>>(a);
@@ -315,8 +314,8 @@ static int cma_update(const sp_cma_state* st, int it, cudaStream_t s) {
         a.arx, a.vec() + 2 * N, a.arfit, P, N, st->ld, st->ctrl);
     SP_CHECK_LAUNCH();
   }
-  rank_kernel<T><<<rank_grid, kThreads, 0, s>>>(a.arfit, P, a.rank, nullptr);
-  SP_CHECK_LAUNCH();
+  if (rank_launch<T>(a.arfit, P, a.rank, nullptr, s) != cudaSuccess) return SP_ERR_CUDA;
+  g_launches.fetch_add(2);
   cma_mean_partial_kernel<T><<<kMeanChunks, 256, 0, s>>>(a);
   SP_CHECK_LAUNCH();
   cma_paths_kernel<T><<<1, 256, 0, s>>>(a);
@@ -360,7 +359,7 @@ using namespace sp;
 extern "C" {
 
 int64_t sp_cma_work_scalars(int N, int64_t P) {
-  return (int64_t)kMeanChunks * N + (int64_t)kCovSplits * N * N + 2LL * N * N + 8LL * N + P;
+  return (int64_t)kMeanChunks * N + (int64_t)kCovSplits * N * N + 2LL * N * N + 9LL * N + 64 + P;
 }
 
 #define SP_CMA_PHASE(NAME, FN)                                                     \

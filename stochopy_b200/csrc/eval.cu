@@ -290,15 +290,20 @@ int sp_fitness_rank(int dtype, const void* fit, int64_t P, int32_t* rank, void* 
   SP_CHECK_ARG(fit && rank && P >= 1 && P < (1LL << 31), "null pointer or bad popsize");
   SP_CHECK_ARG(dtype == SP_F32 || dtype == SP_F64, "dtype");
   cudaStream_t s = (cudaStream_t)stream;
-  const int grid = (int)((P + kThreads - 1) / kThreads);
-  if (dtype == SP_F32) rank_kernel<float><<<grid, kThreads, 0, s>>>((const float*)fit, P, rank, nullptr);
-  else rank_kernel<double><<<grid, kThreads, 0, s>>>((const double*)fit, P, rank, nullptr);
-  SP_CHECK_LAUNCH();
+  cudaError_t e = dtype == SP_F32 ? rank_launch<float>((const float*)fit, P, rank, nullptr, s)
+                                  : rank_launch<double>((const double*)fit, P, rank, nullptr, s);
+  if (e != cudaSuccess) {
+    set_error("sp_fitness_rank: %s", cudaGetErrorString(e));
+    return SP_ERR_CUDA;
+  }
+  g_launches.fetch_add(2);
   return SP_OK;
 }
 
+int64_t sp_sym_eigh_work_scalars(int N) { return (int64_t)jacobi_work_scalars(N); }
+
 int sp_sym_eigh(int dtype, void* C, int N, void* w, void* B, void* work, void* stream) {
-  SP_CHECK_ARG(C && w && B && work && N >= 1 && N <= 1024, "null pointer or N outside [1, 1024]");
+  SP_CHECK_ARG(C && w && B && work && N >= 1 && N <= 1024, "null pointer or N outside [1, 1024]");  // work: sp_sym_eigh_work_scalars(N)
   SP_CHECK_ARG(dtype == SP_F32 || dtype == SP_F64, "dtype");
   cudaStream_t s = (cudaStream_t)stream;
   cudaError_t e = dtype == SP_F32

@@ -3,6 +3,8 @@
 // CMA-ES matrices are N x N with N <= ~1024 and the GEMMs are <= 1 GFLOP, fp64 by
 // default (tcgen05 has no f64 kind), so these are CUDA-core DFMA/FFMA kernels.
 #pragma once
+#include <cooperative_groups.h>
+
 #include "common.cuh"
 
 namespace sp {
@@ -267,24 +269,175 @@ jacobi_eigh_kernel(T* __restrict__ C, int N, T* __restrict__ w_out, T* __restric
   }
 }
 
+// Multi-CTA variant for matrices that do not fit one SM's shared memory: the N/2 pairs of
+// a round are spread over the warps of a cooperative grid (one pair per warp), W and Q
+// live in global memory (L2 resident, 2 N^2 scalars), rounds are separated by grid-wide
+// barriers.  Same rotations, ordering, warm start, sorting and sign rule as above.
+// scratch: W, Q (2 N^2), lam (N), sweep flags (64 x 4 bytes).
+template <typename T>
+__global__ void __launch_bounds__(256)
+jacobi_grid_kernel(T* __restrict__ C, int N, T* __restrict__ w_out, T* __restrict__ B, T* __restrict__ W,
+                   T* __restrict__ Q, T* __restrict__ lam, unsigned int* __restrict__ off, int warm,
+                   const int* __restrict__ gate, const int* __restrict__ status_gate, int* __restrict__ sweeps_out) {
+  namespace cg = cooperative_groups;
+  cg::grid_group grid = cg::this_grid();
+  if (gate != nullptr && *gate == 0) return;  // uniform over the grid: nobody reaches a barrier
+  if (status_gate != nullptr && *status_gate != SP_RUNNING) return;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int gthreads = gridDim.x * blockDim.x, gtid = blockIdx.x * blockDim.x + tid;
+  const int gwarp = gtid >> 5, gwarps = gthreads >> 5;
+
+  for (int e = gtid; e < N * N; e += gthreads) {  // C = triu(C) + triu(C,1)^T (_cmaes.py:303)
+    const int r = e / N, c = e - r * N;
+    if (r > c) C[e] = C[c * N + r];
+  }
+  if (gtid < 64) off[gtid] = 0u;
+  grid.sync();
+  if (warm) {
+    for (int e = gtid; e < N * N; e += gthreads) {
+      const int j = e / N, r = e - j * N;
+      Q[e] = B[r * N + j];
+    }
+    grid.sync();
+    for (int e = gtid; e < N * N; e += gthreads) {  // W = Q C
+      const int j = e / N, c = e - j * N;
+      T acc = 0;
+      for (int k = 0; k < N; ++k) acc += Q[j * N + k] * C[k * N + c];
+      W[e] = acc;
+    }
+  } else {
+    for (int e = gtid; e < N * N; e += gthreads) {
+      const int r = e / N, c = e - r * N;
+      W[e] = C[e];
+      Q[e] = r == c ? T(1) : T(0);
+    }
+  }
+  grid.sync();
+
+  const T tol = T(4) * JacobiEps<T>::eps() * sqrt((T)(N < 16 ? 16 : N));
+  const int n = N + (N & 1), half = n / 2;
+  int sweep = 0;
+  for (; sweep < 60; ++sweep) {
+    for (int r = 0; r < n - 1; ++r) {
+      for (int i = gwarp; i < half; i += gwarps) {
+        int p, q;
+        if (i == 0) {
+          p = n - 1;
+          q = r;
+        } else {
+          p = (r + i) % (n - 1);
+          q = (r - i + (n - 1)) % (n - 1);
+        }
+        if (p >= N || q >= N) continue;
+        T* wp = W + (size_t)p * N;
+        T* wq = W + (size_t)q * N;
+        T al = 0, be = 0, ga = 0;
+        for (int k = lane; k < N; k += 32) {
+          const T a = wp[k], b = wq[k];
+          al += a * a;
+          be += b * b;
+          ga += a * b;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          al += __shfl_xor_sync(0xffffffffu, al, o);
+          be += __shfl_xor_sync(0xffffffffu, be, o);
+          ga += __shfl_xor_sync(0xffffffffu, ga, o);
+        }
+        if (fabs(ga) > tol * sqrt(al * be) && al > T(0) && be > T(0)) {
+          if (lane == 0) off[sweep] = 1u;
+          const T zeta = (be - al) / (T(2) * ga);
+          const T t = (zeta >= T(0) ? T(1) : T(-1)) / (fabs(zeta) + sqrt(T(1) + zeta * zeta));
+          const T cs = T(1) / sqrt(T(1) + t * t), sn = cs * t;
+          T* qp = Q + (size_t)p * N;
+          T* qq = Q + (size_t)q * N;
+          for (int k = lane; k < N; k += 32) {
+            const T a = wp[k], b = wq[k];
+            wp[k] = cs * a - sn * b;
+            wq[k] = sn * a + cs * b;
+            const T c = qp[k], d = qq[k];
+            qp[k] = cs * c - sn * d;
+            qq[k] = sn * c + cs * d;
+          }
+        }
+      }
+      grid.sync();
+    }
+    if (*reinterpret_cast<volatile unsigned int*>(&off[sweep]) == 0u) break;
+  }
+  if (gtid == 0 && sweeps_out != nullptr) *sweeps_out = sweep + 1;
+
+  for (int j = gwarp; j < N; j += gwarps) {  // signed eigenvalues
+    T acc = 0;
+    for (int k = lane; k < N; k += 32) acc += W[(size_t)j * N + k] * Q[(size_t)j * N + k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) lam[j] = acc;
+  }
+  grid.sync();
+  for (int j = gwarp; j < N; j += gwarps) {  // ascending stable rank, sign rule, scatter
+    const T mine = lam[j];
+    int rk = 0;
+    for (int k = lane; k < N; k += 32) {
+      const T o = lam[k];
+      rk += (o < mine) || (o == mine && k < j);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) rk += __shfl_xor_sync(0xffffffffu, rk, o);
+    T best = T(-1);
+    int bidx = 0;
+    for (int k = lane; k < N; k += 32) {
+      const T a = fabs(Q[(size_t)j * N + k]);
+      if (a > best) {
+        best = a;
+        bidx = k;
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const T ob = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bidx, o);
+      if (ob > best || (ob == best && oi < bidx)) {
+        best = ob;
+        bidx = oi;
+      }
+    }
+    const T sgn = Q[(size_t)j * N + bidx] < T(0) ? T(-1) : T(1);
+    if (lane == 0) w_out[rk] = mine;
+    for (int k = lane; k < N; k += 32) B[(size_t)k * N + rk] = sgn * Q[(size_t)j * N + k];
+  }
+}
+
+// scratch scalars needed behind `work` for an N x N decomposition
+inline size_t jacobi_work_scalars(int N) { return 2 * (size_t)N * N + (size_t)N + 64; }
+
 template <typename T>
 inline cudaError_t jacobi_launch(T* C, int N, T* w, T* B, T* work, int warm, const int* gate,
                                  const int* status_gate, int* sweeps, cudaStream_t s) {
   const size_t need = 2 * (size_t)N * N * sizeof(T);
-  const int use_smem = need <= 200 * 1024 ? 1 : 0;
-  auto kern = jacobi_eigh_kernel<T>;
-  static thread_local bool configured[64];
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (dev < 0 || dev >= 64) dev = 0;
-  if (!configured[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    if (e != cudaSuccess) return e;
-    configured[dev] = true;
+  if (need <= 200 * 1024) {  // whole problem in one SM's shared memory
+    auto kern = jacobi_eigh_kernel<T>;
+    static thread_local bool configured[64];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) dev = 0;
+    if (!configured[dev]) {
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      if (e != cudaSuccess) return e;
+      configured[dev] = true;
+    }
+    kern<<<1, kJacobiThreads, need, s>>>(C, N, w, B, work, work + (size_t)N * N, 1, warm, gate, status_gate, sweeps);
+    return cudaGetLastError();
   }
-  kern<<<1, kJacobiThreads, use_smem ? need : 0, s>>>(C, N, w, B, work, work + (size_t)N * N, use_smem, warm, gate,
-                                                       status_gate, sweeps);
-  return cudaSuccess;
+  T* W = work;
+  T* Q = work + (size_t)N * N;
+  T* lam = Q + (size_t)N * N;
+  unsigned int* off = reinterpret_cast<unsigned int*>(lam + N);
+  int pairs = (N + 1) / 2, grid = (pairs + 7) / 8;
+  const int cap = sm_count();
+  if (grid > cap) grid = cap;
+  void* args[] = {&C, &N, &w, &B, &W, &Q, &lam, &off, &warm, &gate, &status_gate, &sweeps};
+  return cudaLaunchCooperativeKernel((const void*)jacobi_grid_kernel<T>, dim3(grid), dim3(256), args, 0, s);
 }
 
 }  // namespace sp

@@ -6,7 +6,7 @@
 //   vd_sample_eval   z -> y -> x, (y/d).vn, objective               row tiles, HBM: write 2 rows
 //   [Penalize]       rank -> percentiles -> weights -> arfit += penalty
 //   rank
-//   vd_wsum          S_x, S_y, P_mu, Q_mu over the mu best           column-parallel, read 2 mu rows
+//   vd_wsum/wreduce  S_x, S_y, P_mu, Q_mu over the mu best           column-parallel, read 2 mu rows
 //   vd_update        mean, sigma (rank gap of rows 0/1), pc, natural gradient on (v, D), ladder
 //   vd_refresh       |v|^2, vn, diagC for the next generation
 #include "es_common.cuh"
@@ -29,6 +29,7 @@ struct VdPtrs {
   __host__ __device__ T* coef() const { return work + (size_t)kVdChunks * 4 * N; }    // N
   __host__ __device__ T* tmp() const { return coef() + N; }                           // 8 * N
   __host__ __device__ T* sorted() const { return tmp() + 8 * (size_t)N; }             // P
+  __host__ __device__ T* sums() const { return sorted() + P; }                        // 4 * N reduced partials
 };
 
 // ctrl->aux: [0] |v|^2, [1] |v|
@@ -219,6 +220,20 @@ vd_wsum_kernel(const VdPtrs<T> a) {
   out[3 * a.N + n] = qm;
 }
 
+// chunk partials -> sums[q][n] in a fixed order (deterministic), one thread per (q, n)
+template <typename T>
+__global__ void __launch_bounds__(256)
+vd_wreduce_kernel(const VdPtrs<T> a) {
+  if (!es_running(a.ctrl)) return;
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= 4 * a.N) return;
+  const T* p = a.part() + e;
+  T acc = 0;
+#pragma unroll 8
+  for (int g = 0; g < kVdChunks; ++g) acc += p[(size_t)g * 4 * a.N];
+  a.sums()[e] = acc;
+}
+
 // mean, step size, paths, natural gradient, termination: one CTA (_vdcma.py:290-396)
 template <typename T>
 __global__ void __launch_bounds__(256)
@@ -243,16 +258,10 @@ vd_update_kernel(const VdPtrs<T> a) {
     s_r0 = a.rank[0];
     s_r1 = a.P > 1 ? a.rank[1] : 0;
   }
-  // chunk partials -> dx, xmean, S_y, P_mu, Q_mu
+  // reduced sums -> dx, xmean, S_y, P_mu, Q_mu
   for (int n = tid; n < N; n += blockDim.x) {
-    T sx = 0, sy = 0, pm = 0, qm = 0;
-    for (int g = 0; g < kVdChunks; ++g) {
-      const T* p = a.part() + (size_t)g * 4 * N;
-      sx += p[n];
-      sy += p[N + n];
-      pm += p[2 * N + n];
-      qm += p[3 * N + n];
-    }
+    const T* p = a.sums();
+    const T sx = p[n], sy = p[N + n], pm = p[2 * N + n], qm = p[3 * N + n];
     const T xm = a.xmean[n];
     const T dx = sub_rn(sx, mul_rn((T)a.wsum, xm));  // _vdcma.py:291
     a.dx[n] = dx;
@@ -460,10 +469,10 @@ template <typename T>
 static int vd_update(const sp_vd_state* st, int it, cudaStream_t s) {
   const VdPtrs<T> a = vd_ptrs<T>(st, it, 1);
   const int64_t P = st->P;
-  const int N = st->N, rank_grid = cdiv(P, kThreads);
+  const int N = st->N;
   if (st->constraint == SP_CONS_PENALIZE) {
-    rank_kernel<T><<<rank_grid, kThreads, 0, s>>>(a.arfit, P, a.rank, nullptr);
-    SP_CHECK_LAUNCH();
+    if (rank_launch<T>(a.arfit, P, a.rank, nullptr, s) != cudaSuccess) return SP_ERR_CUDA;
+    g_launches.fetch_add(2);
     scatter_sorted_kernel<T><<<cdiv(P, 256) < 1024 ? cdiv(P, 256) : 1024, 256, 0, s>>>(a.arfit, a.rank, a.sorted(), P, st->ctrl);
     SP_CHECK_LAUNCH();
     vd_penalty_state_kernel<T><<<1, 256, 0, s>>>(a);
@@ -472,9 +481,11 @@ static int vd_update(const sp_vd_state* st, int it, cudaStream_t s) {
         a.arx, a.coef(), a.arfit, P, N, st->ld, st->ctrl);
     SP_CHECK_LAUNCH();
   }
-  rank_kernel<T><<<rank_grid, kThreads, 0, s>>>(a.arfit, P, a.rank, nullptr);
-  SP_CHECK_LAUNCH();
+  if (rank_launch<T>(a.arfit, P, a.rank, nullptr, s) != cudaSuccess) return SP_ERR_CUDA;
+  g_launches.fetch_add(2);
   vd_wsum_kernel<T><<<dim3(cdiv(N, 256), kVdChunks), 256, 0, s>>>(a);
+  SP_CHECK_LAUNCH();
+  vd_wreduce_kernel<T><<<cdiv(4 * N, 256), 256, 0, s>>>(a);
   SP_CHECK_LAUNCH();
   vd_update_kernel<T><<<1, 256, 0, s>>>(a);
   SP_CHECK_LAUNCH();
@@ -505,7 +516,7 @@ using namespace sp;
 
 extern "C" {
 
-int64_t sp_vd_work_scalars(int N, int64_t P) { return (int64_t)kVdChunks * 4 * N + 9LL * N + P; }
+int64_t sp_vd_work_scalars(int N, int64_t P) { return (int64_t)kVdChunks * 4 * N + 13LL * N + P; }
 
 int sp_vd_refresh(const sp_vd_state* st, void* stream) {
   int rc = vd_check(st, 1);

@@ -36,13 +36,13 @@ def device_eigh(C, dtype="float64"):
     eng = Engine(dtype)
     N = C.shape[0]
     dC = torch.from_numpy(np.ascontiguousarray(C, dtype=eng.np_dt)).to(eng.device)
-    w, B, work = eng.zeros(N), eng.zeros(N, N), eng.zeros(2 * N * N)
+    w, B, work = eng.zeros(N), eng.zeros(N, N), eng.zeros(int(L.load().sp_sym_eigh_work_scalars(N)))
     L.call("sp_sym_eigh", eng.sp_dt, dC.data_ptr(), N, w.data_ptr(), B.data_ptr(), work.data_ptr(), eng.stream)
     eng.sync()
     return w.cpu().numpy().astype(np.float64), B.cpu().numpy().astype(np.float64), dC.cpu().numpy().astype(np.float64)
 
 
-@pytest.mark.parametrize("N", [1, 2, 3, 5, 16, 33, 64, 100, 128, 200, 256])
+@pytest.mark.parametrize("N", [1, 2, 3, 5, 16, 33, 64, 100, 113, 114, 128, 200, 256, 301])
 def test_sym_eigh_matches_lapack(N):
     rs = np.random.RandomState(N)
     A = rs.normal(0, 1, (N, N))
