@@ -218,7 +218,10 @@ int sp_fitness_rank(int dtype, const void* d_fit, int64_t P, int32_t* d_rank, vo
  * when 2 N^2 scalars fit, otherwise a cooperative multi-CTA kernel (one pair per warp,
  * grid barriers between rounds).  d_work: sp_sym_eigh_work_scalars(N) scalars. */
 int64_t sp_sym_eigh_work_scalars(int N);
-int sp_sym_eigh(int dtype, void* d_C, int N, void* d_w, void* d_B, void* d_work, void* stream);
+/* warm != 0: d_B holds an approximate eigenbasis to start from (few sweeps when C moved
+ * little).  d_sweeps (optional, device int32): number of Jacobi sweeps performed. */
+int sp_sym_eigh(int dtype, void* d_C, int N, void* d_w, void* d_B, void* d_work, int warm, int32_t* d_sweeps,
+                void* stream);
 
 /* ---- a15-a17: (mu,lambda)-CMA-ES generation (stochopy/optimize/cmaes/_cmaes.py:228-343,
  * converge :360-434, Penalize cmaes/_constraints.py:4-82).  Works in the space

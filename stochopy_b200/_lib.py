@@ -146,7 +146,7 @@ SIGNATURES = {
     "sp_pso_run": (_i, [C.POINTER(PsoState), _i, _i, vp, vp]),
     "sp_random_fill": (_i, [_i, vp, _i64, _i, _i64, _i, _i, _u64, _i, vp]),
     "sp_fitness_rank": (_i, [_i, vp, _i64, vp, vp]),
-    "sp_sym_eigh": (_i, [_i, vp, _i, vp, vp, vp, vp]),
+    "sp_sym_eigh": (_i, [_i, vp, _i, vp, vp, vp, _i, vp, vp]),
     "sp_sym_eigh_work_scalars": (_i64, [_i]),
     "sp_cma_work_scalars": (_i64, [_i, _i64]),
     "sp_cma_generation": (_i, [C.POINTER(CmaState), _i, vp]),

@@ -302,13 +302,13 @@ int sp_fitness_rank(int dtype, const void* fit, int64_t P, int32_t* rank, void* 
 
 int64_t sp_sym_eigh_work_scalars(int N) { return (int64_t)jacobi_work_scalars(N); }
 
-int sp_sym_eigh(int dtype, void* C, int N, void* w, void* B, void* work, void* stream) {
+int sp_sym_eigh(int dtype, void* C, int N, void* w, void* B, void* work, int warm, int32_t* sweeps, void* stream) {
   SP_CHECK_ARG(C && w && B && work && N >= 1 && N <= 1024, "null pointer or N outside [1, 1024]");  // work: sp_sym_eigh_work_scalars(N)
   SP_CHECK_ARG(dtype == SP_F32 || dtype == SP_F64, "dtype");
   cudaStream_t s = (cudaStream_t)stream;
   cudaError_t e = dtype == SP_F32
-                      ? jacobi_launch<float>((float*)C, N, (float*)w, (float*)B, (float*)work, 0, nullptr, nullptr, nullptr, s)
-                      : jacobi_launch<double>((double*)C, N, (double*)w, (double*)B, (double*)work, 0, nullptr, nullptr, nullptr, s);
+                      ? jacobi_launch<float>((float*)C, N, (float*)w, (float*)B, (float*)work, warm, nullptr, nullptr, sweeps, s)
+                      : jacobi_launch<double>((double*)C, N, (double*)w, (double*)B, (double*)work, warm, nullptr, nullptr, sweeps, s);
   if (e != cudaSuccess) {
     set_error("sp_sym_eigh: %s", cudaGetErrorString(e));
     return SP_ERR_CUDA;

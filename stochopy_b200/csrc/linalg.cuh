@@ -121,6 +121,7 @@ struct JacobiEps<float> {
 };
 
 constexpr int kJacobiThreads = 1024;
+constexpr int kJacobiRegs = 8;  // row elements per lane staged in registers (N <= 256)
 
 template <typename T>
 __global__ void __launch_bounds__(kJacobiThreads, 1)
@@ -274,13 +275,21 @@ jacobi_eigh_kernel(T* __restrict__ C, int N, T* __restrict__ w_out, T* __restric
 // live in global memory (L2 resident, 2 N^2 scalars), rounds are separated by grid-wide
 // barriers.  Same rotations, ordering, warm start, sorting and sign rule as above.
 // scratch: W, Q (2 N^2), lam (N), sweep flags (64 x 4 bytes).
-template <typename T>
-__global__ void __launch_bounds__(256)
+// CLUSTER: the whole grid is ONE thread-block cluster (<= 16 CTAs) and rounds are separated
+// by the hardware cluster barrier (barrier.cluster, a few hundred cycles, release/acquire at
+// cluster scope incl. the L1 invalidate) instead of a cooperative grid barrier.
+template <typename T, bool CLUSTER, int THREADS>
+__global__ void __launch_bounds__(THREADS)
 jacobi_grid_kernel(T* __restrict__ C, int N, T* __restrict__ w_out, T* __restrict__ B, T* __restrict__ W,
                    T* __restrict__ Q, T* __restrict__ lam, unsigned int* __restrict__ off, int warm,
                    const int* __restrict__ gate, const int* __restrict__ status_gate, int* __restrict__ sweeps_out) {
   namespace cg = cooperative_groups;
-  cg::grid_group grid = cg::this_grid();
+  struct Barrier {
+    __device__ void sync() {
+      if (CLUSTER) cg::this_cluster().sync();
+      else cg::this_grid().sync();
+    }
+  } grid;
   if (gate != nullptr && *gate == 0) return;  // uniform over the grid: nobody reaches a barrier
   if (status_gate != nullptr && *status_gate != SP_RUNNING) return;
   const int tid = threadIdx.x, lane = tid & 31;
@@ -331,6 +340,56 @@ jacobi_grid_kernel(T* __restrict__ C, int N, T* __restrict__ w_out, T* __restric
         if (p >= N || q >= N) continue;
         T* wp = W + (size_t)p * N;
         T* wq = W + (size_t)q * N;
+        T* qp = Q + (size_t)p * N;
+        T* qq = Q + (size_t)q * N;
+        if (THREADS <= 512 && N <= 32 * kJacobiRegs) {
+          // rows staged in registers: all loads of a phase are in flight together (the four
+          // row pointers alias as far as the compiler knows, so a load/store loop serialises)
+          T ra[kJacobiRegs], rb[kJacobiRegs];
+          T al = 0, be = 0, ga = 0;
+#pragma unroll
+          for (int u = 0; u < kJacobiRegs; ++u) {
+            const int k = lane + 32 * u;
+            ra[u] = k < N ? wp[k] : T(0);
+            rb[u] = k < N ? wq[k] : T(0);
+          }
+#pragma unroll
+          for (int u = 0; u < kJacobiRegs; ++u) {
+            al += ra[u] * ra[u];
+            be += rb[u] * rb[u];
+            ga += ra[u] * rb[u];
+          }
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            al += __shfl_xor_sync(0xffffffffu, al, o);
+            be += __shfl_xor_sync(0xffffffffu, be, o);
+            ga += __shfl_xor_sync(0xffffffffu, ga, o);
+          }
+          if (fabs(ga) > tol * sqrt(al * be) && al > T(0) && be > T(0)) {
+            if (lane == 0) off[sweep] = 1u;
+            T rc[kJacobiRegs], rd[kJacobiRegs];
+#pragma unroll
+            for (int u = 0; u < kJacobiRegs; ++u) {
+              const int k = lane + 32 * u;
+              rc[u] = k < N ? qp[k] : T(0);
+              rd[u] = k < N ? qq[k] : T(0);
+            }
+            const T zeta = (be - al) / (T(2) * ga);
+            const T t = (zeta >= T(0) ? T(1) : T(-1)) / (fabs(zeta) + sqrt(T(1) + zeta * zeta));
+            const T cs = T(1) / sqrt(T(1) + t * t), sn = cs * t;
+#pragma unroll
+            for (int u = 0; u < kJacobiRegs; ++u) {
+              const int k = lane + 32 * u;
+              if (k < N) {
+                wp[k] = cs * ra[u] - sn * rb[u];
+                wq[k] = sn * ra[u] + cs * rb[u];
+                qp[k] = cs * rc[u] - sn * rd[u];
+                qq[k] = sn * rc[u] + cs * rd[u];
+              }
+            }
+          }
+          continue;
+        }
         T al = 0, be = 0, ga = 0;
         for (int k = lane; k < N; k += 32) {
           const T a = wp[k], b = wq[k];
@@ -349,8 +408,6 @@ jacobi_grid_kernel(T* __restrict__ C, int N, T* __restrict__ w_out, T* __restric
           const T zeta = (be - al) / (T(2) * ga);
           const T t = (zeta >= T(0) ? T(1) : T(-1)) / (fabs(zeta) + sqrt(T(1) + zeta * zeta));
           const T cs = T(1) / sqrt(T(1) + t * t), sn = cs * t;
-          T* qp = Q + (size_t)p * N;
-          T* qq = Q + (size_t)q * N;
           for (int k = lane; k < N; k += 32) {
             const T a = wp[k], b = wq[k];
             wp[k] = cs * a - sn * b;
@@ -433,11 +490,37 @@ inline cudaError_t jacobi_launch(T* C, int N, T* w, T* B, T* work, int warm, con
   T* Q = work + (size_t)N * N;
   T* lam = Q + (size_t)N * N;
   unsigned int* off = reinterpret_cast<unsigned int*>(lam + N);
-  int pairs = (N + 1) / 2, grid = (pairs + 7) / 8;
-  const int cap = sm_count();
-  if (grid > cap) grid = cap;
-  void* args[] = {&C, &N, &w, &B, &W, &Q, &lam, &off, &warm, &gate, &status_gate, &sweeps};
-  return cudaLaunchCooperativeKernel((const void*)jacobi_grid_kernel<T>, dim3(grid), dim3(256), args, 0, s);
+  const int pairs = (N + 1) / 2;
+  // one cluster: 8 CTAs (portable) up to 512 pairs' worth of warps, 16 CTAs beyond
+  int ctas = pairs <= 8 * 32 ? 8 : 16;
+  int warps = (pairs + ctas - 1) / ctas;
+  if (warps > 32) warps = 32;
+  const int threads = warps * 32;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(ctas);
+  cfg.blockDim = dim3(threads);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = ctas;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e;
+  if (threads <= 512) {
+    auto kern = jacobi_grid_kernel<T, true, 512>;
+    e = cudaLaunchKernelEx(&cfg, kern, C, N, w, B, W, Q, lam, off, warm, gate, status_gate, sweeps);
+  } else {
+    auto kern = jacobi_grid_kernel<T, true, 1024>;
+    if (ctas > 8) {
+      e = cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+      if (e != cudaSuccess) return e;
+    }
+    e = cudaLaunchKernelEx(&cfg, kern, C, N, w, B, W, Q, lam, off, warm, gate, status_gate, sweeps);
+  }
+  return e;
 }
 
 }  // namespace sp

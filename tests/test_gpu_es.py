@@ -37,7 +37,7 @@ def device_eigh(C, dtype="float64"):
     N = C.shape[0]
     dC = torch.from_numpy(np.ascontiguousarray(C, dtype=eng.np_dt)).to(eng.device)
     w, B, work = eng.zeros(N), eng.zeros(N, N), eng.zeros(int(L.load().sp_sym_eigh_work_scalars(N)))
-    L.call("sp_sym_eigh", eng.sp_dt, dC.data_ptr(), N, w.data_ptr(), B.data_ptr(), work.data_ptr(), eng.stream)
+    L.call("sp_sym_eigh", eng.sp_dt, dC.data_ptr(), N, w.data_ptr(), B.data_ptr(), work.data_ptr(), 0, None, eng.stream)
     eng.sync()
     return w.cpu().numpy().astype(np.float64), B.cpu().numpy().astype(np.float64), dC.cpu().numpy().astype(np.float64)
 
