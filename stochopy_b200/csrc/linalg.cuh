@@ -5,6 +5,8 @@
 #pragma once
 #include <cooperative_groups.h>
 
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace sp {
@@ -465,6 +467,185 @@ jacobi_grid_kernel(T* __restrict__ C, int N, T* __restrict__ w_out, T* __restric
   }
 }
 
+// Block Jacobi for matrices beyond one SM: the rows are cut into blocks of b rows; in an
+// outer round every CTA of the (single) cluster loads one PAIR of blocks (2b rows of W and
+// of Q) into shared memory, runs a complete inner round-robin sweep over those 2b rows
+// there (b warps, one pair per warp, __syncthreads between inner rounds), and writes the
+// rows back; outer rounds follow the same circle-method tournament over the blocks and are
+// separated by the hardware cluster barrier.  Compared with one global barrier per scalar
+// round this needs (2 N / b - 1) barriers per sweep instead of (N - 1) and keeps the
+// rotations in shared memory.  A sweep whose largest |cos| was tiny ends the iteration
+// without a separate all-quiet sweep (quadratic convergence).
+__device__ __forceinline__ void circle_pair(int n, int r, int i, int* p, int* q) {
+  if (i == 0) {
+    *p = n - 1;
+    *q = r;
+  } else {
+    *p = (r + i) % (n - 1);
+    *q = (r - i + (n - 1)) % (n - 1);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(512)
+jacobi_block_kernel(T* __restrict__ C, int N, T* __restrict__ w_out, T* __restrict__ B, T* __restrict__ W,
+                    T* __restrict__ Q, T* __restrict__ lam, unsigned int* __restrict__ off, int warm, int b, int nblk,
+                    const int* __restrict__ gate, const int* __restrict__ status_gate, int* __restrict__ sweeps_out) {
+  namespace cg = cooperative_groups;
+  extern __shared__ __align__(16) unsigned char jbs[];
+  if (gate != nullptr && *gate == 0) return;
+  if (status_gate != nullptr && *status_gate != SP_RUNNING) return;
+  cg::cluster_group cl = cg::this_cluster();
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int gthreads = gridDim.x * blockDim.x, gtid = blockIdx.x * blockDim.x + tid;
+  const int gwarp = gtid >> 5, gwarps = gthreads >> 5;
+  T* sW = reinterpret_cast<T*>(jbs);     // [2b][N]
+  T* sQ = sW + (size_t)2 * b * N;        // [2b][N]
+
+  for (int e = gtid; e < N * N; e += gthreads) {  // C = triu(C) + triu(C,1)^T (_cmaes.py:303)
+    const int r = e / N, c = e - r * N;
+    if (r > c) C[e] = C[c * N + r];
+  }
+  if (gtid < 64) off[gtid] = 0u;
+  cl.sync();
+  if (warm) {
+    for (int e = gtid; e < N * N; e += gthreads) {
+      const int j = e / N, r = e - j * N;
+      Q[e] = B[r * N + j];
+    }
+    cl.sync();
+    for (int e = gtid; e < N * N; e += gthreads) {  // W = Q C
+      const int j = e / N, c = e - j * N;
+      T acc = 0;
+      for (int k = 0; k < N; ++k) acc += Q[j * N + k] * C[k * N + c];
+      W[e] = acc;
+    }
+  } else {
+    for (int e = gtid; e < N * N; e += gthreads) {
+      const int r = e / N, c = e - r * N;
+      W[e] = C[e];
+      Q[e] = r == c ? T(1) : T(0);
+    }
+  }
+  cl.sync();
+
+  const T tol = T(4) * JacobiEps<T>::eps() * sqrt((T)(N < 16 ? 16 : N));
+  const float quiet = 0.25f * sqrtf((float)tol);  // a sweep below this needs no follow-up sweep
+  const int m = nblk / 2, n2 = 2 * b;
+  int sweep = 0;
+  for (; sweep < 60; ++sweep) {
+    for (int R = 0; R < nblk - 1; ++R) {
+      for (int bp = blockIdx.x; bp < m; bp += gridDim.x) {
+        int I, J;
+        circle_pair(nblk, R, bp, &I, &J);
+        // load the 2b rows (rows past N are zero)
+        for (int e = tid; e < n2 * N; e += blockDim.x) {
+          const int lr = e / N, k = e - lr * N;
+          const int gr = (lr < b ? I * b + lr : J * b + (lr - b));
+          sW[e] = gr < N ? W[(size_t)gr * N + k] : T(0);
+          sQ[e] = gr < N ? Q[(size_t)gr * N + k] : T(0);
+        }
+        __syncthreads();
+        for (int r = 0; r < n2 - 1; ++r) {
+          if (warp < b) {
+            int p, q;
+            circle_pair(n2, r, warp, &p, &q);
+            const int gp = (p < b ? I * b + p : J * b + (p - b)), gq = (q < b ? I * b + q : J * b + (q - b));
+            if (gp < N && gq < N) {
+              T* wp = sW + (size_t)p * N;
+              T* wq = sW + (size_t)q * N;
+              T al = 0, be = 0, ga = 0;
+              for (int k = lane; k < N; k += 32) {
+                const T a = wp[k], c = wq[k];
+                al += a * a;
+                be += c * c;
+                ga += a * c;
+              }
+#pragma unroll
+              for (int o = 16; o > 0; o >>= 1) {
+                al += __shfl_xor_sync(0xffffffffu, al, o);
+                be += __shfl_xor_sync(0xffffffffu, be, o);
+                ga += __shfl_xor_sync(0xffffffffu, ga, o);
+              }
+              const T nrm = sqrt(al * be);
+              if (fabs(ga) > tol * nrm && al > T(0) && be > T(0)) {
+                if (lane == 0) atomicMax(&off[sweep], __float_as_uint((float)(fabs(ga) / nrm)));
+                const T zeta = (be - al) / (T(2) * ga);
+                const T t = (zeta >= T(0) ? T(1) : T(-1)) / (fabs(zeta) + sqrt(T(1) + zeta * zeta));
+                const T cs = T(1) / sqrt(T(1) + t * t), sn = cs * t;
+                T* qp = sQ + (size_t)p * N;
+                T* qq = sQ + (size_t)q * N;
+                for (int k = lane; k < N; k += 32) {
+                  const T a = wp[k], c = wq[k];
+                  wp[k] = cs * a - sn * c;
+                  wq[k] = sn * a + cs * c;
+                  const T d = qp[k], f = qq[k];
+                  qp[k] = cs * d - sn * f;
+                  qq[k] = sn * d + cs * f;
+                }
+              }
+            }
+          }
+          __syncthreads();
+        }
+        for (int e = tid; e < n2 * N; e += blockDim.x) {  // write the rows back
+          const int lr = e / N, k = e - lr * N;
+          const int gr = (lr < b ? I * b + lr : J * b + (lr - b));
+          if (gr < N) {
+            W[(size_t)gr * N + k] = sW[e];
+            Q[(size_t)gr * N + k] = sQ[e];
+          }
+        }
+        __syncthreads();
+      }
+      cl.sync();
+    }
+    const unsigned int worst = *reinterpret_cast<volatile unsigned int*>(&off[sweep]);
+    if (worst == 0u || __uint_as_float(worst) < quiet) break;
+  }
+  if (gtid == 0 && sweeps_out != nullptr) *sweeps_out = sweep + 1;
+
+  for (int j = gwarp; j < N; j += gwarps) {  // signed eigenvalues
+    T acc = 0;
+    for (int k = lane; k < N; k += 32) acc += W[(size_t)j * N + k] * Q[(size_t)j * N + k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) lam[j] = acc;
+  }
+  cl.sync();
+  for (int j = gwarp; j < N; j += gwarps) {  // ascending stable rank, sign rule, scatter
+    const T mine = lam[j];
+    int rk = 0;
+    for (int k = lane; k < N; k += 32) {
+      const T o = lam[k];
+      rk += (o < mine) || (o == mine && k < j);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) rk += __shfl_xor_sync(0xffffffffu, rk, o);
+    T best = T(-1);
+    int bidx = 0;
+    for (int k = lane; k < N; k += 32) {
+      const T a = fabs(Q[(size_t)j * N + k]);
+      if (a > best) {
+        best = a;
+        bidx = k;
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const T ob = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bidx, o);
+      if (ob > best || (ob == best && oi < bidx)) {
+        best = ob;
+        bidx = oi;
+      }
+    }
+    const T sgn = Q[(size_t)j * N + bidx] < T(0) ? T(-1) : T(1);
+    if (lane == 0) w_out[rk] = mine;
+    for (int k = lane; k < N; k += 32) B[(size_t)k * N + rk] = sgn * Q[(size_t)j * N + k];
+  }
+}
+
 // scratch scalars needed behind `work` for an N x N decomposition
 inline size_t jacobi_work_scalars(int N) { return 2 * (size_t)N * N + (size_t)N + 64; }
 
@@ -490,6 +671,39 @@ inline cudaError_t jacobi_launch(T* C, int N, T* w, T* B, T* work, int warm, con
   T* Q = work + (size_t)N * N;
   T* lam = Q + (size_t)N * N;
   unsigned int* off = reinterpret_cast<unsigned int*>(lam + N);
+  static const bool scalar_rounds = getenv("SP_EIGH_SCALAR") != nullptr;  // profiling switch
+  if (!scalar_rounds) {
+    int b = 16;
+    while (b > 2 && 4 * (size_t)b * N * sizeof(T) > 200 * 1024) b >>= 1;
+    int nblk = (N + b - 1) / b;
+    nblk += nblk & 1;
+    const int m = nblk / 2;
+    const int ctas = m < 8 ? m : 8;
+    const size_t smem = 4 * (size_t)b * N * sizeof(T);
+    auto kern = jacobi_block_kernel<T>;
+    static thread_local bool configured[64];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) dev = 0;
+    if (!configured[dev]) {
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      if (e != cudaSuccess) return e;
+      configured[dev] = true;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(ctas);
+    cfg.blockDim = dim3(b * 32 < 128 ? 128 : b * 32);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = ctas;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, C, N, w, B, W, Q, lam, off, warm, b, nblk, gate, status_gate, sweeps);
+  }
   const int pairs = (N + 1) / 2;
   // one cluster: 8 CTAs (portable) up to 512 pairs' worth of warps, 16 CTAs beyond
   int ctas = pairs <= 8 * 32 ? 8 : 16;
