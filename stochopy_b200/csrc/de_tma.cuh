@@ -28,36 +28,6 @@ struct Strat {
   static constexpr bool kBest = STRAT >= SP_DE_BEST1BIN;
 };
 
-// Philox4x32-10 with the ten round keys taken from kernel parameters (constant bank
-// operands of the LOP3s) instead of being re-derived from the seed for every call.
-struct PhiloxKeys {
-  uint32_t k[20];
-};
-inline PhiloxKeys philox_keys(uint64_t seed) {
-  PhiloxKeys r;
-  uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
-  for (int i = 0; i < 10; ++i) {
-    r.k[2 * i] = k0;
-    r.k[2 * i + 1] = k1;
-    k0 += 0x9E3779B9u;
-    k1 += 0xBB67AE85u;
-  }
-  return r;
-}
-__device__ __forceinline__ uint4 philox4x32_keyed(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, const PhiloxKeys& K) {
-#pragma unroll
-  for (int r = 0; r < 10; ++r) {
-    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
-    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
-    const uint32_t n0 = hi1 ^ c1 ^ K.k[2 * r], n2 = hi0 ^ c3 ^ K.k[2 * r + 1];
-    c0 = n0;
-    c1 = lo1;
-    c2 = n2;
-    c3 = lo0;
-  }
-  return make_uint4(c0, c1, c2, c3);
-}
-
 __device__ __forceinline__ bool cross_take(uint32_t w, uint64_t cut) { return w <= (uint32_t)cut; }
 __device__ __forceinline__ bool cross_take(unsigned long long m53, uint64_t cut) { return m53 <= cut; }
 
