@@ -28,6 +28,9 @@ struct Strat {
   static constexpr bool kBest = STRAT >= SP_DE_BEST1BIN;
 };
 
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __device__ __forceinline__ bool cross_take(uint32_t w, uint64_t cut) { return w <= (uint32_t)cut; }
 __device__ __forceinline__ bool cross_take(unsigned long long m53, uint64_t cut) { return m53 <= cut; }
 
@@ -101,7 +104,6 @@ de_pool_kernel(const DeArgs<T> a, int nb, const PhiloxKeys keys) {
   constexpr int K = Strat<STRAT>::K;
   constexpr int S = kPoolStages;
   using RS = RowSet<T, CH, K>;
-  if (!running(a.ctrl)) return;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5, warps = blockDim.x >> 5;
   const int ld = FULL ? TL::COLS : (int)a.ld;
@@ -137,8 +139,14 @@ de_pool_kernel(const DeArgs<T> a, int nb, const PhiloxKeys keys) {
     tab_ir[t] = ir;
 #pragma unroll
     for (int k = 0; k < K; ++k) tab_d[k * nb + t] = dd[k];
-    s_best[t] = a.pbestfit[b0 + t];
   }
+  // Programmatic dependent launch: everything above depends only on (seed, generation), so
+  // it overlaps the tail of the previous generation's kernel; from here on we read what that
+  // kernel wrote (status, pbestfit, gbest, the population).
+  pdl_wait();
+  if (!running(a.ctrl)) return;
+  pdl_launch_dependents();  // the next generation may start its own prologue as SMs free up
+  for (int t = tid; t < rows; t += blockDim.x) s_best[t] = a.pbestfit[b0 + t];
   TL gb;
   if (Strat<STRAT>::kBest) gb.load(a.gbest, lane, ld);
   const uint64_t cut = a.cr_cut;
@@ -332,8 +340,17 @@ static cudaError_t de_pool_launch(const DeArgs<T>& a, cudaStream_t s) {
     if (e != cudaSuccess) return e;
     configured[dev] = 220 * 1024;
   }
-  kern<<<ps.grid, ps.threads, ps.smem, s>>>(a, ps.nb, philox_keys(a.seed));
-  return cudaSuccess;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(ps.grid);
+  cfg.blockDim = dim3(ps.threads);
+  cfg.dynamicSmemBytes = ps.smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, a, ps.nb, philox_keys(a.seed));
 }
 
 template <typename T, int CH, int STRAT>
