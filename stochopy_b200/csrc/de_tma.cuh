@@ -126,6 +126,8 @@ de_pool_kernel(const DeArgs<T> a, int nb, const PhiloxKeys keys) {
   const int rows = (int)(q + (blockIdx.x < rem ? 1 : 0));
 
   // ---- phase 0: tables ------------------------------------------------------------------
+  // (an explicit cp.async.bulk.prefetch.L2 of the CTA's slice was measured slower when the L2 is
+  // full of dirty lines: 38.3 vs 36.1 us per generation -- demand fetches are left alone)
   if (tid == 0) *s_next = 0;
   if (lane == 0) {
 #pragma unroll
