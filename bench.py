@@ -57,7 +57,7 @@ def traffic_from_profile():
     """DRAM bytes per launch of the DE kernel from the committed ncu capture, if any."""
     try:
         with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
-            return float(json.load(f)["de_generation_kernel"]["dram_bytes_per_launch"])
+            return float(json.load(f)["de_pool_kernel"]["dram_bytes_per_launch"])
     except Exception:
         return None
 
@@ -305,7 +305,7 @@ def our_arm(args):
                     "call": "stochopy_b200.optimize.minimize(rosenbrock, bounds, x0=<host fp32 array>, method='de')"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic_from_profile(), "kernel": "de_generation_kernel<float,1,32,true>",
+                         "traffic": traffic_from_profile(), "kernel": "de_pool_kernel<float,CH=1,best1bin,FULL,PLAIN>",
                          "algorithmic_bytes_per_launch": ALG_BYTES_PER_EVAL * P, "peak_source": peak_src,
                          "launch_us": per_launch_s * 1e6},
             "clocks": clocks.summary(),
