@@ -206,7 +206,8 @@ int sp_random_fill(int dtype, void* d_out, int64_t P, int N, int64_t ld, int it,
 
 /* ---- fitness ranking (np.argsort(arfitness), _cmaes.py:272 / _vdcma.py:290) ----
  * d_rank[i] = number of individuals that sort before i (ascending, ties by
- * index = a stable argsort); O(P^2) counting, P <= 2^31. */
+ * index = a stable argsort; NaN last); chunk sort + merge (csrc/rank.cuh), P < 2^31.
+ * Scratch comes from the device's stream-ordered pool (cudaMallocAsync). */
 int sp_fitness_rank(int dtype, const void* d_fit, int64_t P, int32_t* d_rank, void* stream);
 
 /* ---- dense symmetric eigendecomposition (np.linalg.eigh, _cmaes.py:304) -------

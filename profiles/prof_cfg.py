@@ -9,6 +9,10 @@ elif which == "cma":
     sb.optimize.minimize(sb.factory.rosenbrock, [[-5.12, 5.12]] * 256, method="cmaes", options=dict(maxiter=4, popsize=4096, seed=0, **off))
 elif which == "pso":
     sb.optimize.minimize(sb.factory.styblinski_tang, [[-5.12, 5.12]] * 64, method="pso", options=dict(maxiter=6, popsize=32768, seed=0, dtype="float32", updating="deferred", **off))
+elif which == "cpso":
+    sb.optimize.minimize(sb.factory.styblinski_tang, [[-5.12, 5.12]] * 64, method="cpso", options=dict(maxiter=6, popsize=32768, seed=0, dtype="float32", updating="deferred", **off))
+elif which == "vd64":
+    sb.optimize.minimize(sb.factory.ackley, [[-5.12, 5.12]] * 1024, method="vdcma", options=dict(maxiter=4, popsize=16384, seed=0, **off))
 if which == "cma_time":
     import time, torch
     for n, p, it in ((256, 4096, 30), (128, 16384, 30), (512, 2048, 10)):
@@ -36,3 +40,24 @@ if which == "eigh_time":
             L.call("sp_sym_eigh", eng.sp_dt, dC.data_ptr(), N, w.data_ptr(), B.data_ptr(), work.data_ptr(), warm, sw.data_ptr(), eng.stream)
             torch.cuda.synchronize(); dt = time.perf_counter() - t0
             print(f"eigh N={N} warm={warm} pert={pert}: {dt*1e3:.3f} ms, sweeps={int(sw.item())}, per round {dt*1e6/max(1,int(sw.item()))/(N-1+N%2):.2f} us", flush=True)
+
+if which == "slopes":
+    # per-generation device time in a real run (no profiler): slope between a short and a long run
+    import time, torch
+    def run(method, fun, n, p, it, **kw):
+        o = dict(maxiter=it, popsize=p, seed=0, **off, **kw)
+        torch.cuda.synchronize(); t0 = time.perf_counter()
+        sb.optimize.minimize(fun, [[-5.12, 5.12]] * n, method=method, options=o)
+        torch.cuda.synchronize(); return time.perf_counter() - t0
+    cases = [("vdcma", sb.factory.ackley, 1024, 16384, dict(dtype="float32")), ("vdcma", sb.factory.ackley, 1024, 16384, {}),
+             ("cpso", sb.factory.styblinski_tang, 64, 32768, dict(dtype="float32", updating="deferred")),
+             ("pso", sb.factory.styblinski_tang, 64, 32768, dict(dtype="float32", updating="deferred")),
+             ("de", sb.factory.rastrigin, 128, 65536, dict(dtype="float32", updating="deferred")),
+             ("cmaes", sb.factory.rosenbrock, 256, 4096, {}), ("cmaes", sb.factory.rosenbrock, 128, 16384, {})]
+    for method, fun, n, p, kw in cases:
+        a, b = (10, 40) if method == "cmaes" else (50, 450)
+        run(method, fun, n, p, 5, **kw)
+        ta = min(run(method, fun, n, p, a, **kw) for _ in range(2))
+        tb = min(run(method, fun, n, p, b, **kw) for _ in range(2))
+        per = (tb - ta) / (b - a)
+        print(f"{method} {fun.__name__} N={n} P={p} {kw.get('dtype', 'float64')}: {per * 1e6:.1f} us/gen, {p / per:.3e} evals/s (fixed {1e3 * (ta - a * per):.2f} ms)", flush=True)

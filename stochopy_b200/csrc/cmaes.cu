@@ -78,7 +78,7 @@ cma_mean_partial_kernel(const CmaPtrs<T> a) {
 template <typename T>
 __global__ void __launch_bounds__(256)
 cma_paths_kernel(const CmaPtrs<T> a) {
-  __shared__ double s_red[8];
+  __shared__ double s_red[kRedDoubles];
   __shared__ int s_best;
   sp_es_ctrl* c = a.ctrl;
   if (!es_running(c)) return;
@@ -201,7 +201,7 @@ cma_invsqrt_kernel(const CmaPtrs<T> a) {
 template <typename T>
 __global__ void __launch_bounds__(256)
 cma_converge_kernel(const CmaPtrs<T> a) {
-  __shared__ double s_red[8];
+  __shared__ double s_red[kRedDoubles];
   if (!es_running(a.ctrl)) return;
   converge_ladder<T>(a.ctrl, a.it, a.N, a.maxiter, a.ilim, a.P, a.xmean, a.xold, a.besthist, a.arfit, a.pc, a.C,
                      a.N + 1, a.B, a.D, a.xtol, a.ftol, a.insigma, s_red);
@@ -210,7 +210,7 @@ cma_converge_kernel(const CmaPtrs<T> a) {
 template <typename T>
 __global__ void __launch_bounds__(256)
 cma_penalty_state_kernel(const CmaPtrs<T> a) {
-  __shared__ double s_red[8];
+  __shared__ double s_red[kRedDoubles];
   if (!es_running(a.ctrl)) return;
   penalize_state<T>(a.ctrl, a.it, a.N, a.P, a.hist_cap, a.mueff, a.sorted(), a.xmean, a.xold, a.C, a.N + 1,
                     a.bnd_weights, a.dfithist, a.vec() + 2 * a.N, s_red);
@@ -305,7 +305,6 @@ static int cma_update(const sp_cma_state* st, int it, cudaStream_t s) {
   const int64_t P = st->P;
   if (st->constraint == SP_CONS_PENALIZE) {
     if (rank_launch<T>(a.arfit, P, a.rank, nullptr, s) != cudaSuccess) return SP_ERR_CUDA;
-    g_launches.fetch_add(2);
     scatter_sorted_kernel<T><<<cdiv(P, 256) < 1024 ? cdiv(P, 256) : 1024, 256, 0, s>>>(a.arfit, a.rank, a.sorted(), P, st->ctrl);
     SP_CHECK_LAUNCH();
     cma_penalty_state_kernel<T><<<1, 256, 0, s>>>(a);
@@ -315,7 +314,6 @@ static int cma_update(const sp_cma_state* st, int it, cudaStream_t s) {
     SP_CHECK_LAUNCH();
   }
   if (rank_launch<T>(a.arfit, P, a.rank, nullptr, s) != cudaSuccess) return SP_ERR_CUDA;
-  g_launches.fetch_add(2);
   cma_mean_partial_kernel<T><<<kMeanChunks, 256, 0, s>>>(a);
   SP_CHECK_LAUNCH();
   cma_paths_kernel<T><<<1, 256, 0, s>>>(a);

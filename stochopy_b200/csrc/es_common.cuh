@@ -29,14 +29,53 @@ __global__ void normal_fill_kernel(T* __restrict__ Z, int64_t P, int N, int64_t 
   }
 }
 
+// Block reductions through shared memory.  s_red must hold kRedDoubles doubles.
+constexpr int kRedMax = 16;                       // values per combined reduction
+constexpr int kRedDoubles = kRedMax * 32 + kRedMax;
+enum RedOp { RED_SUM = 0, RED_MIN = 1, RED_MAX = 2 };
+
+__device__ __forceinline__ double red_apply(double a, double b, int op) {
+  return op == RED_SUM ? a + b : (op == RED_MIN ? fmin(a, b) : fmax(a, b));
+}
+__device__ __forceinline__ double red_identity(int op) {
+  return op == RED_SUM ? 0.0 : (op == RED_MIN ? 1.0 / 0.0 : -1.0 / 0.0);
+}
+__device__ __forceinline__ double red_warp(double v, int op) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = red_apply(v, __shfl_xor_sync(0xffffffffu, v, o), op);
+  return v;
+}
+
+// K values at once (K <= kRedMax), each with its own operator: warp butterflies, one
+// shared-memory row per value, warp k folds row k; 3 barriers whatever K is.  Every
+// thread of the CTA must call it; every thread receives all K results.  The order of
+// the additions is fixed by the launch shape, so results are reproducible.
+template <int K>
+__device__ __forceinline__ void block_reduce(double (&v)[K], const int (&op)[K], double* s_red) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+#pragma unroll
+  for (int k = 0; k < K; ++k) v[k] = red_warp(v[k], op[k]);
+  __syncthreads();  // s_red may still be read by the previous reduction
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < K; ++k) s_red[k * 32 + warp] = v[k];
+  }
+  __syncthreads();
+  for (int k = warp; k < K; k += nw) {
+    double x = lane < nw ? s_red[k * 32 + lane] : red_identity(op[k]);
+    x = red_warp(x, op[k]);
+    if (lane == 0) s_red[kRedMax * 32 + k] = x;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < K; ++k) v[k] = s_red[kRedMax * 32 + k];
+}
+
 __device__ __forceinline__ double block_sum(double v, double* s_red) {
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  __syncthreads();
-  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = v;
-  __syncthreads();
-  double t = 0.0;
-  for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += s_red[w];
-  return t;
+  double x[1] = {v};
+  const int op[1] = {RED_SUM};
+  block_reduce<1>(x, op, s_red);
+  return x[0];
 }
 
 // ---- termination ladder (_cmaes.py:360-434), one CTA ----------------------------------------------
@@ -49,8 +88,9 @@ __device__ void converge_ladder(sp_es_ctrl* c, int it, int N, int maxiter, int i
   const int tid = threadIdx.x;
   const double sigma = c->sigma;
   const double best = c->base.gfit;
-  double dsq = 0.0, fmin_ = 1.0 / 0.0, fmax_ = -1.0 / 0.0, hmin = 1.0 / 0.0, hmax = -1.0 / 0.0;
-  double wmin = 1.0 / 0.0, wmax = -1.0 / 0.0, dmin = 1.0 / 0.0, dmax = -1.0 / 0.0, sdmax = 0.0;
+  const double inf = 1.0 / 0.0;
+  double dsq = 0.0, fmin_ = inf, fmax_ = -inf, hmin = inf, hmax = -inf;
+  double wmin = inf, wmax = -inf, dmin = inf, dmax = -inf, sdmax = 0.0;
   int axis_all = 1, coord_any = 0, tolxup_any = 0, tolx_all = 1;
   const int ax = it % N;
   for (int n = tid; n < N; n += blockDim.x) {
@@ -79,33 +119,14 @@ __device__ void converge_ladder(sp_es_ctrl* c, int it, int N, int maxiter, int i
       wmax = fmax(wmax, (double)besthist[i]);
     }
   }
-  // block reductions (sum / min / max / and / or) through shared memory
-  auto red = [&](double v, int op) {
-    for (int o = 16; o > 0; o >>= 1) {
-      const double u = __shfl_xor_sync(0xffffffffu, v, o);
-      v = op == 0 ? v + u : (op == 1 ? fmin(v, u) : fmax(v, u));
-    }
-    __syncthreads();
-    if ((tid & 31) == 0) s_red[tid >> 5] = v;
-    __syncthreads();
-    double t = s_red[0];
-    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) t = op == 0 ? t + s_red[w] : (op == 1 ? fmin(t, s_red[w]) : fmax(t, s_red[w]));
-    return t;
-  };
-  dsq = red(dsq, 0);
-  fmin_ = red(fmin_, 1);
-  fmax_ = red(fmax_, 2);
-  hmin = red(hmin, 1);
-  hmax = red(hmax, 2);
-  wmin = red(wmin, 1);
-  wmax = red(wmax, 2);
-  dmin = red(dmin, 1);
-  dmax = red(dmax, 2);
-  sdmax = red(sdmax, 2);
-  axis_all = red((double)axis_all, 1) > 0.5;
-  coord_any = red((double)coord_any, 2) > 0.5;
-  tolxup_any = red((double)tolxup_any, 2) > 0.5;
-  tolx_all = red((double)tolx_all, 1) > 0.5;
+  double v[14] = {dsq, fmin_, fmax_, hmin, hmax, wmin, wmax, dmin, dmax, sdmax,
+                  (double)axis_all, (double)coord_any, (double)tolxup_any, (double)tolx_all};
+  const int op[14] = {RED_SUM, RED_MIN, RED_MAX, RED_MIN, RED_MAX, RED_MIN, RED_MAX, RED_MIN, RED_MAX, RED_MAX,
+                      RED_MIN, RED_MAX, RED_MAX, RED_MIN};
+  block_reduce<14>(v, op, s_red);
+  dsq = v[0], fmin_ = v[1], fmax_ = v[2], hmin = v[3], hmax = v[4], wmin = v[5], wmax = v[6];
+  dmin = v[7], dmax = v[8], sdmax = v[9];
+  axis_all = v[10] > 0.5, coord_any = v[11] > 0.5, tolxup_any = v[12] > 0.5, tolx_all = v[13] > 0.5;
   if (tid == 0) {
     int st = SP_RUNNING;
     if (it >= maxiter) st = -1;

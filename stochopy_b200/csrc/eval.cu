@@ -296,7 +296,6 @@ int sp_fitness_rank(int dtype, const void* fit, int64_t P, int32_t* rank, void* 
     set_error("sp_fitness_rank: %s", cudaGetErrorString(e));
     return SP_ERR_CUDA;
   }
-  g_launches.fetch_add(2);
   return SP_OK;
 }
 

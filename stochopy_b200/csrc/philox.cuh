@@ -88,17 +88,36 @@ __device__ __forceinline__ void uniform_block(uint4 o, double (&u)[2]) {
   u[1] = __ull2double_rn(b) * 1.1102230246251565e-16;
 }
 
-// N(0,1) by Box-Muller on the same block
+// N(0,1) by Box-Muller on the same block.  fp32 uses the SFU (lg2 / sqrt / sin / cos
+// approximations, abs error ~2^-21 on reduced arguments): -ln u1 switches to the series of
+// -ln(1 - x) for u1 > 1 - 2^-6 (1 - u1 is exact there) so small radii keep their relative
+// accuracy, and the angle 2 pi u2 is centred on [-pi, pi) before sin/cos.
+// |z - exact| <= 4e-6 + 2e-6 |z| (tests/test_gpu_es.py::test_normal_draws_match_oracle).
+__device__ __forceinline__ float neg_log_u(float u) {  // -ln(u), u in (0, 1]
+  const float x = 1.0f - u;
+  const float series = x + x * x * (0.5f + x * (0.33333334f + 0.25f * x));
+  return x < 0.015625f ? series : -0.69314718f * __log2f(u);
+}
+__device__ __forceinline__ float fast_sqrt(float x) {
+  float r;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ void fast_sincos_2pi(float u, float* sn, float* cs) {  // u in [0, 1)
+  const float a = 6.2831855f * (u - (u >= 0.5f ? 1.0f : 0.0f));  // same angle mod 2 pi, in [-pi, pi)
+  *sn = __sinf(a);
+  *cs = __cosf(a);
+}
 __device__ __forceinline__ void normal_block(uint4 o, float (&z)[4]) {
   const float s = 5.9604644775390625e-08f;
   float u1 = (__uint2float_rn(o.x >> 8) + 1.0f) * s, u2 = __uint2float_rn(o.y >> 8) * s;
   float u3 = (__uint2float_rn(o.z >> 8) + 1.0f) * s, u4 = __uint2float_rn(o.w >> 8) * s;
-  float r0 = sqrtf(-2.0f * logf(u1)), r1 = sqrtf(-2.0f * logf(u3));
+  float r0 = fast_sqrt(2.0f * neg_log_u(u1)), r1 = fast_sqrt(2.0f * neg_log_u(u3));
   float sn, cs;
-  sincospif(2.0f * u2, &sn, &cs);
+  fast_sincos_2pi(u2, &sn, &cs);
   z[0] = r0 * cs;
   z[1] = r0 * sn;
-  sincospif(2.0f * u4, &sn, &cs);
+  fast_sincos_2pi(u4, &sn, &cs);
   z[2] = r1 * cs;
   z[3] = r1 * sn;
 }

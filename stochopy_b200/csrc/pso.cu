@@ -311,7 +311,6 @@ static int restart_plan_launch(const sp_pso_state* st, int it, int32_t* rank, cu
   restart_plan_kernel<<<1, 1, 0, s>>>(st->ctrl, st->P, st->N, it, st->maxiter, st->gamma, st->delta);
   SP_CHECK_LAUNCH();
   if (rank_launch<T>((const T*)st->pbestfit, st->P, rank, &st->ctrl->flag, s) != cudaSuccess) return SP_ERR_CUDA;
-  g_launches.fetch_add(2);
   return SP_OK;
 }
 

@@ -3,6 +3,7 @@
 #pragma once
 #include "objectives.cuh"
 #include "philox.cuh"
+#include "rank.cuh"
 
 namespace sp {
 
@@ -80,65 +81,6 @@ __global__ void random_fill_kernel(T* __restrict__ out, int64_t P, int N, int64_
     for (int e = 0; e < VEC; ++e)
       if (b * VEC + e < N) out[row * ld + b * VEC + e] = z[e];
   }
-}
-
-// ascending stable rank by counting: rank[i] = #{j : f_j < f_i or (f_j == f_i and j < i)}
-// = the position of i in np.argsort(f, kind="stable").  2-D grid: blockIdx.x picks 256
-// candidates i, blockIdx.y a slice of the comparands j; partial counts are added with
-// integer atomics (distinct addresses), so rank must be zero on entry -> rank_launch.
-// `gate` (optional): skip unless *gate > 0.
-template <typename T>
-__global__ void __launch_bounds__(kThreads)
-rank_kernel(const T* __restrict__ fit, int64_t P, int32_t* __restrict__ rank, const int32_t* gate, int64_t jper) {
-  if (gate != nullptr && *gate <= 0) return;
-  __shared__ T s_f[kThreads];
-  const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
-  const T mine = i < P ? fit[i] : T(0);
-  const int64_t j0 = (int64_t)blockIdx.y * jper, j1 = (j0 + jper < P) ? j0 + jper : P;
-  int r = 0;
-  for (int64_t base = j0; base < j1; base += kThreads) {
-    const int64_t j = base + threadIdx.x;
-    s_f[threadIdx.x] = j < j1 ? fit[j] : Num<T>::inf();
-    __syncthreads();
-    const int lim = (int)((j1 - base) < kThreads ? (j1 - base) : kThreads);
-    if (base + lim <= i) {  // every comparand has a smaller index: ties count
-#pragma unroll 8
-      for (int t = 0; t < lim; ++t) r += s_f[t] <= mine;
-    } else if (base > i) {  // every comparand has a larger index: ties do not count
-#pragma unroll 8
-      for (int t = 0; t < lim; ++t) r += s_f[t] < mine;
-    } else {
-#pragma unroll 8
-      for (int t = 0; t < lim; ++t) {
-        const T o = s_f[t];
-        r += (o < mine) || (o == mine && base + t < i);
-      }
-    }
-    __syncthreads();
-  }
-  if (i < P && r != 0) atomicAdd(&rank[i], r);
-}
-
-static __global__ void rank_zero_kernel(int32_t* __restrict__ rank, int64_t P, const int32_t* gate) {
-  if (gate != nullptr && *gate <= 0) return;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < P; i += (int64_t)gridDim.x * blockDim.x) rank[i] = 0;
-}
-
-// zero + count; the comparand axis is split so that about 4 waves of CTAs are in flight
-template <typename T>
-inline cudaError_t rank_launch(const T* fit, int64_t P, int32_t* rank, const int32_t* gate, cudaStream_t s) {
-  const int64_t gx = (P + kThreads - 1) / kThreads;
-  int64_t gy = (4LL * sm_count() + gx - 1) / gx;
-  const int64_t maxy = (P + kThreads - 1) / kThreads;
-  if (gy > maxy) gy = maxy;
-  if (gy < 1) gy = 1;
-  if (gy > 65535) gy = 65535;
-  int64_t jper = (P + gy - 1) / gy;
-  jper = (jper + kThreads - 1) / kThreads * kThreads;
-  gy = (P + jper - 1) / jper;
-  rank_zero_kernel<<<(int)(gx < 1024 ? gx : 1024), kThreads, 0, s>>>(rank, P, gate);
-  rank_kernel<T><<<dim3((unsigned)gx, (unsigned)gy), kThreads, 0, s>>>(fit, P, rank, gate, jper);
-  return cudaGetLastError();
 }
 
 }  // namespace sp

@@ -2,18 +2,18 @@
 // Reference: stochopy/optimize/vdcma/_vdcma.py:235-409 (generation), :426-458
 // (pvec_and_qvec, ngv_ngd), converge from cmaes/_cmaes.py:360-434 without B, D.
 //
-//   vd_inject        dy = |g| / sqrt(mnorm) dx                       one CTA      [from gen 2]
 //   vd_sample_eval   z -> y -> x, (y/d).vn, objective               row tiles, HBM: write 2 rows
 //   [Penalize]       rank -> percentiles -> weights -> arfit += penalty
-//   rank
-//   vd_wsum/wreduce  S_x, S_y, P_mu, Q_mu over the mu best           column-parallel, read 2 mu rows
-//   vd_update        mean, sigma (rank gap of rows 0/1), pc, natural gradient on (v, D), ladder
-//   vd_refresh       |v|^2, vn, diagC for the next generation
+//   rank             chunk sort + merge (rank.cuh)
+//   vd_wsum/wreduce  S_x, S_y, P_mu, Q_mu over the mu best           column-parallel, read mu rows of y
+//   vd_update        mean, sigma (rank gap of rows 0/1), pc, natural gradient on (v, D), ladder,
+//                    then |v|^2, vn, diagC and the injection dy of the next generation   one CTA
+//   (vd_inject / vd_refresh stand alone only for host-provided draws and the first generation)
 #include "es_common.cuh"
 
 namespace sp {
 
-constexpr int kVdChunks = 128;
+constexpr int kVdChunks = 256;
 
 template <typename T>
 struct VdPtrs {
@@ -21,7 +21,7 @@ struct VdPtrs {
       *xshift, *besthist, *work, *bnd_weights, *dfithist;
   int32_t* rank;
   sp_es_ctrl* ctrl;
-  int N, mu, maxiter, ilim, hist_cap, constraint, objective, it, host_z, evaluate;
+  int N, mu, maxiter, ilim, hist_cap, constraint, objective, it, host_z, evaluate, chunks;
   int64_t P, ld;
   double cc, c1, cmu, mueff, wsum, xtol, ftol, insigma;
   uint64_t seed;
@@ -34,9 +34,7 @@ struct VdPtrs {
 
 // ctrl->aux: [0] |v|^2, [1] |v|
 template <typename T>
-__global__ void __launch_bounds__(256)
-vd_refresh_kernel(const VdPtrs<T> a) {
-  __shared__ double s_red[8];
+__device__ void vd_refresh_body(const VdPtrs<T>& a, double* s_red) {
   sp_es_ctrl* c = a.ctrl;
   double sq = 0.0;
   for (int n = threadIdx.x; n < a.N; n += blockDim.x) sq += (double)a.vvec[n] * (double)a.vvec[n];
@@ -51,16 +49,17 @@ vd_refresh_kernel(const VdPtrs<T> a) {
     c->aux[1] = nv;
   }
 }
-
-// injection, _vdcma.py:243-246
 template <typename T>
 __global__ void __launch_bounds__(256)
-vd_inject_kernel(const VdPtrs<T> a) {
+vd_refresh_kernel(const VdPtrs<T> a) {
+  __shared__ double s_red[kRedDoubles];
+  vd_refresh_body<T>(a, s_red);
+}
+
+// injection of generation `it`, _vdcma.py:243-246 (nv2 = |v|^2 of the current v)
+template <typename T>
+__device__ void vd_inject_body(const VdPtrs<T>& a, int it, double nv2, double* s_red) {
   constexpr int VEC = Num<T>::VEC;
-  __shared__ double s_red[8];
-  sp_es_ctrl* c = a.ctrl;
-  if (!es_running(c) || !c->inject) return;
-  const double nv2 = c->aux[0];
   double g2 = 0.0, s1 = 0.0, s2 = 0.0;
   for (int n = threadIdx.x; n < a.N; n += blockDim.x) {
     T g;
@@ -68,7 +67,7 @@ vd_inject_kernel(const VdPtrs<T> a) {
       g = a.ginj[n];
     } else {
       T z[VEC];
-      normal_block(philox4x32((uint32_t)(n / VEC), 0u, (uint32_t)a.it, kVdInject, a.seed), z);
+      normal_block(philox4x32((uint32_t)(n / VEC), 0u, (uint32_t)it, kVdInject, a.seed), z);
       g = z[n % VEC];
     }
     g2 += (double)g * (double)g;
@@ -83,12 +82,25 @@ vd_inject_kernel(const VdPtrs<T> a) {
   const T k = (T)(sqrt(g2) / sqrt(mnorm));
   for (int n = threadIdx.x; n < a.N; n += blockDim.x) a.dy[n] = mul_rn(k, a.dx[n]);
 }
+template <typename T>
+__global__ void __launch_bounds__(256)
+vd_inject_kernel(const VdPtrs<T> a) {
+  __shared__ double s_red[kRedDoubles];
+  sp_es_ctrl* c = a.ctrl;
+  if (!es_running(c) || !c->inject) return;
+  vd_inject_body<T>(a, a.it, c->aux[0], s_red);
+}
 
-// row-local sampling + objective, _vdcma.py:239-277
+// row-local sampling + objective, _vdcma.py:239-277.  One register tile per row (z, then y,
+// then x in place); the N-vectors (vn, D, mean, scale, shift) are re-read from L1 as 16-byte
+// read-only loads per chunk, so a 1024-wide row costs ~40 registers and 3-4 CTAs fit an SM.
+// (y / D) . vn is taken from t = z + fac (z.vn) vn before the multiplication by D (y = D t)
+// instead of dividing y by D again (the reference divides, _vdcma.py:428: <= 1 ulp apart).
 template <typename T, int CH, int LPR>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, (CH * (int)sizeof(T) <= 32 ? 3 : 2))
 vd_sample_eval_kernel(const VdPtrs<T> a) {
   using TL = Tile<T, CH, LPR>;
+  using V = typename Num<T>::vec_t;
   constexpr int VEC = Num<T>::VEC;
   const sp_es_ctrl* c = a.ctrl;
   if (!es_running(c)) return;
@@ -102,10 +114,19 @@ vd_sample_eval_kernel(const VdPtrs<T> a) {
   const bool inject = c->inject != 0;
   if (blockIdx.x == 0 && threadIdx.x == 0) const_cast<sp_es_ctrl*>(c)->sigma_gen = c->sigma;
   const bool clip = a.constraint == SP_CONS_PENALIZE;
+  auto vec = [&](const T* __restrict__ p, int cc, T (&o)[VEC]) {
+    const int j0 = TL::col(cc, l, 0);
+    if (j0 < ld) {
+      const V t = __ldg(reinterpret_cast<const V*>(p + j0));
+      const T* q = reinterpret_cast<const T*>(&t);
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) o[e] = q[e];
+    } else {
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) o[e] = T(0);
+    }
+  };
 
-  TL vn, dv;
-  vn.load(a.vn, l, ld);
-  dv.load(a.dvec, l, ld);
   for (int64_t g = warp; g < groups; g += nwarps) {
     int64_t row = g * TL::RPW + sub;
     const bool live = row < a.P;
@@ -125,181 +146,264 @@ vd_sample_eval_kernel(const VdPtrs<T> a) {
     }
     T zv = 0;
 #pragma unroll
-    for (int cc = 0; cc < CH; ++cc)
+    for (int cc = 0; cc < CH; ++cc) {
+      T vn[VEC];
+      vec(a.vn, cc, vn);
 #pragma unroll
-      for (int e = 0; e < VEC; ++e) zv += y.v[cc][e] * vn.v[cc][e];
+      for (int e = 0; e < VEC; ++e) zv += y.v[cc][e] * vn[e];
+    }
     zv = group_sum<LPR>(zv);
     const bool inj_row = inject && row < 2;
-    if (inj_row) {
-      TL dyv;
-      dyv.load(a.dy, l, ld);
-#pragma unroll
-      for (int cc = 0; cc < CH; ++cc)
-#pragma unroll
-        for (int e = 0; e < VEC; ++e) y.v[cc][e] = row == 0 ? dyv.v[cc][e] : -dyv.v[cc][e];
-    } else {
-#pragma unroll
-      for (int cc = 0; cc < CH; ++cc)
-#pragma unroll
-        for (int e = 0; e < VEC; ++e)
-          y.v[cc][e] = mul_rn(dv.v[cc][e], add_rn(y.v[cc][e], mul_rn(fac, mul_rn(zv, vn.v[cc][e]))));
-    }
-    // (y / dvec) . vn for the rank-mu update (_vdcma.py:428 with y = ary / dvec)
     T yv = 0;
 #pragma unroll
-    for (int cc = 0; cc < CH; ++cc)
-#pragma unroll
-      for (int e = 0; e < VEC; ++e)
-        if (TL::col(cc, l, e) < N) yv += div_rn(y.v[cc][e], dv.v[cc][e]) * vn.v[cc][e];
-    yv = group_sum<LPR>(yv);
-    TL x;
-    {
-      TL xm;
-      xm.load(a.xmean, l, ld);
-#pragma unroll
-      for (int cc = 0; cc < CH; ++cc)
-#pragma unroll
-        for (int e = 0; e < VEC; ++e) x.v[cc][e] = add_rn(xm.v[cc][e], mul_rn(sigma, y.v[cc][e]));
-    }
-    if (live) {
-      y.store(a.ary + row * a.ld, l, ld);
-      x.store(a.arx + row * a.ld, l, ld);
-      if (l == 0) a.yvn[row] = yv;
-    }
-    if (!a.evaluate) continue;
-    {
-      TL sc, sh;
-      sc.load(a.xscale, l, ld);
-      sh.load(a.xshift, l, ld);
-#pragma unroll
-      for (int cc = 0; cc < CH; ++cc)
+    for (int cc = 0; cc < CH; ++cc) {
+      T vn[VEC], dv[VEC];
+      vec(a.vn, cc, vn);
+      vec(a.dvec, cc, dv);
+      if (inj_row) {  // rows 0 / 1 carry +-dy (_vdcma.py:247-248)
+        T dy[VEC];
+        vec(a.dy, cc, dy);
 #pragma unroll
         for (int e = 0; e < VEC; ++e) {
-          T v = x.v[cc][e];
-          if (clip) v = v < T(-1) ? T(-1) : (v > T(1) ? T(1) : v);
-          x.v[cc][e] = add_rn(mul_rn(v, sc.v[cc][e]), sh.v[cc][e]);
+          y.v[cc][e] = row == 0 ? dy[e] : -dy[e];
+          if (TL::col(cc, l, e) < N) yv += div_rn(y.v[cc][e], dv[e]) * vn[e];
         }
+      } else {
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) {
+          const T t = add_rn(y.v[cc][e], mul_rn(fac, mul_rn(zv, vn[e])));
+          yv += t * vn[e];
+          y.v[cc][e] = mul_rn(dv[e], t);
+        }
+      }
     }
-    const T f = evaluate_tile<T, CH, LPR>(a.objective, x, l, N);
+    yv = group_sum<LPR>(yv);
+    if (live) {
+      y.store(a.ary + row * a.ld, l, ld);
+      if (l == 0) a.yvn[row] = yv;
+    }
+#pragma unroll
+    for (int cc = 0; cc < CH; ++cc) {
+      T xm[VEC];
+      vec(a.xmean, cc, xm);
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) y.v[cc][e] = add_rn(xm[e], mul_rn(sigma, y.v[cc][e]));
+    }
+    if (live) y.store(a.arx + row * a.ld, l, ld);
+    if (!a.evaluate) continue;
+#pragma unroll
+    for (int cc = 0; cc < CH; ++cc) {
+      T sc[VEC], sh[VEC];
+      vec(a.xscale, cc, sc);
+      vec(a.xshift, cc, sh);
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) {
+        T v = y.v[cc][e];
+        if (clip) v = v < T(-1) ? T(-1) : (v > T(1) ? T(1) : v);
+        y.v[cc][e] = add_rn(mul_rn(v, sc[e]), sh[e]);
+      }
+    }
+    const T f = evaluate_tile<T, CH, LPR>(a.objective, y, l, N);
     if (live && l == 0) a.arfit[row] = f;
   }
 }
 
-// weighted sums over the mu best, column-parallel; chunk partials in a fixed order.
-// part[chunk][0..3][n] = S_x, S_y, P_mu, Q_mu   (_vdcma.py:291, 313, 426-441)
+// weighted sums over the mu best; part[chunk][0..3][n] = S_x, S_y, P_mu, Q_mu
+// (_vdcma.py:291, 313, 426-441).  A CTA owns 256 x VEC columns and one chunk of rows: the
+// selected rows of the chunk are compacted (in row order, so the sums are deterministic) into
+// shared memory, then streamed 4 rows at a time with 16-byte loads by two thread groups that
+// take alternate batches and are folded in a fixed order.  x is rebuilt from y (x = mean +
+// sigma y, the very operations of the sampling kernel), so only y is read.
+constexpr int kWsTile = 512, kWsUnroll = 4, kWsThreads = 512;
 template <typename T>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kWsThreads, 2)
 vd_wsum_kernel(const VdPtrs<T> a) {
+  using V = typename Num<T>::vec_t;
+  constexpr int VEC = Num<T>::VEC;
   if (!es_running(a.ctrl)) return;
-  const int n = blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t per = (a.P + kVdChunks - 1) / kVdChunks;
+  __shared__ int s_row[kWsTile];
+  __shared__ T s_w[kWsTile], s_yv[kWsTile];
+  __shared__ int s_cnt[kWsThreads / 32];
+  __shared__ T s_acc[4 * VEC][256];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, t = tid & 255, grp = tid >> 8;
+  const int j0 = (blockIdx.x * 256 + t) * VEC;
+  const bool col_ok = j0 < (int)a.ld;
+  const int64_t per = (a.P + gridDim.y - 1) / gridDim.y;
   const int64_t i0 = blockIdx.y * per, i1 = (i0 + per < a.P) ? i0 + per : a.P;
-  if (n >= a.N) return;
   const double nv2 = a.ctrl->aux[0];
-  const T k1 = (T)(nv2 / (1.0 + nv2));
-  const T vn = a.vn[n], dv = a.dvec[n];
+  const T k1 = (T)(nv2 / (1.0 + nv2)), nv2t = (T)nv2;
+  const T sigma = (T)a.ctrl->sigma_gen;
   const bool with_mu = a.cmu != 0.0;
-  T sx = 0, sy = 0, pm = 0, qm = 0;
-  for (int64_t i = i0; i < i1; ++i) {
-    const int r = a.rank[i];
-    if (r >= a.mu) continue;
-    const T w = a.weights[r];
-    const T y = a.ary[i * a.ld + n];
-    sx += w * a.arx[i * a.ld + n];
-    sy += w * y;
-    if (with_mu) {
-      const T yd = div_rn(y, dv), yv = a.yvn[i];
-      pm += w * (yd * yd - k1 * (yv * (yd * vn)) - T(1));
-      qm += w * (yv * yd - (T(0.5) * (yv * yv + T(1) + (T)nv2)) * vn);
+  T vn[VEC], inv[VEC], xm[VEC], sx[VEC], sy[VEC], pm[VEC], qm[VEC];
+#pragma unroll
+  for (int e = 0; e < VEC; ++e) {
+    const bool ok = col_ok && j0 + e < a.N;
+    vn[e] = ok ? a.vn[j0 + e] : T(0);
+    inv[e] = ok ? div_rn(T(1), a.dvec[j0 + e]) : T(0);
+    xm[e] = ok ? a.xmean[j0 + e] : T(0);
+    sx[e] = sy[e] = pm[e] = qm[e] = T(0);
+  }
+  for (int64_t t0 = i0; t0 < i1; t0 += kWsTile) {
+    __syncthreads();
+    const int64_t i = t0 + tid;
+    const int r = i < i1 ? a.rank[i] : a.mu;
+    const bool sel = r < a.mu;
+    const unsigned m = __ballot_sync(0xffffffffu, sel);
+    if (lane == 0) s_cnt[warp] = __popc(m);
+    __syncthreads();
+    int off = 0, cnt = 0;
+#pragma unroll
+    for (int w = 0; w < kWsThreads / 32; ++w) {
+      off += w < warp ? s_cnt[w] : 0;
+      cnt += s_cnt[w];
+    }
+    if (sel) {
+      off += __popc(m & ((1u << lane) - 1u));
+      s_row[off] = (int)(i - i0);
+      s_w[off] = a.weights[r];
+      s_yv[off] = a.yvn[i];
+    }
+    __syncthreads();
+    if (!col_ok) continue;
+    const T* __restrict__ ybase = a.ary + i0 * a.ld + j0;
+    for (int k = grp * kWsUnroll; k < cnt; k += 2 * kWsUnroll) {
+      V yv[kWsUnroll];
+#pragma unroll
+      for (int u = 0; u < kWsUnroll; ++u)
+        if (k + u < cnt) yv[u] = *reinterpret_cast<const V*>(ybase + (int64_t)s_row[k + u] * a.ld);
+#pragma unroll
+      for (int u = 0; u < kWsUnroll; ++u) {
+        if (k + u < cnt) {
+          const T w = s_w[k + u], yn = s_yv[k + u];
+          const T* yy = reinterpret_cast<const T*>(&yv[u]);
+#pragma unroll
+          for (int e = 0; e < VEC; ++e) {
+            const T y = yy[e];
+            sx[e] += w * add_rn(xm[e], mul_rn(sigma, y));
+            sy[e] += w * y;
+            if (with_mu) {
+              const T yd = y * inv[e];
+              pm[e] += w * (yd * yd - k1 * (yn * (yd * vn[e])) - T(1));
+              qm[e] += w * (yn * yd - (T(0.5) * (yn * yn + T(1) + nv2t)) * vn[e]);
+            }
+          }
+        }
+      }
     }
   }
+  // fold group 1 into group 0, write the chunk's partial
+  __syncthreads();
+  if (grp == 1) {
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) {
+      s_acc[e][t] = sx[e];
+      s_acc[VEC + e][t] = sy[e];
+      s_acc[2 * VEC + e][t] = pm[e];
+      s_acc[3 * VEC + e][t] = qm[e];
+    }
+  }
+  __syncthreads();
+  if (grp != 0) return;
   T* out = a.part() + (size_t)blockIdx.y * 4 * a.N;
-  out[n] = sx;
-  out[a.N + n] = sy;
-  out[2 * a.N + n] = pm;
-  out[3 * a.N + n] = qm;
+#pragma unroll
+  for (int e = 0; e < VEC; ++e)
+    if (col_ok && j0 + e < a.N) {
+      out[j0 + e] = sx[e] + s_acc[e][t];
+      out[a.N + j0 + e] = sy[e] + s_acc[VEC + e][t];
+      out[2 * a.N + j0 + e] = pm[e] + s_acc[2 * VEC + e][t];
+      out[3 * a.N + j0 + e] = qm[e] + s_acc[3 * VEC + e][t];
+    }
 }
 
-// chunk partials -> sums[q][n] in a fixed order (deterministic), one thread per (q, n)
+// chunk partials -> sums[q][n], fixed order: a CTA owns 32 outputs, 8 thread groups take
+// every 8th chunk, then the 8 group sums are added in order
 template <typename T>
 __global__ void __launch_bounds__(256)
 vd_wreduce_kernel(const VdPtrs<T> a) {
   if (!es_running(a.ctrl)) return;
-  const int e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= 4 * a.N) return;
-  const T* p = a.part() + e;
+  __shared__ T s_p[8][32];
+  const int o = threadIdx.x & 31, g = threadIdx.x >> 5;
+  const int e = blockIdx.x * 32 + o;
   T acc = 0;
+  if (e < 4 * a.N) {
+    const T* p = a.part() + e;
 #pragma unroll 8
-  for (int g = 0; g < kVdChunks; ++g) acc += p[(size_t)g * 4 * a.N];
-  a.sums()[e] = acc;
+    for (int c = g; c < a.chunks; c += 8) acc += p[(size_t)c * 4 * a.N];
+  }
+  s_p[g][o] = acc;
+  __syncthreads();
+  if (g == 0 && e < 4 * a.N) {
+    T tot = s_p[0][o];
+#pragma unroll
+    for (int k = 1; k < 8; ++k) tot += s_p[k][o];
+    a.sums()[e] = tot;
+  }
 }
 
-// mean, step size, paths, natural gradient, termination: one CTA (_vdcma.py:290-396)
-template <typename T>
+// mean, step size, paths, natural gradient, termination: one CTA (_vdcma.py:290-396).
+// The N-vectors live in registers (kVdNpt elements per thread, 256 threads: the scalar fp64
+// algebra between the reductions is replicated per warp, so few warps) and every dependent step
+// is one combined block reduction: ~10 barrier rounds instead of ~30 global round trips.
+template <typename T, int kVdNpt>
 __global__ void __launch_bounds__(256)
 vd_update_kernel(const VdPtrs<T> a) {
-  __shared__ double s_red[8];
-  __shared__ int s_best, s_r0, s_r1;
+  __shared__ double s_red[kRedDoubles];
+  __shared__ int s_best;
   sp_es_ctrl* c = a.ctrl;
   if (!es_running(c)) return;
-  const int N = a.N, tid = threadIdx.x;
-  T* Sy = a.tmp();
-  T* pv = a.tmp() + N;
-  T* qv = a.tmp() + 2 * N;
-  T* sv = a.tmp() + 3 * N;
-  T* ngv = a.tmp() + 4 * N;
-  T* ngd = a.tmp() + 5 * N;
+  const int N = a.N, tid = threadIdx.x, nt = blockDim.x;
   const double nv2 = c->aux[0], nv = c->aux[1];
-  if (tid == 0) s_best = 0;
-  __syncthreads();
-  for (int64_t i = tid; i < a.P; i += blockDim.x)
-    if (a.rank[i] == 0) s_best = (int)i;
-  if (tid == 0) {
-    s_r0 = a.rank[0];
-    s_r1 = a.P > 1 ? a.rank[1] : 0;
-  }
-  // reduced sums -> dx, xmean, S_y, P_mu, Q_mu
-  for (int n = tid; n < N; n += blockDim.x) {
+  // ---- everything this generation reads, issued up front ------------------------------------------
+  bool ok[kVdNpt];
+  T xm[kVdNpt], pc[kVdNpt], vnT[kVdNpt], dv[kVdNpt], vv[kVdNpt], Sx[kVdNpt], Sy[kVdNpt], Pm[kVdNpt], Qm[kVdNpt];
+#pragma unroll
+  for (int k = 0; k < kVdNpt; ++k) {
+    const int n = tid + k * nt;
+    ok[k] = n < N;
+    const int m = ok[k] ? n : 0;
     const T* p = a.sums();
-    const T sx = p[n], sy = p[N + n], pm = p[2 * N + n], qm = p[3 * N + n];
-    const T xm = a.xmean[n];
-    const T dx = sub_rn(sx, mul_rn((T)a.wsum, xm));  // _vdcma.py:291
-    a.dx[n] = dx;
-    a.xold[n] = xm;
-    a.xmean[n] = add_rn(xm, dx);
-    Sy[n] = sy;
-    pv[n] = pm;
-    qv[n] = qm;
+    Sx[k] = p[m], Sy[k] = p[N + m], Pm[k] = p[2 * N + m], Qm[k] = p[3 * N + m];
+    xm[k] = a.xmean[m], pc[k] = a.pc[m], vnT[k] = a.vn[m], dv[k] = a.dvec[m], vv[k] = a.vvec[m];
   }
-  __syncthreads();
+  const int r0 = a.rank[0], r1 = a.P > 1 ? a.rank[1] : 0;
+  for (int64_t i = tid; i < a.P; i += nt)
+    if (a.rank[i] == 0) s_best = (int)i;
   // sigma from the rank gap of the injected pair, _vdcma.py:299-307
   bool hsig = true;
-  double sigma = c->sigma_gen;
-  if (c->inject) {
-    const double alpha_act = (double)(s_r1 - s_r0) / ((double)a.P - 1.0);
-    const double ps = c->vd_ps + 0.3 * (alpha_act - c->vd_ps);
-    sigma *= exp(ps / sqrt((double)N));
-    hsig = ps < 0.5;
-    if (tid == 0) c->vd_ps = ps;
+  double sigma = c->sigma_gen, ps_new = c->vd_ps;
+  const bool injected = c->inject != 0;
+  if (injected) {
+    const double alpha_act = (double)(r1 - r0) / ((double)a.P - 1.0);
+    ps_new = c->vd_ps + 0.3 * (alpha_act - c->vd_ps);
+    sigma *= exp(ps_new / sqrt((double)N));
+    hsig = ps_new < 0.5;
   }
-  __syncthreads();
+  // mean, _vdcma.py:291; evolution path, :310-315
   const T kpc = (T)sqrt(a.cc * (2.0 - a.cc) * a.mueff);
-  double vmax = 0.0;
-  for (int n = tid; n < N; n += blockDim.x) {
-    T v = mul_rn(a.pc[n], (T)(1.0 - a.cc));
-    if (hsig) v = add_rn(v, mul_rn(kpc, Sy[n]));
-    a.pc[n] = v;
-    const double vn = (double)a.vn[n];
-    vmax = fmax(vmax, vn * vn);
+  T dx[kVdNpt];
+  double red2[2] = {0.0, 0.0};  // max vn^2, (pc / D) . vn
+#pragma unroll
+  for (int k = 0; k < kVdNpt; ++k) {
+    dx[k] = sub_rn(Sx[k], mul_rn((T)a.wsum, xm[k]));
+    T v = mul_rn(pc[k], (T)(1.0 - a.cc));
+    if (hsig) v = add_rn(v, mul_rn(kpc, Sy[k]));
+    pc[k] = v;
+    if (ok[k]) {
+      const int n = tid + k * nt;
+      a.dx[n] = dx[k];
+      a.xold[n] = xm[k];
+      a.xmean[n] = add_rn(xm[k], dx[k]);
+      a.pc[n] = v;
+      const double vn = (double)vnT[k];
+      red2[0] = fmax(red2[0], vn * vn);
+      red2[1] += (double)div_rn(v, dv[k]) * vn;
+    }
   }
-  // block max of vnn
-  for (int o = 16; o > 0; o >>= 1) vmax = fmax(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
-  __syncthreads();
-  if ((tid & 31) == 0) s_red[tid >> 5] = vmax;
-  __syncthreads();
-  vmax = s_red[0];
-  for (int w = 1; w < 8; ++w) vmax = fmax(vmax, s_red[w]);
-  __syncthreads();
+  {
+    const int op[2] = {RED_MAX, RED_SUM};
+    block_reduce<2>(red2, op, s_red);
+  }
+  const double vmax = red2[0], yv1 = red2[1];
   // alpha and friends, _vdcma.py:318-329
   const double gamma = 1.0 / sqrt(1.0 + nv2);
   double alpha = sqrt(nv2 * nv2 + (1.0 + nv2) / vmax * (2.0 - gamma)) / (2.0 + nv2), beta = 0.0;
@@ -307,70 +411,81 @@ vd_update_kernel(const VdPtrs<T> a) {
   else alpha = 1.0;
   const double bsca = 2.0 * alpha * alpha - beta;
   // rank-one vectors from pc / dvec, then p = cmu p_mu (+ c1 p_1), q likewise
-  double yv1 = 0.0;
-  for (int n = tid; n < N; n += blockDim.x) yv1 += (double)div_rn(a.pc[n], a.dvec[n]) * (double)a.vn[n];
-  yv1 = block_sum(yv1, s_red);
   const double k1 = nv2 / (1.0 + nv2);
+  T pv[kVdNpt], qv[kVdNpt];
   double vq = 0.0;
-  for (int n = tid; n < N; n += blockDim.x) {
-    const double vn = (double)a.vn[n];
-    double p = a.cmu == 0.0 ? 0.0 : a.cmu * (double)pv[n];
-    double q = a.cmu == 0.0 ? 0.0 : a.cmu * (double)qv[n];
+#pragma unroll
+  for (int k = 0; k < kVdNpt; ++k) {
+    const double vn = (double)vnT[k];
+    double p = a.cmu == 0.0 ? 0.0 : a.cmu * (double)Pm[k];
+    double q = a.cmu == 0.0 ? 0.0 : a.cmu * (double)Qm[k];
     if (hsig && a.c1 != 0.0) {
-      const double y1 = (double)div_rn(a.pc[n], a.dvec[n]);
+      const double y1 = (double)div_rn(pc[k], dv[k]);
       p += a.c1 * (y1 * y1 - k1 * (yv1 * y1 * vn) - 1.0);
       q += a.c1 * (yv1 * y1 - (0.5 * (yv1 * yv1 + 1.0 + nv2)) * vn);
     }
-    pv[n] = (T)p;
-    qv[n] = (T)q;
-    vq += vn * q;
+    pv[k] = (T)p;
+    qv[k] = (T)q;
+    if (ok[k]) vq += vn * q;
   }
-  vq = block_sum(vq, s_red);
   double up = 1.0;
   if (a.cmu + a.c1 > 0.0) {  // natural gradient, _vdcma.py:444-458
-    double ria = 0.0, via = 0.0;
-    for (int n = tid; n < N; n += blockDim.x) {
-      const double vn = (double)a.vn[n], vnn = vn * vn, avec = 2.0 - (bsca + 2.0 * alpha * alpha) * vnn;
-      const double r = (double)pv[n] - alpha / (1.0 + nv2) * ((2.0 + nv2) * (double)qv[n] * vn - nv2 * vq * vnn);
-      sv[n] = (T)r;  // r for now
-      ria += r * (vnn / avec);
-      via += vnn * (vnn / avec);
+    vq = block_sum(vq, s_red);
+    T sv[kVdNpt];
+    double red3[2] = {0.0, 0.0};  // ria, via
+#pragma unroll
+    for (int k = 0; k < kVdNpt; ++k) {
+      const double vn = (double)vnT[k], vnn = vn * vn, avec = 2.0 - (bsca + 2.0 * alpha * alpha) * vnn;
+      const double r = (double)pv[k] - alpha / (1.0 + nv2) * ((2.0 + nv2) * (double)qv[k] * vn - nv2 * vq * vnn);
+      sv[k] = (T)r;
+      if (ok[k]) {
+        red3[0] += r * (vnn / avec);
+        red3[1] += vnn * (vnn / avec);
+      }
     }
-    ria = block_sum(ria, s_red);
-    via = block_sum(via, s_red);
+    {
+      const int op[2] = {RED_SUM, RED_SUM};
+      block_reduce<2>(red3, op, s_red);
+    }
+    const double ria = red3[0], via = red3[1];
     double svnn = 0.0;
-    for (int n = tid; n < N; n += blockDim.x) {
-      const double vn = (double)a.vn[n], vnn = vn * vn, avec = 2.0 - (bsca + 2.0 * alpha * alpha) * vnn;
-      const double s = (double)sv[n] / avec - bsca * ria / (1.0 + bsca * via) * (vnn / avec);
-      sv[n] = (T)s;
-      svnn += s * vnn;
+#pragma unroll
+    for (int k = 0; k < kVdNpt; ++k) {
+      const double vn = (double)vnT[k], vnn = vn * vn, avec = 2.0 - (bsca + 2.0 * alpha * alpha) * vnn;
+      const double sn = (double)sv[k] / avec - bsca * ria / (1.0 + bsca * via) * (vnn / avec);
+      sv[k] = (T)sn;
+      if (ok[k]) svnn += sn * vnn;
     }
     svnn = block_sum(svnn, s_red);
-    double g2 = 0.0, dmin = 1.0 / 0.0;
-    for (int n = tid; n < N; n += blockDim.x) {
-      const double vn = (double)a.vn[n], s = (double)sv[n];
-      const double gv = (double)qv[n] / nv - alpha / nv * ((2.0 + nv2) * (vn * s) - svnn * vn);
-      const double gd = (double)a.dvec[n] * s;
-      ngv[n] = (T)gv;
-      ngd[n] = (T)gd;
-      g2 += gv * gv;
-      dmin = fmin(dmin, (double)a.dvec[n] / fabs(gd));
+    T ngv[kVdNpt], ngd[kVdNpt];
+    double red4[2] = {0.0, 1.0 / 0.0};  // |ngv|^2, min D / |ngd|
+#pragma unroll
+    for (int k = 0; k < kVdNpt; ++k) {
+      const double vn = (double)vnT[k], sn = (double)sv[k];
+      const double gv = (double)qv[k] / nv - alpha / nv * ((2.0 + nv2) * (vn * sn) - svnn * vn);
+      const double gd = (double)dv[k] * sn;
+      ngv[k] = (T)gv;
+      ngd[k] = (T)gd;
+      if (ok[k]) {
+        red4[0] += gv * gv;
+        red4[1] = fmin(red4[1], (double)dv[k] / fabs(gd));
+      }
     }
-    g2 = block_sum(g2, s_red);
-    for (int o = 16; o > 0; o >>= 1) dmin = fmin(dmin, __shfl_xor_sync(0xffffffffu, dmin, o));
-    __syncthreads();
-    if ((tid & 31) == 0) s_red[tid >> 5] = dmin;
-    __syncthreads();
-    dmin = s_red[0];
-    for (int w = 1; w < 8; ++w) dmin = fmin(dmin, s_red[w]);
-    __syncthreads();
-    up = fmin(1.0, 0.7 * nv / sqrt(g2));  // at most 70 % change, _vdcma.py:361-363
-    up = fmin(up, 0.7 * dmin);
-    for (int n = tid; n < N; n += blockDim.x) {
-      a.vvec[n] = add_rn(a.vvec[n], mul_rn((T)up, ngv[n]));
-      a.dvec[n] = add_rn(a.dvec[n], mul_rn((T)up, ngd[n]));
+    {
+      const int op[2] = {RED_SUM, RED_MIN};
+      block_reduce<2>(red4, op, s_red);
     }
+    up = fmin(1.0, 0.7 * nv / sqrt(red4[0]));  // at most 70 % change, _vdcma.py:361-363
+    up = fmin(up, 0.7 * red4[1]);
+#pragma unroll
+    for (int k = 0; k < kVdNpt; ++k)
+      if (ok[k]) {
+        const int n = tid + k * nt;
+        a.vvec[n] = add_rn(vv[k], mul_rn((T)up, ngv[k]));
+        a.dvec[n] = add_rn(dv[k], mul_rn((T)up, ngd[k]));
+      }
   }
+  __syncthreads();  // s_best, and the vectors written above, are visible to the whole CTA
   if (tid == 0) {
     const double best = (double)a.arfit[s_best];
     c->base.gbest_row = s_best;
@@ -379,6 +494,7 @@ vd_update_kernel(const VdPtrs<T> a) {
     c->hsig = hsig ? 1 : 0;
     c->nfev += a.P;
     c->sigma = sigma;
+    if (injected) c->vd_ps = ps_new;
     c->inject = 1;
     c->aux[2] = up;
   }
@@ -386,15 +502,26 @@ vd_update_kernel(const VdPtrs<T> a) {
   // diagC still describes the population just evaluated (_vdcma.py:380-396: no B, D)
   converge_ladder<T>(c, a.it, N, a.maxiter, a.ilim, a.P, a.xmean, a.xold, a.besthist, a.arfit, a.pc, a.diagC, 1,
                      (const T*)nullptr, (const T*)nullptr, a.xtol, a.ftol, a.insigma, s_red);
+  // next generation's |v|^2, vn, diagC and (in-kernel draws) its injected direction dy
+  __syncthreads();
+  vd_refresh_body<T>(a, s_red);
+  __syncthreads();
+  if (!a.host_z && es_running(c)) vd_inject_body<T>(a, a.it + 1, c->aux[0], s_red);
 }
 
 template <typename T>
 __global__ void __launch_bounds__(256)
 vd_penalty_state_kernel(const VdPtrs<T> a) {
-  __shared__ double s_red[8];
+  __shared__ double s_red[kRedDoubles];
   if (!es_running(a.ctrl)) return;
   penalize_state<T>(a.ctrl, a.it, a.N, a.P, a.hist_cap, a.mueff, a.sorted(), a.xmean, a.xold, a.diagC, 1,
                     a.bnd_weights, a.dfithist, a.coef(), s_red);
+}
+
+// row chunks of the weighted sums: >= 64 rows each, at most kVdChunks
+static inline int vd_chunks(int64_t P) {
+  int64_t c = P / 64;
+  return (int)(c < 1 ? 1 : (c > kVdChunks ? kVdChunks : c));
 }
 
 template <typename T>
@@ -433,6 +560,7 @@ static VdPtrs<T> vd_ptrs(const sp_vd_state* st, int it, int evaluate) {
   a.it = it;
   a.host_z = st->host_z;
   a.evaluate = evaluate;
+  a.chunks = vd_chunks(st->P);
   a.P = st->P;
   a.ld = st->ld;
   a.cc = st->cc;
@@ -455,9 +583,11 @@ static int vd_sample(const sp_vd_state* st, int it, int evaluate, cudaStream_t s
     set_error("sp_vd_sample: ndim %d exceeds the compiled row shapes", st->N);
     return SP_ERR_SHAPE;
   }
-  vd_inject_kernel<T><<<1, 256, 0, s>>>(a);
-  SP_CHECK_LAUNCH();
-  const int grid = grid_for_rows(st->P, sh.lpr, sh.ch >= 4 ? 2 : 4);
+  if (st->host_z) {  // in-kernel draws: dy was prepared by the previous generation's vd_update_kernel
+    vd_inject_kernel<T><<<1, 256, 0, s>>>(a);
+    SP_CHECK_LAUNCH();
+  }
+  const int grid = grid_for_rows(st->P, sh.lpr, sh.ch * (int)sizeof(T) <= 32 ? 3 : 2);
 #define SP_CALL(TT, C, L) vd_sample_eval_kernel<TT, C, L><<<grid, kThreads, 0, s>>>(a)
   SP_DISPATCH_SHAPE(T, sh, SP_CALL);
 #undef SP_CALL
@@ -472,7 +602,6 @@ static int vd_update(const sp_vd_state* st, int it, cudaStream_t s) {
   const int N = st->N;
   if (st->constraint == SP_CONS_PENALIZE) {
     if (rank_launch<T>(a.arfit, P, a.rank, nullptr, s) != cudaSuccess) return SP_ERR_CUDA;
-    g_launches.fetch_add(2);
     scatter_sorted_kernel<T><<<cdiv(P, 256) < 1024 ? cdiv(P, 256) : 1024, 256, 0, s>>>(a.arfit, a.rank, a.sorted(), P, st->ctrl);
     SP_CHECK_LAUNCH();
     vd_penalty_state_kernel<T><<<1, 256, 0, s>>>(a);
@@ -482,14 +611,15 @@ static int vd_update(const sp_vd_state* st, int it, cudaStream_t s) {
     SP_CHECK_LAUNCH();
   }
   if (rank_launch<T>(a.arfit, P, a.rank, nullptr, s) != cudaSuccess) return SP_ERR_CUDA;
-  g_launches.fetch_add(2);
-  vd_wsum_kernel<T><<<dim3(cdiv(N, 256), kVdChunks), 256, 0, s>>>(a);
+  vd_wsum_kernel<T><<<dim3(cdiv(st->ld, 256 * Num<T>::VEC), a.chunks), kWsThreads, 0, s>>>(a);
   SP_CHECK_LAUNCH();
-  vd_wreduce_kernel<T><<<cdiv(4 * N, 256), 256, 0, s>>>(a);
+  vd_wreduce_kernel<T><<<cdiv(4 * N, 32), 256, 0, s>>>(a);
   SP_CHECK_LAUNCH();
-  vd_update_kernel<T><<<1, 256, 0, s>>>(a);
-  SP_CHECK_LAUNCH();
-  vd_refresh_kernel<T><<<1, 256, 0, s>>>(a);
+  // also refreshes vn / diagC (and dy) for the next generation
+  if (N <= 256) vd_update_kernel<T, 1><<<1, 256, 0, s>>>(a);
+  else if (N <= 512) vd_update_kernel<T, 2><<<1, 256, 0, s>>>(a);
+  else if (N <= 1024) vd_update_kernel<T, 4><<<1, 256, 0, s>>>(a);
+  else vd_update_kernel<T, 8><<<1, 256, 0, s>>>(a);
   SP_CHECK_LAUNCH();
   return SP_OK;
 }

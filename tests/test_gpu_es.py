@@ -69,16 +69,21 @@ def test_sym_eigh_fp32_and_degenerate():
     assert np.allclose(w, 1.0) and np.allclose(np.abs(B), np.eye(7))
 
 
-@pytest.mark.parametrize("P", [1, 2, 10, 257, 4096, 20000])
-def test_fitness_rank_is_a_stable_argsort(P):
+@pytest.mark.parametrize("dtype", ["float64", "float32"])
+@pytest.mark.parametrize("P", [1, 2, 3, 10, 257, 512, 513, 2048, 2049, 4096, 20000, 70001])
+def test_fitness_rank_is_a_stable_argsort(P, dtype):
+    """chunk sort + merge rank (rank.cuh): one chunk (P <= 512), several, ragged last chunk; ties, -0.0, inf"""
     import torch
 
     from stochopy_b200 import _lib as L
     from stochopy_b200.optimize._common import Engine
 
-    eng = Engine("float64")
+    eng = Engine(dtype)
     rs = np.random.RandomState(P)
-    f = rs.normal(0, 1, P).round(2 if P > 100 else 6)  # rounding makes ties
+    f = rs.normal(0, 1, P).round(2 if P > 100 else 6).astype(dtype)  # rounding makes ties
+    if P > 10:
+        f[rs.randint(P, size=4)] = [-0.0, 0.0, np.inf, -np.inf]
+        f[rs.randint(P, size=3)] = 1.0e30  # the CPSO restart sentinel (_cpso.py:424)
     d = eng.upload_vec(f)
     rank = eng.zeros(P, dtype=torch.int32)
     L.call("sp_fitness_rank", eng.sp_dt, d.data_ptr(), P, rank.data_ptr(), eng.stream)
@@ -86,6 +91,31 @@ def test_fitness_rank_is_a_stable_argsort(P):
     want = np.empty(P, dtype=np.int64)
     want[order] = np.arange(P)
     assert np.array_equal(rank.cpu().numpy(), want)
+
+
+@pytest.mark.parametrize("dtype", ["float64", "float32"])
+def test_normal_draws_match_oracle(dtype):
+    """N(0,1) draws of the ES kernels (Philox + Box-Muller, philox.cuh) against oracle/philox.py on the
+    same counters.  fp64: libm accuracy.  fp32: the kernels use the SFU approximations, stated tolerance
+    |dz| <= 4e-6 + 2e-6 |z|; the tail (|z| > 4) and the small radii (|z| < 1e-3) are in the sample."""
+    import torch
+
+    from oracle import philox as oph
+    from stochopy_b200 import _lib as L
+    from stochopy_b200.optimize._common import Engine
+
+    eng = Engine(dtype)
+    P, N, it, purpose, seed = 4096, 515, 7, 3, 12345
+    out = eng.rows(P, N)
+    L.call("sp_random_fill", eng.sp_dt, out.data_ptr(), P, N, eng.ld(N), it, purpose, seed, 1, eng.stream)
+    got = eng.download_rows(out, P, N)
+    want = oph.normal(np.arange(P), N, it, purpose, seed, np.dtype(dtype)).astype(np.float64)
+    assert np.abs(want).max() > 4.0 and np.abs(want).min() < 1e-3
+    if dtype == "float64":
+        assert np.allclose(got, want, rtol=1e-11, atol=1e-13)
+    else:
+        assert np.all(np.abs(got - want) <= 4e-6 + 2e-6 * np.abs(want))
+    assert abs(got.mean()) < 5e-3 and abs(got.std() - 1.0) < 5e-3
 
 
 # ---- reference trajectories (numpy draws + LAPACK eigh = the reference's exact path) -----------
