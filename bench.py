@@ -239,7 +239,9 @@ def our_arm(args):
         for k in range(K):
             flush.fill_(k & 1)
             ev[k][0].record()
-            L.call("sp_de_generation", C.byref(st), it, eng.stream)
+            # chained like sp_de_run does it: generation k resolves the argmin / gbest / status of
+            # generation k-1 in its prologue and leaves its own to k+1; the last one resolves itself
+            L.call("sp_de_generation_chained", C.byref(st), it, (1 if k > 0 else 0) | (2 if k < K - 1 else 0), eng.stream)
             ev[k][1].record()
             it += 1
         barrier()
@@ -295,7 +297,9 @@ def our_arm(args):
             "config": {"workload": f"DE best1bin, Rosenbrock ndim={N}, popsize={P} per GPU, fp32, bounds +-{BOUND}, "
                                    "one independent seed per GPU, in-kernel Philox draws",
                        "popsize": P, "ndim": N, "l2": "flushed (256 MiB write) before every timed generation",
-                       "timing": "CUDA events around each generation launch, summed; max over ranks",
+                       "timing": "CUDA events around each generation launch, summed; max over ranks; generations chained "
+                                 "as in sp_de_run (each launch resolves the previous generation's argmin/gbest/status "
+                                 "in its prologue, the last one its own)",
                        "best_fun_over_seeds": best_fun},
             "value_l2_resident": world * P * K / (warm_ms * 1e-3),
             "ms_per_step_l2_resident": warm_ms / K,

@@ -140,6 +140,17 @@ typedef struct {
   const void* repair;     /* (P x ld)  de/_constraints.py:24 uniform(lower,upper) */
 } sp_de_state;
 int sp_de_generation(const sp_de_state* st, int it, void* stream);
+/* Chained generations.  SP_CHAIN_OUT: this generation leaves the reduction of its
+ * per-CTA minima (gbest, |gbest_old - gbest_new|, nit, status: selection_sync,
+ * _common.py:129-158) to the NEXT launch, which must carry SP_CHAIN_IN and resolves it
+ * in its prologue before it touches the population (so nit/status are exactly the
+ * reference's per-generation test).  ctrl/gbest are current only after a launch
+ * without SP_CHAIN_OUT.  sp_de_chainable() != 0 when the state runs on the kernel
+ * that supports this (in-kernel draws, device objective, full-warp rows). */
+#define SP_CHAIN_IN 1
+#define SP_CHAIN_OUT 2
+int sp_de_chainable(const sp_de_state* st);
+int sp_de_generation_chained(const sp_de_state* st, int it, int flags, void* stream);
 /* propose only: writes the trial population U into X[(it&1)^1] (SP_OBJ_HOST path) */
 int sp_de_propose(const sp_de_state* st, int it, void* stream);
 /* enqueue generations it_first .. it_first+n-1 (Philox draws only) */

@@ -134,6 +134,8 @@ SIGNATURES = {
     "sp_select_sync": (_i, [_i, _i, _i, _d, _d, vp, vp, vp, vp, _i64, _i, _i64, _i, vp, vp, vp, vp]),
     "sp_best_init": (_i, [_i, vp, vp, _i64, _i, _i64, vp, vp, vp, vp]),
     "sp_de_generation": (_i, [C.POINTER(DeState), _i, vp]),
+    "sp_de_generation_chained": (_i, [C.POINTER(DeState), _i, _i, vp]),
+    "sp_de_chainable": (_i, [C.POINTER(DeState)]),
     "sp_de_propose": (_i, [C.POINTER(DeState), _i, vp]),
     "sp_de_run": (_i, [C.POINTER(DeState), _i, _i, vp]),
     "sp_pso_generation": (_i, [C.POINTER(PsoState), _i, vp]),

@@ -163,24 +163,32 @@ __device__ __forceinline__ Best warp_best(Best b) {
   return b;
 }
 
+// minimum over the CTA (valid in thread 0 and, after the barrier, in s_best[0..warps))
+__device__ __forceinline__ Best block_best(Best mine, Best* s_best /* [32] shared */) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  mine = warp_best(mine);
+  if (lane == 0) s_best[warp] = mine;
+  __syncthreads();
+  Best b{1.0 / 0.0, 0x7fffffffffffffffLL};
+  if (warp == 0) {
+    if (lane < (int)(blockDim.x >> 5)) b = s_best[lane];
+    b = warp_best(b);
+  }
+  return b;
+}
+
 // Per-CTA minimum -> scratch[blockIdx]; the last CTA to arrive reduces all of
 // them.  Returns true (for every thread of that last CTA) with the global best.
 __device__ __forceinline__ bool grid_best(Best mine, Best* scratch, sp_ctrl* ctrl, Best* out) {
   __shared__ Best s_best[32];  // up to 1024 threads
   __shared__ bool s_last;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  mine = warp_best(mine);
-  if (lane == 0) s_best[warp] = mine;
-  __syncthreads();
-  if (warp == 0) {
-    Best b = lane < (blockDim.x >> 5) ? s_best[lane] : Best{1.0 / 0.0, 0x7fffffffffffffffLL};
-    b = warp_best(b);
-    if (lane == 0) {
-      scratch[blockIdx.x] = b;
-      __threadfence();
-      unsigned prev = atomicAdd(&ctrl->done_blocks, 1u);
-      s_last = (prev == gridDim.x - 1);
-    }
+  Best b0 = block_best(mine, s_best);
+  if (warp == 0 && lane == 0) {
+    scratch[blockIdx.x] = b0;
+    __threadfence();
+    unsigned prev = atomicAdd(&ctrl->done_blocks, 1u);
+    s_last = (prev == gridDim.x - 1);
   }
   __syncthreads();
   if (!s_last) return false;
@@ -200,6 +208,29 @@ __device__ __forceinline__ bool grid_best(Best mine, Best* scratch, sp_ctrl* ctr
   *out = b;
   if (threadIdx.x == 0) ctrl->done_blocks = 0;  // ready for the next launch
   return true;
+}
+
+// ---- chained generations ---------------------------------------------------------
+// A generation launched with SP_CHAIN_OUT skips the last-CTA epilogue: every CTA only
+// leaves its (fitness, row) minimum in a scratch region picked by the generation's
+// parity.  The next launch (SP_CHAIN_IN) reduces those <= 148 records in every CTA's
+// prologue -- the stop decision needs only the best fitness and the generation count --
+// and one warp of CTA 0 writes gbest / dist / nit / status for the generation before.
+// The serial tail (fence, atomic, scratch read, row read: ~9k cycles on one SM while
+// 147 idle) leaves the critical path; the scratch regions are disjoint from region 0,
+// which grid_best() uses.
+constexpr int kChainRegion = 512;  // records per region; regions 1 and 2 (parity)
+__device__ __forceinline__ Best* chain_region(Best* scratch, int it) { return scratch + (1 + (it & 1)) * kChainRegion; }
+
+// warp-level read of the previous generation's per-CTA minima (valid in every lane)
+__device__ __forceinline__ Best chain_best(const Best* region, int n) {
+  const int lane = threadIdx.x & 31;
+  Best b{1.0 / 0.0, 0x7fffffffffffffffLL};
+  for (int i = lane; i < n; i += 32) {
+    Best o{__ldcg(&region[i].f), __ldcg(&region[i].row)};
+    if (better(o.f, o.row, b.f, b.row)) b = o;
+  }
+  return warp_best(b);
 }
 
 // Last-CTA epilogue of every generation: new best row -> gbest, distance to
@@ -237,6 +268,39 @@ __device__ __forceinline__ void finalize_generation(Best b, const T* __restrict_
       ctrl->status = st;
     }
   }
+}
+
+// the same epilogue executed by ONE warp (chained generations: a warp of CTA 0 resolves the
+// generation before while the other warps already work on rows)
+template <typename T>
+__device__ __forceinline__ void finalize_generation_warp(Best b, const T* __restrict__ xrows, int64_t ld, int N,
+                                                         T* gbest, sp_ctrl* ctrl, int it, int maxiter, double xtol,
+                                                         double ftol) {
+  const int lane = threadIdx.x & 31;
+  const T* src = xrows + b.row * ld;
+  double acc = 0.0;
+  for (int j = lane; j < N; j += 32) {
+    T nv = src[j];
+    double d = (double)(T)(gbest[j] - nv);
+    acc += d * d;
+    gbest[j] = nv;
+  }
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) {
+    double dist = sqrt(acc);
+    ctrl->gbest_row = b.row;
+    ctrl->gfit = b.f;
+    ctrl->dist = dist;
+    ctrl->nit = it;
+    int st = SP_RUNNING;
+    if (dist <= xtol && b.f <= ftol) st = 0;
+    else if (b.f <= ftol) st = 1;
+    else if (it >= maxiter) st = -1;
+    ctrl->status = st;
+  }
+}
+__device__ __forceinline__ bool chain_stops(double f, int it, int maxiter, double ftol) {
+  return f <= ftol || it >= maxiter;  // status 0 / 1 / -1 of _common.py:135-158: all of them stop
 }
 
 __device__ __forceinline__ bool running(const sp_ctrl* ctrl) {

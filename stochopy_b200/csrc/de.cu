@@ -168,7 +168,7 @@ de_generation_kernel(const DeArgs<T> a) {
 
 
 template <typename T>
-static int de_launch(const sp_de_state* st, int it, int propose_only, cudaStream_t s) {
+static int de_launch(const sp_de_state* st, int it, int propose_only, int chain, cudaStream_t s) {
   Shape sh;
   if (!pick_shape(st->N, Num<T>::VEC, &sh)) {
     set_error("sp_de_generation: ndim %d exceeds the compiled row shapes", st->N);
@@ -202,10 +202,17 @@ static int de_launch(const sp_de_state* st, int it, int propose_only, cudaStream
   a.donors = st->donors;
   a.irand = st->irand;
   a.repair = (const T*)st->repair;
+  a.chain = 0;
   const bool philox = st->r1 == nullptr;
   const int k = de_donor_count(st->strategy);
-  if (philox && sh.lpr == 32 && !g_force_direct && de_tma_fits(sh.ch, st->P, k, st->ld, sizeof(T))) {
+  const bool pool = philox && sh.lpr == 32 && !g_force_direct && de_tma_fits(sh.ch, st->P, k, st->ld, sizeof(T));
+  if (!pool && chain != 0) {  // the direct-load kernel always resolves its own generation
+    set_error("sp_de_generation_chained: this problem shape does not run on the pool kernel (sp_de_chainable)");
+    return SP_ERR_ARG;
+  }
+  if (pool) {
     a.cr_cut = crossover_cut<T>(st->CR);
+    a.chain = propose_only ? 0 : chain;
     cudaError_t e = de_tma_dispatch(a, sh.ch, s);
     if (e != cudaSuccess) {
       set_error("sp_de_generation: %s", cudaGetErrorString(e));
@@ -254,21 +261,43 @@ int sp_de_generation(const sp_de_state* st, int it, void* stream) {
   if (rc) return rc;
   SP_CHECK_ARG(st->objective >= SP_OBJ_ACKLEY && st->objective <= SP_OBJ_STYBLINSKI_TANG,
                "device objective required (use sp_de_propose + sp_select_sync for host objectives)");
-  return st->dtype == SP_F32 ? de_launch<float>(st, it, 0, (cudaStream_t)stream)
-                             : de_launch<double>(st, it, 0, (cudaStream_t)stream);
+  return st->dtype == SP_F32 ? de_launch<float>(st, it, 0, 0, (cudaStream_t)stream)
+                             : de_launch<double>(st, it, 0, 0, (cudaStream_t)stream);
+}
+
+int sp_de_chainable(const sp_de_state* st) {
+  if (st == nullptr || st->r1 != nullptr || g_force_direct) return 0;
+  if (st->objective < SP_OBJ_ACKLEY || st->objective > SP_OBJ_STYBLINSKI_TANG) return 0;
+  const int vec = st->dtype == SP_F32 ? 4 : 2;
+  Shape sh;
+  if (!pick_shape(st->N, vec, &sh) || sh.lpr != 32) return 0;
+  return de_tma_fits(sh.ch, st->P, de_donor_count(st->strategy), st->ld, st->dtype == SP_F32 ? 4 : 8) ? 1 : 0;
+}
+
+int sp_de_generation_chained(const sp_de_state* st, int it, int flags, void* stream) {
+  int rc = de_check(st, it);
+  if (rc) return rc;
+  SP_CHECK_ARG((flags & ~(SP_CHAIN_IN | SP_CHAIN_OUT)) == 0, "flags");
+  SP_CHECK_ARG(st->objective >= SP_OBJ_ACKLEY && st->objective <= SP_OBJ_STYBLINSKI_TANG, "device objective required");
+  SP_CHECK_ARG(flags == 0 || sp_de_chainable(st), "state is not chainable (sp_de_chainable)");
+  return st->dtype == SP_F32 ? de_launch<float>(st, it, 0, flags, (cudaStream_t)stream)
+                             : de_launch<double>(st, it, 0, flags, (cudaStream_t)stream);
 }
 
 int sp_de_propose(const sp_de_state* st, int it, void* stream) {
   int rc = de_check(st, it);
   if (rc) return rc;
-  return st->dtype == SP_F32 ? de_launch<float>(st, it, 1, (cudaStream_t)stream)
-                             : de_launch<double>(st, it, 1, (cudaStream_t)stream);
+  return st->dtype == SP_F32 ? de_launch<float>(st, it, 1, 0, (cudaStream_t)stream)
+                             : de_launch<double>(st, it, 1, 0, (cudaStream_t)stream);
 }
 
 int sp_de_run(const sp_de_state* st, int it_first, int n, void* stream) {
   SP_CHECK_ARG(st != nullptr && st->r1 == nullptr, "sp_de_run needs in-kernel draws");
+  // inside the chunk the generations are chained: only the last one runs the last-CTA epilogue
+  const bool chain = sp_de_chainable(st) != 0;
   for (int g = 0; g < n; ++g) {
-    int rc = sp_de_generation(st, it_first + g, stream);
+    const int flags = chain ? ((g > 0 ? SP_CHAIN_IN : 0) | (g < n - 1 ? SP_CHAIN_OUT : 0)) : 0;
+    int rc = sp_de_generation_chained(st, it_first + g, flags, stream);
     if (rc) return rc;
   }
   return SP_OK;

@@ -25,6 +25,7 @@ struct DeArgs {
   const int64_t* donors;
   const int64_t* irand;
   const T* repair;
+  int chain;        // SP_CHAIN_IN / SP_CHAIN_OUT (pool kernel only)
   uint64_t cr_cut;  // integer form of `r <= CR` for the Philox words (crossover_cut)
 };
 

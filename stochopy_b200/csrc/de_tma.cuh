@@ -147,14 +147,28 @@ de_pool_kernel(const DeArgs<T> a, int nb, const PhiloxKeys keys) {
   // kernel wrote (status, pbestfit, gbest, the population).
   pdl_wait();
   if (!running(a.ctrl)) return;
+  const bool chain_in = (a.chain & SP_CHAIN_IN) != 0;
+  __shared__ Best s_top;
+  if (chain_in && wib == 0) {  // best of the generation before, from its per-CTA minima
+    const Best b = chain_best(chain_region(a.scratch, a.it - 1), (int)gridDim.x);
+    if (lane == 0) s_top = b;
+  }
   pdl_launch_dependents();  // the next generation may start its own prologue as SMs free up
   for (int t = tid; t < rows; t += blockDim.x) s_best[t] = a.pbestfit[b0 + t];
   TL gb;
-  if (Strat<STRAT>::kBest) gb.load(a.gbest, lane, ld);
+  if (Strat<STRAT>::kBest && !chain_in) gb.load(a.gbest, lane, ld);
   const uint64_t cut = a.cr_cut;
   const T F = a.F;
   const uint32_t it = (uint32_t)a.it;
   __syncthreads();
+  if (chain_in) {
+    const Best top = s_top;
+    // one warp of CTA 0 writes gbest / dist / nit / status of generation it-1 (off the critical path)
+    if (blockIdx.x == 0 && wib == warps - 1)
+      finalize_generation_warp<T>(top, a.Xold, a.ld, a.N, a.gbest, a.ctrl, a.it - 1, a.maxiter, a.xtol, a.ftol);
+    if (chain_stops(top.f, a.it - 1, a.maxiter, a.ftol)) return;
+    if (Strat<STRAT>::kBest) gb.load(a.Xold + top.row * (int64_t)ld, lane, ld);
+  }
 
   // ---- phase 1: claim / fetch / process ----------------------------------------------------
   const uint32_t s_next_addr = smem_u32(s_next);
@@ -302,6 +316,12 @@ de_pool_kernel(const DeArgs<T> a, int nb, const PhiloxKeys keys) {
     a.pbestfit[b0 + t] = b;
     a.pfit[b0 + t] = s_fnew[t];
     if (better((double)b, b0 + t, mine.f, mine.row)) mine = Best{(double)b, b0 + t};
+  }
+  if (a.chain & SP_CHAIN_OUT) {  // leave the CTA minimum for the next launch's prologue
+    __shared__ Best s_red[32];
+    const Best b = block_best(mine, s_red);
+    if (tid == 0) chain_region(a.scratch, a.it)[blockIdx.x] = b;
+    return;
   }
   Best top;
   if (grid_best(mine, a.scratch, a.ctrl, &top))

@@ -354,6 +354,52 @@ def test_reference_trajectories_through_minimize(run):
     assert np.allclose(r.x, got["x"], rtol=1e-7, atol=1e-10) and np.isclose(r.fun, got["fun"], rtol=1e-6, atol=1e-12)
 
 
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("strategy,cons,ftol,maxiter", [("best1bin", None, 5.0e2, 400), ("rand1bin", "Random", -1.0, 23),
+                                                        ("best2bin", None, 1.0e9, 50)])
+def test_de_chained_generations_equal_unchained(strategy, cons, ftol, maxiter, dtype):
+    """sp_de_run chains its generations (SP_CHAIN_OUT / SP_CHAIN_IN: the per-generation
+    argmin / gbest / status resolution moves into the next launch's prologue).  State,
+    nit and status must equal the one-launch-per-generation path bit for bit, including
+    a stop in the middle of a chunk (ftol), at the chunk's first generation (1e9) and by maxiter."""
+    import ctypes as C
+
+    from gpu_util import DeRig, device_eval
+    from stochopy_b200 import _lib as L
+
+    P, N = 3001, 128
+    rs = np.random.RandomState(3)
+    X = rs.uniform(-5.12, 5.12, (P, N)).astype(dtype)
+    fit = device_eval("sphere", X.astype(np.float64), dtype).astype(dtype)
+    gbest = X[int(np.argmin(fit))]
+    lo, hi = -5.12 * np.ones(N), 5.12 * np.ones(N)
+
+    def rig():
+        return DeRig(X, fit, gbest, "sphere", strategy, cons, 0.5, 0.9, lo, hi, seed=11, dtype=dtype, maxiter=maxiter,
+                     xtol=1e-8, ftol=ftol)
+
+    a = rig()
+    assert L.load().sp_de_chainable(C.byref(a.st)) == 1
+    it = 1
+    while a.eng.read_ctrl(a.ctrl).status == L.SP_RUNNING:
+        it += 1
+        a.step(it)
+    ca = a.eng.read_ctrl(a.ctrl)
+    assert ca.nit == it and (ftol < 0 or ca.nit < maxiter or ftol > 1e8)
+
+    b = rig()
+    nxt = 2
+    while b.eng.read_ctrl(b.ctrl).status == L.SP_RUNNING:
+        L.call("sp_de_run", C.byref(b.st), nxt, 7, b.eng.stream)
+        nxt += 7
+    cb = b.eng.read_ctrl(b.ctrl)
+    assert (cb.nit, cb.status, cb.gbest_row, cb.gfit) == (ca.nit, ca.status, ca.gbest_row, ca.gfit)
+    assert np.isclose(cb.dist, ca.dist, rtol=1e-12, atol=0)
+    oa, ob = a.get(ca.nit), b.get(cb.nit)
+    for k in ("X", "pbestfit", "pfit", "gbest"):
+        assert np.array_equal(oa[k], ob[k]), k
+
+
 @pytest.mark.parametrize("method,opts", [
     ("de", dict(strategy="best1bin")), ("de", dict(strategy="rand1bin", constraints="Random")),
     ("pso", dict(constraints="Shrink")), ("cpso", dict(competitivity=1.0)),
