@@ -92,12 +92,20 @@ def main():
             report(f"C5 vdcma ackley N=1024 P=16384 {dt_name}", r.nfev, dt, dict(nit=r.nit, fun=r.fun, status=r.status))
     else:
         b64 = [[-5.12, 5.12]] * 64
-        o = dict(maxiter=300 // q, popsize=32768, seed=0, dtype="float32", competitivity=1.0, **off)
-        parallel.cpso_sharded(sb.factory.styblinski_tang, b64, **dict(o, maxiter=5))
-        dist.barrier()
-        dt, r = timed(lambda: parallel.cpso_sharded(sb.factory.styblinski_tang, b64, **o), 2)
-        report(f"C3 cpso ONE swarm sharded over {world} GPUs, styblinski_tang N=64 P=32768 fp32", r.nfev, dt,
-               dict(nit=r.nit, fun=r.fun))
+        # C3: ONE swarm row-sharded over the GPUs; "peer" = exchange fused into the kernels over
+        # NVLink peer memory, "nccl" = one host-driven all-gather per generation (the baseline)
+        for method, comp in (("cpso", 1.0), ("pso", None)):
+            for exchange in ("peer", "nccl"):
+                o = dict(maxiter=300 // q, popsize=32768, seed=0, dtype="float32", competitivity=comp,
+                         exchange=exchange, **off)
+                parallel.cpso_sharded(sb.factory.styblinski_tang, b64, **dict(o, maxiter=5))
+                dist.barrier()
+                dt, r = timed(lambda: parallel.cpso_sharded(sb.factory.styblinski_tang, b64, **o), 2)
+                report(f"C3 {method} ONE swarm sharded over {world} GPUs ({exchange} exchange), styblinski_tang N=64 "
+                       f"P=32768 fp32", r.nfev, dt, dict(nit=r.nit, fun=r.fun))
+        # warm-up of the vdcma kernels (module load, allocator) before the timed seeds
+        parallel.minimize_seeds(sb.factory.ackley, [[-5.12, 5.12]] * 1024, [0] * world, method="vdcma",
+                                options=dict(maxiter=3, popsize=16384, dtype="float32", **off))
         # C5: 8 seeds per GPU, independent
         seeds = list(range(8 * world if not args.quick else world))
         o = dict(maxiter=50 // q, popsize=16384, dtype="float32", **off)

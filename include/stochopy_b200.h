@@ -187,8 +187,14 @@ typedef struct {
   int64_t row0;
   int64_t P_total;
   void* xch;       /* (ld + 1) */
-  int32_t shard;
+  int32_t shard;   /* 0 whole swarm; 1 sharded, exchange by the caller (xch + sp_gbest_reduce);
+                    * 2 sharded, exchange inside the kernels over the peer mailboxes below */
   int32_t pad2_;
+  /* shard == 2 (sp_peer_*): world mailboxes of sp_peer_bytes() each, one per rank, all mapped
+   * into this process (CUDA IPC; NVLink peer memory on an NVSwitch box). */
+  int32_t world, rank;
+  void* mailbox;         /* this rank's own mailbox (device pointer) */
+  void* const* peers;    /* DEVICE array [world]: rank r's mailbox as addressed from this process */
 } sp_pso_state;
 int sp_pso_generation(const sp_pso_state* st, int it, void* stream);
 int sp_pso_propose(const sp_pso_state* st, int it, void* stream);
@@ -207,6 +213,33 @@ int sp_cpso_radius(const sp_pso_state* st, int it, void* stream);
 int sp_cpso_decide(const sp_pso_state* st, int it, void* stream);
 /* enqueue generations it_first .. it_first+n-1 (+ restart when gamma >= 0) */
 int sp_pso_run(const sp_pso_state* st, int it_first, int n, int32_t* d_rank, void* stream);
+
+/* ---- 8e: one swarm row-sharded over GPUs, exchange fused into the kernels ----------
+ * Reference analogue: the mpi backend's Bcast / Allreduce around the population
+ * evaluation (_common.py:58-72); here the rows live on their GPUs and only the best
+ * record moves.  Every rank owns a mailbox in device memory that all ranks map (CUDA IPC
+ * handle exported by sp_peer_alloc, opened with sp_peer_open).  Per generation the last
+ * CTA of the generation kernel STORES the rank's local best [fit, x_0..x_{N-1}] straight
+ * into every peer's mailbox (NVLink stores), publishes a flag after a system-scope
+ * fence, waits for the peers' flags and reduces the `world` records exactly like
+ * selection_sync (first minimum, rank order = row order) -- gbest, dist, nit and status
+ * come out identical on every rank with no NCCL call and no host round trip.  The
+ * competitive restart exchanges the swarm radius (max) the same way inside the plan
+ * kernel and, when it fires, the pbestfit shards (all-gather by peer stores) so every
+ * rank ranks the whole swarm.  A peer that does not answer within ~10 s sets
+ * ctrl.status = SP_STATUS_PEER_TIMEOUT on the waiting rank instead of hanging the GPU. */
+#define SP_STATUS_PEER_TIMEOUT (-900)
+#define SP_PEER_HANDLE_BYTES 64
+int64_t sp_peer_bytes(int dtype, int world, int64_t ld, int64_t P_total);
+/* cudaMalloc + zero-fill + export handle (SP_PEER_HANDLE_BYTES bytes, host memory) */
+int sp_peer_alloc(int64_t bytes, void** d_mailbox, void* handle_out);
+/* map a peer's mailbox from its handle; own mailbox: pass the pointer itself, no open needed */
+int sp_peer_open(const void* handle, void** d_mailbox);
+int sp_peer_close(void* d_mailbox);
+int sp_peer_free(void* d_mailbox);
+/* enqueue generations it_first .. it_first+n-1 of a shard == 2 swarm (+ restart when
+ * gamma >= 0); d_rank_all: P_total int32 of scratch.  Every rank must enqueue the same calls. */
+int sp_pso_run_sharded(const sp_pso_state* st, int it_first, int n, int32_t* d_rank_all, void* stream);
 
 
 /* ---- counter-based draws as a buffer: out[row][j] = U[0,1) (normal = 0) or N(0,1)

@@ -61,3 +61,7 @@ if which == "slopes":
         tb = min(run(method, fun, n, p, b, **kw) for _ in range(2))
         per = (tb - ta) / (b - a)
         print(f"{method} {fun.__name__} N={n} P={p} {kw.get('dtype', 'float64')}: {per * 1e6:.1f} us/gen, {p / per:.3e} evals/s (fixed {1e3 * (ta - a * per):.2f} ms)", flush=True)
+if which in ("shard_pso", "shard_cpso"):
+    from stochopy_b200 import parallel
+    parallel.cpso_sharded(sb.factory.styblinski_tang, [[-5.12, 5.12]] * 64, maxiter=6, popsize=32768, seed=0, dtype="float32",
+                          competitivity=(None if which == "shard_pso" else 1.0), exchange="peer", **off)

@@ -11,6 +11,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libstochopy_b200.so")
 
 SP_RUNNING = -1000
+SP_STATUS_PEER_TIMEOUT = -900
+PEER_HANDLE_BYTES = 64
 SP_F32, SP_F64 = 0, 1
 OBJECTIVES = {
     "ackley": 0,
@@ -69,6 +71,7 @@ class PsoState(C.Structure):
         ("lower", vp), ("upper", vp), ("ctrl", vp), ("scratch", vp),
         ("r1", vp), ("r2", vp),
         ("row0", C.c_int64), ("P_total", C.c_int64), ("xch", vp), ("shard", C.c_int32), ("pad2_", C.c_int32),
+        ("world", C.c_int32), ("rank", C.c_int32), ("mailbox", vp), ("peers", vp),
     ]
 
 
@@ -146,6 +149,12 @@ SIGNATURES = {
     "sp_cpso_radius": (_i, [C.POINTER(PsoState), _i, vp]),
     "sp_cpso_decide": (_i, [C.POINTER(PsoState), _i, vp]),
     "sp_pso_run": (_i, [C.POINTER(PsoState), _i, _i, vp, vp]),
+    "sp_peer_bytes": (_i64, [_i, _i, _i64, _i64]),
+    "sp_peer_alloc": (_i, [_i64, C.POINTER(vp), vp]),
+    "sp_peer_open": (_i, [vp, C.POINTER(vp)]),
+    "sp_peer_close": (_i, [vp]),
+    "sp_peer_free": (_i, [vp]),
+    "sp_pso_run_sharded": (_i, [C.POINTER(PsoState), _i, _i, vp, vp]),
     "sp_random_fill": (_i, [_i, vp, _i64, _i, _i64, _i, _i, _u64, _i, vp]),
     "sp_fitness_rank": (_i, [_i, vp, _i64, vp, vp]),
     "sp_sym_eigh": (_i, [_i, vp, _i, vp, vp, vp, _i, vp, vp]),

@@ -236,15 +236,16 @@ __device__ __forceinline__ Best chain_best(const Best* region, int n) {
 // Last-CTA epilogue of every generation: new best row -> gbest, distance to
 // the previous best, status ladder of selection_sync (_common.py:135-158).
 // `it` < 0: initial population (no status test).
-template <typename T>
-__device__ __forceinline__ void finalize_generation(Best b, const T* __restrict__ xrows, int64_t ld, int N,
+// VOL: the winning row was stored by a peer GPU into this rank's mailbox -> volatile loads.
+template <typename T, bool VOL = false>
+__device__ __forceinline__ void finalize_generation(Best b, const T* xrows, int64_t ld, int N,
                                                     T* gbest, sp_ctrl* ctrl, int it, int maxiter, double xtol,
                                                     double ftol) {
   __shared__ double s_part[32];
   const T* src = xrows + b.row * ld;
   double acc = 0.0;
   for (int j = threadIdx.x; j < N; j += blockDim.x) {
-    T nv = src[j];
+    T nv = VOL ? *reinterpret_cast<const volatile T*>(src + j) : src[j];
     double d = (double)(T)(gbest[j] - nv);
     acc += d * d;
     gbest[j] = nv;

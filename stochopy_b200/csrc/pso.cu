@@ -5,6 +5,7 @@
 //
 // Per particle (row-local, in place): read X, V, pbest; write X, V and, on
 // improvement only, pbest.  Algorithmic HBM bytes per particle: 5 * N * s + 3 * s.
+#include "peer.cuh"
 #include "rows.cuh"
 
 namespace sp {
@@ -31,7 +32,38 @@ struct PsoArgs {
   int64_t row0, P_total;  // sharded swarm: global index of local row 0, whole swarm size
   T* xch;                  // shard mode: [fit, x_0..x_{N-1}] of the local best for the exchange
   int shard;
+  PeerArgs peer;           // shard == 2: exchange inside the kernel over the peer mailboxes
 };
+
+// shard == 2, last CTA of the generation kernel: local best -> every peer's mailbox (NVLink
+// stores), flags, wait, then selection_sync's reduction over the `world` records on every rank.
+template <typename T>
+__device__ __forceinline__ void peer_best_exchange(const PsoArgs<T>& a, Best top) {
+  const PeerArgs& p = a.peer;
+  const int par = a.it & 1;
+  const int off = 16 / (int)sizeof(T);  // x starts 16-byte aligned behind the fitness
+  const T* src = a.pbest + top.row * a.ld;
+  for (int r = 0; r < p.world; ++r) {
+    T* dst = peer_rec<T>(p, r, par, p.rank);
+    for (int j = threadIdx.x; j < a.N; j += blockDim.x) dst[off + j] = src[j];
+    if (threadIdx.x == 0) dst[0] = (T)top.f;
+  }
+  if (!peer_exchange_flags(p, kPeerBest, par, (uint32_t)a.it)) {
+    if (threadIdx.x == 0) a.ctrl->status = SP_STATUS_PEER_TIMEOUT;
+    return;
+  }
+  int best = 0;
+  T bf = ld_volatile(peer_rec<T>(p, p.rank, par, 0));
+  for (int r = 1; r < p.world; ++r) {  // first minimum: rank order is row order (np.argmin's tie rule)
+    const T f = ld_volatile(peer_rec<T>(p, p.rank, par, r));
+    if (f < bf) {
+      bf = f;
+      best = r;
+    }
+  }
+  finalize_generation<T, true>(Best{(double)bf, (long long)best}, peer_rec<T>(p, p.rank, par, 0) + off, p.L.rec_ld, a.N,
+                               a.gbest, a.ctrl, a.it, a.maxiter, a.xtol, a.ftol);
+}
 
 template <typename T, int CH, int LPR, bool PHILOX>
 __global__ void __launch_bounds__(kThreads)
@@ -148,7 +180,9 @@ pso_generation_kernel(const PsoArgs<T> a, const PhiloxKeys keys) {
   if (a.propose_only) return;
   Best top;
   if (grid_best(mine, a.scratch, a.ctrl, &top)) {
-    if (a.shard) {  // local best -> exchange record; gbest/status come from sp_gbest_reduce on every rank
+    if (a.shard == 2) {
+      peer_best_exchange<T>(a, top);
+    } else if (a.shard) {  // local best -> exchange record; gbest/status come from sp_gbest_reduce on every rank
       const T* src = a.pbest + top.row * a.ld;
       for (int j = threadIdx.x; j < a.N; j += blockDim.x) a.xch[1 + j] = src[j];
       if (threadIdx.x == 0) a.xch[0] = (T)top.f;
@@ -204,6 +238,54 @@ __global__ void restart_plan_kernel(sp_ctrl* ctrl, int64_t P, int N, int it, int
   ctrl->aux[0] = 0.0;
 }
 
+// (2') sharded swarm: the local maxima travel through the peer mailboxes first (max-reduce)
+__global__ void restart_plan_peer_kernel(sp_ctrl* ctrl, int64_t P, int N, int it, int maxiter, double gamma,
+                                         double delta, const PeerArgs p) {
+  if (!running(ctrl)) {
+    if (threadIdx.x == 0) ctrl->flag = 0;
+    return;
+  }
+  const int par = it & 1;
+  const double mine = ctrl->aux[0];
+  for (int r = threadIdx.x; r < p.world; r += blockDim.x) *peer_rad(p, r, par, p.rank) = mine;
+  const bool ok = peer_exchange_flags(p, kPeerRadius, par, (uint32_t)it);
+  if (threadIdx.x != 0) return;
+  if (!ok) {
+    ctrl->status = SP_STATUS_PEER_TIMEOUT;
+    ctrl->flag = 0;
+    return;
+  }
+  double m = 0.0;
+  for (int r = 0; r < p.world; ++r) m = fmax(m, ld_volatile(peer_rad(p, p.rank, par, r)));
+  const double radius = sqrt(m) / sqrt(4.0 * (double)N);
+  int nw = 0;
+  if (radius < delta) {
+    const double inorm = (double)it / (double)maxiter;
+    nw = (int)(((double)P - 1.0) / (1.0 + exp(1.0 / 0.09 * (inorm - gamma + 0.5))));
+    if (nw < 0) nw = 0;
+  }
+  ctrl->flag = nw;
+  ctrl->aux[1] = radius;
+  ctrl->aux[0] = 0.0;
+}
+
+// (3') restart fired (ctrl->flag > 0 on every rank alike): all-gather the pbestfit shards by
+// storing this rank's shard into every peer's mailbox, so each rank can rank the whole swarm
+template <typename T>
+__global__ void __launch_bounds__(1024)
+peer_gather_fit_kernel(const T* __restrict__ pbestfit, int64_t P, int64_t row0, sp_ctrl* ctrl, int it,
+                       const PeerArgs p) {
+  if (!running(ctrl) || ctrl->flag <= 0) return;
+  for (int r = 0; r < p.world; ++r) {
+    T* dst = peer_fit<T>(p, r) + row0;
+    for (int64_t i = threadIdx.x; i < P; i += blockDim.x) dst[i] = pbestfit[i];
+  }
+  if (!peer_exchange_flags(p, kPeerFit, it & 1, (uint32_t)it) && threadIdx.x == 0) {
+    ctrl->status = SP_STATUS_PEER_TIMEOUT;
+    ctrl->flag = 0;
+  }
+}
+
 // (4) reset the nw worst: V = 0, X = U(lower, upper), pbest = X, pbestfit = 1e30
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
@@ -232,6 +314,18 @@ restart_apply_kernel(T* X, T* V, T* pbest, T* pbestfit, const int32_t* __restric
     V[i * ld + j] = T(0);
     if (j == 0) pbestfit[i] = T(1.0e30);
   }
+}
+
+template <typename T>
+static PeerArgs peer_args(const sp_pso_state* st) {
+  PeerArgs p = {};
+  if (st->shard == 2) {
+    p.peers = reinterpret_cast<unsigned char* const*>(st->peers);
+    p.world = st->world;
+    p.rank = st->rank;
+    p.L = peer_layout(st->world, st->ld, st->P_total, sizeof(T));
+  }
+  return p;
 }
 
 template <typename T>
@@ -272,6 +366,7 @@ static int pso_launch(const sp_pso_state* st, int it, int propose_only, cudaStre
   a.P_total = st->shard ? st->P_total : st->P;
   a.xch = (T*)st->xch;
   a.shard = st->shard;
+  a.peer = peer_args<T>(st);
   const bool philox = st->r1 == nullptr;
   const PhiloxKeys keys = philox_keys(st->seed);
   const int grid = grid_for_rows(st->P, sh.lpr, sh.ch >= 4 ? 2 : 4);
@@ -297,8 +392,13 @@ static int pso_check(const sp_pso_state* st, int it) {
                "null buffer");
   SP_CHECK_ARG(st->constraint == SP_CONS_NONE || (st->lower && st->upper), "bounds needed for Shrink");
   SP_CHECK_ARG((st->r1 == nullptr) == (st->r2 == nullptr), "r1 and r2 must come together");
-  SP_CHECK_ARG(!st->shard || (st->xch && st->r1 == nullptr && st->row0 >= 0 && st->row0 + st->P <= st->P_total),
-               "shard mode needs the exchange record, in-kernel draws and a row range inside the swarm");
+  SP_CHECK_ARG(st->shard >= 0 && st->shard <= 2, "shard");
+  SP_CHECK_ARG(!st->shard || (st->r1 == nullptr && st->row0 >= 0 && st->row0 + st->P <= st->P_total),
+               "shard mode needs in-kernel draws and a row range inside the swarm");
+  SP_CHECK_ARG(st->shard != 1 || st->xch, "shard == 1 needs the exchange record");
+  SP_CHECK_ARG(st->shard != 2 || (st->mailbox && st->peers && st->world >= 1 && st->world <= 64 && st->rank >= 0 &&
+                                  st->rank < st->world),
+               "shard == 2 needs the peer mailboxes (sp_peer_alloc / sp_peer_open), world <= 64");
   SP_CHECK_ARG(it >= 2, "generation index starts at 2 (_cpso.py:256-258)");
   return SP_OK;
 }
@@ -326,6 +426,43 @@ static int restart_apply_launch(const sp_pso_state* st, int it, const int32_t* r
   return SP_OK;
 }
 
+template <typename T>
+static int pso_run_sharded(const sp_pso_state* st, int it_first, int n, int32_t* rank_all, cudaStream_t s) {
+  const PeerArgs p = peer_args<T>(st);
+  const T* fit_all = reinterpret_cast<const T*>(static_cast<const unsigned char*>(st->mailbox) + p.L.fit);
+  for (int g = 0; g < n; ++g) {
+    const int it = it_first + g;
+    int rc = pso_launch<T>(st, it, 0, s);
+    if (rc) return rc;
+    if (st->gamma < 0.0) continue;
+    const int grid = grid_for_rows(st->P, 32, 8);
+    radius_kernel<T><<<grid, kThreads, 0, s>>>((const T*)st->X, (const T*)st->gbest, st->P, st->N, st->ld, st->ctrl);
+    SP_CHECK_LAUNCH();
+    restart_plan_peer_kernel<<<1, 64, 0, s>>>(st->ctrl, st->P_total, st->N, it, st->maxiter, st->gamma, st->delta, p);
+    SP_CHECK_LAUNCH();
+    peer_gather_fit_kernel<T><<<1, 1024, 0, s>>>((const T*)st->pbestfit, st->P, st->row0, st->ctrl, it, p);
+    SP_CHECK_LAUNCH();
+    if (rank_launch<T>(fit_all, st->P_total, rank_all, &st->ctrl->flag, s) != cudaSuccess) return SP_ERR_CUDA;
+    rc = restart_apply_launch<T>(st, it, rank_all + st->row0, nullptr, s);
+    if (rc) return rc;
+  }
+  return SP_OK;
+}
+
+}  // namespace sp
+
+extern "C" int sp_pso_run_sharded(const sp_pso_state* st, int it_first, int n, int32_t* rank_all, void* stream) {
+  using namespace sp;
+  int rc = pso_check(st, it_first);
+  if (rc) return rc;
+  SP_CHECK_ARG(st->shard == 2, "sp_pso_run_sharded needs shard == 2");
+  SP_CHECK_ARG(st->objective >= SP_OBJ_ACKLEY && st->objective <= SP_OBJ_STYBLINSKI_TANG, "device objective required");
+  SP_CHECK_ARG(st->gamma < 0.0 || (rank_all != nullptr && st->lower && st->upper), "rank scratch and bounds");
+  return st->dtype == SP_F32 ? pso_run_sharded<float>(st, it_first, n, rank_all, (cudaStream_t)stream)
+                             : pso_run_sharded<double>(st, it_first, n, rank_all, (cudaStream_t)stream);
+}
+
+namespace sp {
 }  // namespace sp
 
 using namespace sp;

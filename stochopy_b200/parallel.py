@@ -23,7 +23,7 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
-__all__ = ["shard_range", "shard_seeds", "reduce_best", "minimize_seeds", "cpso_sharded"]
+__all__ = ["shard_range", "shard_seeds", "reduce_best", "minimize_seeds", "cpso_sharded", "PeerMailboxes"]
 
 
 def _all_gather_flat(out, part, group):
@@ -34,6 +34,57 @@ def _all_gather_flat(out, part, group):
         world = dist.get_world_size(group)
         chunks = list(out.view(world, -1).unbind(0))
         dist.all_gather(chunks, part, group=group)
+
+
+class PeerMailboxes:
+    """One device mailbox per rank, every mailbox mapped into every process (CUDA IPC;
+    NVLink peer memory between GPUs).  ``torch.distributed`` only carries the 64-byte
+    handles once; afterwards the kernels store into the peers' mailboxes themselves
+    (csrc/peer.cuh).  ``table`` is the device array of the `world` mailbox pointers as
+    addressed from this process; ``own`` is this rank's mailbox."""
+
+    def __init__(self, nbytes, group=None, device=None):
+        from . import _lib as L
+
+        self._L = L
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        own, handle = C.c_void_p(), C.create_string_buffer(L.PEER_HANDLE_BYTES)
+        L.call("sp_peer_alloc", int(nbytes), C.byref(own), handle)
+        self.own = own.value
+        handles = [None] * self.world
+        if self.world > 1:
+            dist.all_gather_object(handles, handle.raw, group=group)
+        else:
+            handles[0] = handle.raw
+        self.ptrs, self._opened = [], []
+        for r, h in enumerate(handles):
+            if r == self.rank:
+                self.ptrs.append(self.own)
+                continue
+            q = C.c_void_p()
+            L.call("sp_peer_open", C.create_string_buffer(h, L.PEER_HANDLE_BYTES), C.byref(q))
+            self.ptrs.append(q.value)
+            self._opened.append(q.value)
+        device = device or torch.device("cuda", torch.cuda.current_device())
+        self.table = torch.tensor(self.ptrs, dtype=torch.int64).to(device)
+        if self.world > 1:
+            dist.barrier(group=group)  # every mailbox is mapped everywhere before the first store
+
+    def close(self):
+        """Collective: unmap the peers' mailboxes, then free the own one."""
+        if self.own is None:
+            return
+        torch.cuda.synchronize()
+        if self.world > 1:
+            dist.barrier(group=self.group)  # nobody stores into a mailbox that is about to go away
+        for q in self._opened:
+            self._L.call("sp_peer_close", C.c_void_p(q))
+        if self.world > 1:
+            dist.barrier(group=self.group)
+        self._L.call("sp_peer_free", C.c_void_p(self.own))
+        self.own, self._opened = None, []
 
 
 def shard_range(total, rank, world):
@@ -98,12 +149,18 @@ def minimize_seeds(fun, bounds, seeds, method="de", options=None, group=None, ru
 
 def cpso_sharded(fun, bounds, maxiter=100, popsize=10, inertia=0.7298, cognitivity=1.49618, sociability=1.49618,
                  competitivity=1.0, seed=None, xtol=1.0e-8, ftol=1.0e-8, constraints=None, dtype="float64",
-                 group=None):
+                 group=None, exchange="peer"):
     """One (C)PSO swarm of `popsize` particles row-sharded over the process group.
 
     Same algorithm, options and result as ``optimize.cpso`` (reference
     ``cpso/_cpso.py:182-321``, synchronous); device objectives only; every rank returns
-    the same result.  With world size 1 it is exactly ``optimize.cpso``'s Philox path."""
+    the same result.  With world size 1 it is exactly ``optimize.cpso``'s Philox path.
+
+    exchange="peer" (default): the per-generation gbest / radius / pbestfit exchanges run
+    inside the kernels over peer-mapped mailboxes (``PeerMailboxes``, ``sp_pso_run_sharded``):
+    generations are enqueued in chunks with no collective call and no host round trip in
+    between.  exchange="nccl": one all-gather + ``sp_gbest_reduce`` per generation driven
+    from the host (the baseline; also what the gloo CPU tests of the host logic use)."""
     from . import _lib as L
     from .optimize._common import Engine, device_objective, fresh_seed, messages
     from .optimize._helpers import OptimizeResult
@@ -116,6 +173,9 @@ def cpso_sharded(fun, bounds, maxiter=100, popsize=10, inertia=0.7298, cognitivi
     cons = {None: L.CONS_NONE, "Shrink": L.CONS_SHRINK}[constraints]
     if seed is None:
         raise ValueError("a sharded swarm needs an explicit seed (all ranks must draw the same stream)")
+    if exchange not in {"peer", "nccl"}:
+        raise ValueError()
+    mode = exchange
 
     eng = Engine(dtype)
     bounds = np.asarray(bounds, dtype=np.float64)
@@ -152,7 +212,7 @@ def cpso_sharded(fun, bounds, maxiter=100, popsize=10, inertia=0.7298, cognitivi
     st.ctrl, st.scratch = ctrl.data_ptr(), scratch.data_ptr()
     st.row0, st.P_total, st.xch, st.shard = row0, Ptot, xch.data_ptr(), 1
 
-    def exchange(it):
+    def exchange_best(it):
         """all-gather the local bests, reduce on every rank (status from the global best)."""
         if world > 1:
             _all_gather_flat(recs.view(-1), xch, group)
@@ -169,15 +229,29 @@ def cpso_sharded(fun, bounds, maxiter=100, popsize=10, inertia=0.7298, cognitivi
     b = int(torch.argmin(pbestfit).item())
     xch[0] = pbestfit[b]
     xch[1:1 + N] = X[b, :N]
-    exchange(-1)
+    exchange_best(-1)
 
     ctrl64 = ctrl.view(torch.float64)  # aux[0] (local max squared radius) sits at byte 40
     it = 1
     c = eng.read_ctrl(ctrl)
+    if mode == "peer":
+        box = PeerMailboxes(L.load().sp_peer_bytes(eng.sp_dt, world, ld, Ptot), group, eng.device)
+        st.shard, st.world, st.rank = 2, world, rank
+        st.mailbox, st.peers = box.own, box.table.data_ptr()
+        try:
+            while c.status == L.SP_RUNNING:
+                n = min(32 if it < 64 else 128, max(int(maxiter), 2) - it)
+                L.call("sp_pso_run_sharded", C.byref(st), it + 1, n, rank_all.data_ptr(), eng.stream)
+                c = eng.read_ctrl(ctrl)
+                it = c.nit
+        finally:
+            box.close()
+        if c.status == L.SP_STATUS_PEER_TIMEOUT:
+            raise L.EngineError("cpso_sharded: a peer did not answer within the exchange timeout")
     while c.status == L.SP_RUNNING:
         it += 1
         L.call("sp_pso_generation", C.byref(st), it, eng.stream)
-        exchange(it)
+        exchange_best(it)
         c = eng.read_ctrl(ctrl)
         if c.status == L.SP_RUNNING and restart:  # _cpso.py:304-307, 405-426
             L.call("sp_cpso_radius", C.byref(st), it, eng.stream)

@@ -23,9 +23,10 @@ def main():
     b = [[-5.12, 5.12]] * 64
     for opts in (dict(competitivity=None, constraints="Shrink"), dict(competitivity=1.0), dict(competitivity=1.0, dtype="float32")):
         o = dict(opts, maxiter=80, popsize=4099, seed=5)
-        r = parallel.cpso_sharded(sb.factory.styblinski_tang, b, **o)
         one = sb.optimize.minimize(sb.factory.styblinski_tang, b, method="cpso", options=dict(o, updating="deferred"))
-        assert np.array_equal(r.x, one.x) and r.fun == one.fun and (r.nit, r.status) == (one.nit, one.status), (rank, opts)
+        for exchange in ("peer", "nccl"):  # in-kernel NVLink mailboxes / host-driven NCCL all-gather
+            r = parallel.cpso_sharded(sb.factory.styblinski_tang, b, exchange=exchange, **o)
+            assert np.array_equal(r.x, one.x) and r.fun == one.fun and (r.nit, r.status) == (one.nit, one.status), (rank, opts, exchange)
     seeds = list(range(2 * world + 1))
     res = parallel.minimize_seeds(sb.factory.rastrigin, [[-5.12, 5.12]] * 16, seeds, method="de",
                                   options=dict(maxiter=60, popsize=256, dtype="float64", updating="deferred"))

@@ -89,14 +89,19 @@ def _sharded(rank, world, opts):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("exchange", ["peer", "nccl"])
 @pytest.mark.parametrize("opts", [dict(competitivity=None, constraints="Shrink"), dict(competitivity=1.0),
                                   dict(competitivity=1.2, dtype="float32")])
-def test_sharded_swarm_equals_single_process(opts):
+def test_sharded_swarm_equals_single_process(opts, exchange):
+    """exchange="peer": gbest / radius / pbestfit travel through CUDA-IPC mapped mailboxes inside
+    the kernels (csrc/peer.cuh); here both ranks sit on one GPU, so the spin-waits resolve by
+    context time-slicing.  exchange="nccl": host-driven collectives (gloo in this test)."""
     import stochopy_b200 as sb
 
-    o = dict(opts, maxiter=60, popsize=101, seed=11)
+    o = dict(opts, maxiter=60, popsize=101, seed=11, exchange=exchange)
+    single = {k: v for k, v in o.items() if k != "exchange"}
     one = sb.optimize.minimize(sb.factory.styblinski_tang, [[-5.12, 5.12]] * 10, method="cpso",
-                               options=dict(o, updating="deferred"))
+                               options=dict(single, updating="deferred"))
     solo = parallel.cpso_sharded(sb.factory.styblinski_tang, [[-5.12, 5.12]] * 10, **o)
     assert np.array_equal(solo.x, one.x) and solo.fun == one.fun and (solo.nit, solo.status) == (one.nit, one.status)
     for rank, (x, fun, nit, status) in _spawn(_sharded, 2, o):  # two ranks, odd split 51 + 50
