@@ -65,3 +65,19 @@ if which in ("shard_pso", "shard_cpso"):
     from stochopy_b200 import parallel
     parallel.cpso_sharded(sb.factory.styblinski_tang, [[-5.12, 5.12]] * 64, maxiter=6, popsize=32768, seed=0, dtype="float32",
                           competitivity=(None if which == "shard_pso" else 1.0), exchange="peer", **off)
+if which == "eigh256":
+    import torch, numpy as np, ctypes as C
+    from stochopy_b200 import _lib as L
+    from stochopy_b200.optimize._common import Engine
+    eng = Engine("float64")
+    N = 256
+    rs = np.random.RandomState(N)
+    A = rs.normal(0, 1, (N, N)); Cm = A @ A.T / N + np.diag(rs.uniform(0.01, 3.0, N))
+    w, B = eng.zeros(N), eng.zeros(N, N)
+    work = eng.zeros(int(L.load().sp_sym_eigh_work_scalars(N)))
+    sw = eng.zeros(1, dtype=torch.int32)
+    for warm, pert in ((0, 0.0), (1, 0.03)):
+        Cp = Cm + pert * (lambda E: E @ E.T / N)(rs.normal(0, 1, (N, N)))
+        dC = torch.from_numpy(Cp).to(eng.device)
+        L.call("sp_sym_eigh", eng.sp_dt, dC.data_ptr(), N, w.data_ptr(), B.data_ptr(), work.data_ptr(), warm, sw.data_ptr(), eng.stream)
+        torch.cuda.synchronize()

@@ -104,13 +104,14 @@ __device__ __forceinline__ void gemm_tn_tile(int R, int Cc, int i0, int i1, int 
 }
 
 // ---- symmetric eigendecomposition: cyclic one-sided Jacobi on rows -----------------
-// W = Q C is driven to mutually orthogonal rows by plane rotations applied to the
-// rows of W and Q alike (Hestenes).  At convergence row j of Q is an eigenvector
-// q_j and row j of W equals lambda_j q_j, so lambda_j = w_j . q_j (signed).
-// One CTA of 1024 threads; a warp owns one (p, q) pair of the round-robin round.
-// W and Q live in shared memory when 2 N^2 scalars fit, otherwise in global (L2).
-// warm != 0: start from Q = previous eigenvectors (rows), W = Q C -- the covariance
-// moves little per generation, so 2-3 sweeps instead of ~8 from the identity.
+// W = Q0 C (Q0 = I, or the previous eigenvectors as rows when warm) is driven to mutually
+// orthogonal rows by plane rotations of row pairs (Hestenes).  At convergence
+// W = Lambda Q with Q orthogonal, so for the positive (semi)definite C of CMA-ES
+//   lambda_j = |w_j|,  q_j = w_j / |w_j|
+// and the accumulated rotations never have to be stored: only W is rotated (half the
+// shared-memory traffic and flops of carrying Q along).  The stopping test is relative
+// (|w_p.w_q| <= tol |w_p||w_q|), so the normalised rows are orthogonal to tol.
+// warm != 0: the covariance moves little per generation, so 3-4 sweeps instead of ~9.
 template <typename T>
 struct JacobiEps;
 template <>
@@ -126,356 +127,115 @@ constexpr int kJacobiThreads = 1024;
 constexpr int kJacobiRegs = 8;  // row elements per lane staged in registers (N <= 256)
 
 template <typename T>
-__global__ void __launch_bounds__(kJacobiThreads, 1)
-jacobi_eigh_kernel(T* __restrict__ C, int N, T* __restrict__ w_out, T* __restrict__ B, T* __restrict__ Wg,
-                   T* __restrict__ Qg, int use_smem, int warm, const int* __restrict__ gate,
-                   const int* __restrict__ status_gate, int* __restrict__ sweeps_out) {
-  extern __shared__ __align__(16) unsigned char jsm[];
-  __shared__ unsigned int s_off;
-  __shared__ int s_rank_tmp;
-  if (gate != nullptr && *gate == 0) return;
-  if (status_gate != nullptr && *status_gate != SP_RUNNING) return;
-  T* W = use_smem ? reinterpret_cast<T*>(jsm) : Wg;
-  T* Q = use_smem ? reinterpret_cast<T*>(jsm) + (size_t)N * N : Qg;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = kJacobiThreads / 32;
-
-  // symmetrise from the upper triangle (_cmaes.py:303): C = triu(C) + triu(C,1)^T
-  for (int e = tid; e < N * N; e += kJacobiThreads) {
-    const int r = e / N, c = e - r * N;
-    if (r > c) C[e] = C[c * N + r];
-  }
-  __syncthreads();
-  if (warm) {  // Q rows = previous eigenvectors (columns of B); W = Q C
-    for (int e = tid; e < N * N; e += kJacobiThreads) {
-      const int j = e / N, r = e - j * N;
-      Q[e] = B[r * N + j];
-    }
-    __syncthreads();
-    for (int e = tid; e < N * N; e += kJacobiThreads) {
-      const int j = e / N, c = e - j * N;
-      T acc = 0;
-      for (int k = 0; k < N; ++k) acc += Q[j * N + k] * C[k * N + c];
-      W[e] = acc;
-    }
-  } else {
-    for (int e = tid; e < N * N; e += kJacobiThreads) {
-      const int r = e / N, c = e - r * N;
-      W[e] = C[e];
-      Q[e] = r == c ? T(1) : T(0);
-    }
-  }
-  __syncthreads();
-
+__device__ __forceinline__ T jacobi_tol(int N) {
   // rotate while |w_p.w_q| exceeds the rounding noise of a length-N dot product
-  const T tol = T(4) * JacobiEps<T>::eps() * sqrt((T)(N < 16 ? 16 : N));
-  const int n = N + (N & 1);  // even player count; index N (if any) is a bye
-  const int half = n / 2;
-  int sweep = 0;
-  for (; sweep < 60; ++sweep) {
-    if (tid == 0) s_off = 0u;
-    __syncthreads();
-    for (int r = 0; r < n - 1; ++r) {
-      for (int i = warp; i < half; i += nwarps) {
-        int p, q;
-        if (i == 0) {
-          p = n - 1;
-          q = r;
-        } else {
-          p = (r + i) % (n - 1);
-          q = (r - i + (n - 1)) % (n - 1);
-        }
-        if (p >= N || q >= N) continue;
-        T* wp = W + (size_t)p * N;
-        T* wq = W + (size_t)q * N;
-        T al = 0, be = 0, ga = 0;
-        for (int k = lane; k < N; k += 32) {
-          const T a = wp[k], b = wq[k];
-          al += a * a;
-          be += b * b;
-          ga += a * b;
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-          al += __shfl_xor_sync(0xffffffffu, al, o);
-          be += __shfl_xor_sync(0xffffffffu, be, o);
-          ga += __shfl_xor_sync(0xffffffffu, ga, o);
-        }
-        const T lim = tol * sqrt(al * be);
-        if (fabs(ga) > lim && al > T(0) && be > T(0)) {
-          if (lane == 0) s_off = 1u;
-          const T zeta = (be - al) / (T(2) * ga);
-          const T t = (zeta >= T(0) ? T(1) : T(-1)) / (fabs(zeta) + sqrt(T(1) + zeta * zeta));
-          const T cs = T(1) / sqrt(T(1) + t * t), sn = cs * t;
-          T* qp = Q + (size_t)p * N;
-          T* qq = Q + (size_t)q * N;
-          for (int k = lane; k < N; k += 32) {
-            const T a = wp[k], b = wq[k];
-            wp[k] = cs * a - sn * b;
-            wq[k] = sn * a + cs * b;
-            const T c = qp[k], d = qq[k];
-            qp[k] = cs * c - sn * d;
-            qq[k] = sn * c + cs * d;
-          }
-        }
-      }
-      __syncthreads();
-    }
-    const unsigned int off = s_off;
-    __syncthreads();
-    if (off == 0u) break;
-  }
-  if (tid == 0 && sweeps_out != nullptr) *sweeps_out = sweep + 1;
-
-  // eigenvalues (Rayleigh product), ascending stable rank, canonical sign, scatter
-  T* lam = w_out;  // temporarily unsorted in global scratch: reuse Wg tail? keep simple: two passes
-  __shared__ T s_lam[1024];
-  for (int j = warp; j < N; j += nwarps) {
-    T acc = 0;
-    for (int k = lane; k < N; k += 32) acc += W[(size_t)j * N + k] * Q[(size_t)j * N + k];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if (lane == 0) s_lam[j] = acc;
-  }
-  __syncthreads();
-  (void)s_rank_tmp;
-  for (int j = warp; j < N; j += nwarps) {
-    const T mine = s_lam[j];
-    int rk = 0;
-    for (int k = lane; k < N; k += 32) {
-      const T o = s_lam[k];
-      rk += (o < mine) || (o == mine && k < j);
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) rk += __shfl_xor_sync(0xffffffffu, rk, o);
-    // sign: largest |component| positive (first one on ties)
-    T best = T(-1);
-    int bidx = 0;
-    for (int k = lane; k < N; k += 32) {
-      const T a = fabs(Q[(size_t)j * N + k]);
-      if (a > best) {
-        best = a;
-        bidx = k;
-      }
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const T ob = __shfl_xor_sync(0xffffffffu, best, o);
-      const int oi = __shfl_xor_sync(0xffffffffu, bidx, o);
-      if (ob > best || (ob == best && oi < bidx)) {
-        best = ob;
-        bidx = oi;
-      }
-    }
-    const T sgn = Q[(size_t)j * N + bidx] < T(0) ? T(-1) : T(1);
-    if (lane == 0) lam[rk] = mine;
-    for (int k = lane; k < N; k += 32) B[(size_t)k * N + rk] = sgn * Q[(size_t)j * N + k];
-  }
+  return T(4) * JacobiEps<T>::eps() * sqrt((T)(N < 16 ? 16 : N));
 }
 
-// Multi-CTA variant for matrices that do not fit one SM's shared memory: the N/2 pairs of
-// a round are spread over the warps of a cooperative grid (one pair per warp), W and Q
-// live in global memory (L2 resident, 2 N^2 scalars), rounds are separated by grid-wide
-// barriers.  Same rotations, ordering, warm start, sorting and sign rule as above.
-// scratch: W, Q (2 N^2), lam (N), sweep flags (64 x 4 bytes).
-// CLUSTER: the whole grid is ONE thread-block cluster (<= 16 CTAs) and rounds are separated
-// by the hardware cluster barrier (barrier.cluster, a few hundred cycles, release/acquire at
-// cluster scope incl. the L1 invalidate) instead of a cooperative grid barrier.
-template <typename T, bool CLUSTER, int THREADS>
-__global__ void __launch_bounds__(THREADS)
-jacobi_grid_kernel(T* __restrict__ C, int N, T* __restrict__ w_out, T* __restrict__ B, T* __restrict__ W,
-                   T* __restrict__ Q, T* __restrict__ lam, unsigned int* __restrict__ off, int warm,
-                   const int* __restrict__ gate, const int* __restrict__ status_gate, int* __restrict__ sweeps_out) {
-  namespace cg = cooperative_groups;
-  struct Barrier {
-    __device__ void sync() {
-      if (CLUSTER) cg::this_cluster().sync();
-      else cg::this_grid().sync();
-    }
-  } grid;
-  if (gate != nullptr && *gate == 0) return;  // uniform over the grid: nobody reaches a barrier
-  if (status_gate != nullptr && *status_gate != SP_RUNNING) return;
-  const int tid = threadIdx.x, lane = tid & 31;
-  const int gthreads = gridDim.x * blockDim.x, gtid = blockIdx.x * blockDim.x + tid;
-  const int gwarp = gtid >> 5, gwarps = gthreads >> 5;
+// Rotation (cs, sn) that orthogonalises a pair with |w_p|^2 = al, |w_q|^2 = be, w_p.w_q = ga.
+// Every lane of the warp executes this, and fp64 division / sqrt are ~25-instruction
+// sequences on a half-rate pipe: done naively (2 divisions, 3 square roots) the scalar
+// work outweighs the rotation itself.  Only cs^2 + sn^2 = 1 has to hold to working
+// precision (orthogonality of the accumulated transformation); the ANGLE may be
+// approximate -- an error of 1e-7 leaves a residual of 1e-7 |ga|, which the quadratically
+// convergent sweeps absorb.  So: tan in fp32 from operands scaled by 2^-exponent(nrm)
+// (range-safe for any eigenvalue scale), then cs = rsqrt(1 + t^2) by two fp64 Newton
+// steps from the fp32 seed (relative error ~1e-14 -> ~1e-28), sn = cs t.
+__device__ __forceinline__ float jacobi_tan(float df, float gf) {
+  const float zf = df / (2.0f * gf);  // zeta = (be - al) / (2 ga)
+  const float az = fabsf(zf);
+  // t = sign(zeta) / (|zeta| + sqrt(1 + zeta^2)); for large |zeta| (zeta^2 would overflow) t = 1 / (2 zeta)
+  return az > 1.0e4f ? 0.5f / zf : copysignf(1.0f, zf) / (az + sqrtf(1.0f + zf * zf));
+}
+// `prod` = al * be (> 0).  Returns |cos(w_p, w_q)| (fp32, for the quiet-sweep test).
+__device__ __forceinline__ float jacobi_angle(double al, double be, double ga, double prod, double* cs, double* sn) {
+  // 2^-ex with ex = exponent(sqrt(prod)) = exponent(prod) / 2: scales ga and be - al into fp32 range
+  const int ex = ((((__double2hiint(prod) >> 20) & 0x7ff) - 1023) >> 1);
+  int bexp = 1023 - ex;
+  bexp = bexp < 1 ? 1 : (bexp > 2046 ? 2046 : bexp);
+  const double sc = __hiloint2double(bexp << 20, 0);
+  const float gf = (float)(ga * sc);
+  const float tf = jacobi_tan((float)((be - al) * sc), gf);
+  const float ratio = fabsf(gf) * rsqrtf((float)(prod * sc * sc));
+  const double t = (double)tf;
+  const double x = fma(t, t, 1.0);
+  double y = (double)rsqrtf(fmaf(tf, tf, 1.0f));
+  y = y * fma(-0.5 * x, y * y, 1.5);
+  y = y * fma(-0.5 * x, y * y, 1.5);
+  *cs = y;
+  *sn = y * t;
+  return ratio;
+}
+__device__ __forceinline__ float jacobi_angle(float al, float be, float ga, float prod, float* cs, float* sn) {
+  const float sc = rsqrtf(prod);
+  const float gf = ga * sc;
+  const float t = jacobi_tan((be - al) * sc, gf);
+  const float x = fmaf(t, t, 1.0f);
+  float y = rsqrtf(x);
+  y = y * fmaf(-0.5f * x, y * y, 1.5f);
+  *cs = y;
+  *sn = y * t;
+  return fabsf(gf);
+}
 
-  for (int e = gtid; e < N * N; e += gthreads) {  // C = triu(C) + triu(C,1)^T (_cmaes.py:303)
-    const int r = e / N, c = e - r * N;
-    if (r > c) C[e] = C[c * N + r];
-  }
-  if (gtid < 64) off[gtid] = 0u;
-  grid.sync();
-  if (warm) {
-    for (int e = gtid; e < N * N; e += gthreads) {
-      const int j = e / N, r = e - j * N;
-      Q[e] = B[r * N + j];
+// one rotation of the row pair (wp, wq) by a full warp; returns |cos(w_p, w_q)| if the
+// pair was rotated, 0 if it already was orthogonal to tol.  REGS: rows of N <= 32 * kJacobiRegs
+// scalars travel through registers once (dot products and rotation share the loads).
+template <typename T, bool REGS>
+__device__ __forceinline__ float jacobi_rotate(T* __restrict__ wp, T* __restrict__ wq, int N, int lane, T tol) {
+  T ra[kJacobiRegs], rb[kJacobiRegs];
+  T al = 0, be = 0, ga = 0;
+  if (REGS) {
+#pragma unroll
+    for (int u = 0; u < kJacobiRegs; ++u) {
+      const int k = lane + 32 * u;
+      ra[u] = k < N ? wp[k] : T(0);
+      rb[u] = k < N ? wq[k] : T(0);
     }
-    grid.sync();
-    for (int e = gtid; e < N * N; e += gthreads) {  // W = Q C
-      const int j = e / N, c = e - j * N;
-      T acc = 0;
-      for (int k = 0; k < N; ++k) acc += Q[j * N + k] * C[k * N + c];
-      W[e] = acc;
+#pragma unroll
+    for (int u = 0; u < kJacobiRegs; ++u) {
+      al += ra[u] * ra[u];
+      be += rb[u] * rb[u];
+      ga += ra[u] * rb[u];
     }
   } else {
-    for (int e = gtid; e < N * N; e += gthreads) {
-      const int r = e / N, c = e - r * N;
-      W[e] = C[e];
-      Q[e] = r == c ? T(1) : T(0);
-    }
-  }
-  grid.sync();
-
-  const T tol = T(4) * JacobiEps<T>::eps() * sqrt((T)(N < 16 ? 16 : N));
-  const int n = N + (N & 1), half = n / 2;
-  int sweep = 0;
-  for (; sweep < 60; ++sweep) {
-    for (int r = 0; r < n - 1; ++r) {
-      for (int i = gwarp; i < half; i += gwarps) {
-        int p, q;
-        if (i == 0) {
-          p = n - 1;
-          q = r;
-        } else {
-          p = (r + i) % (n - 1);
-          q = (r - i + (n - 1)) % (n - 1);
-        }
-        if (p >= N || q >= N) continue;
-        T* wp = W + (size_t)p * N;
-        T* wq = W + (size_t)q * N;
-        T* qp = Q + (size_t)p * N;
-        T* qq = Q + (size_t)q * N;
-        if (THREADS <= 512 && N <= 32 * kJacobiRegs) {
-          // rows staged in registers: all loads of a phase are in flight together (the four
-          // row pointers alias as far as the compiler knows, so a load/store loop serialises)
-          T ra[kJacobiRegs], rb[kJacobiRegs];
-          T al = 0, be = 0, ga = 0;
-#pragma unroll
-          for (int u = 0; u < kJacobiRegs; ++u) {
-            const int k = lane + 32 * u;
-            ra[u] = k < N ? wp[k] : T(0);
-            rb[u] = k < N ? wq[k] : T(0);
-          }
-#pragma unroll
-          for (int u = 0; u < kJacobiRegs; ++u) {
-            al += ra[u] * ra[u];
-            be += rb[u] * rb[u];
-            ga += ra[u] * rb[u];
-          }
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1) {
-            al += __shfl_xor_sync(0xffffffffu, al, o);
-            be += __shfl_xor_sync(0xffffffffu, be, o);
-            ga += __shfl_xor_sync(0xffffffffu, ga, o);
-          }
-          if (fabs(ga) > tol * sqrt(al * be) && al > T(0) && be > T(0)) {
-            if (lane == 0) off[sweep] = 1u;
-            T rc[kJacobiRegs], rd[kJacobiRegs];
-#pragma unroll
-            for (int u = 0; u < kJacobiRegs; ++u) {
-              const int k = lane + 32 * u;
-              rc[u] = k < N ? qp[k] : T(0);
-              rd[u] = k < N ? qq[k] : T(0);
-            }
-            const T zeta = (be - al) / (T(2) * ga);
-            const T t = (zeta >= T(0) ? T(1) : T(-1)) / (fabs(zeta) + sqrt(T(1) + zeta * zeta));
-            const T cs = T(1) / sqrt(T(1) + t * t), sn = cs * t;
-#pragma unroll
-            for (int u = 0; u < kJacobiRegs; ++u) {
-              const int k = lane + 32 * u;
-              if (k < N) {
-                wp[k] = cs * ra[u] - sn * rb[u];
-                wq[k] = sn * ra[u] + cs * rb[u];
-                qp[k] = cs * rc[u] - sn * rd[u];
-                qq[k] = sn * rc[u] + cs * rd[u];
-              }
-            }
-          }
-          continue;
-        }
-        T al = 0, be = 0, ga = 0;
-        for (int k = lane; k < N; k += 32) {
-          const T a = wp[k], b = wq[k];
-          al += a * a;
-          be += b * b;
-          ga += a * b;
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-          al += __shfl_xor_sync(0xffffffffu, al, o);
-          be += __shfl_xor_sync(0xffffffffu, be, o);
-          ga += __shfl_xor_sync(0xffffffffu, ga, o);
-        }
-        if (fabs(ga) > tol * sqrt(al * be) && al > T(0) && be > T(0)) {
-          if (lane == 0) off[sweep] = 1u;
-          const T zeta = (be - al) / (T(2) * ga);
-          const T t = (zeta >= T(0) ? T(1) : T(-1)) / (fabs(zeta) + sqrt(T(1) + zeta * zeta));
-          const T cs = T(1) / sqrt(T(1) + t * t), sn = cs * t;
-          for (int k = lane; k < N; k += 32) {
-            const T a = wp[k], b = wq[k];
-            wp[k] = cs * a - sn * b;
-            wq[k] = sn * a + cs * b;
-            const T c = qp[k], d = qq[k];
-            qp[k] = cs * c - sn * d;
-            qq[k] = sn * c + cs * d;
-          }
-        }
-      }
-      grid.sync();
-    }
-    if (*reinterpret_cast<volatile unsigned int*>(&off[sweep]) == 0u) break;
-  }
-  if (gtid == 0 && sweeps_out != nullptr) *sweeps_out = sweep + 1;
-
-  for (int j = gwarp; j < N; j += gwarps) {  // signed eigenvalues
-    T acc = 0;
-    for (int k = lane; k < N; k += 32) acc += W[(size_t)j * N + k] * Q[(size_t)j * N + k];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if (lane == 0) lam[j] = acc;
-  }
-  grid.sync();
-  for (int j = gwarp; j < N; j += gwarps) {  // ascending stable rank, sign rule, scatter
-    const T mine = lam[j];
-    int rk = 0;
     for (int k = lane; k < N; k += 32) {
-      const T o = lam[k];
-      rk += (o < mine) || (o == mine && k < j);
+      const T a = wp[k], b = wq[k];
+      al += a * a;
+      be += b * b;
+      ga += a * b;
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) rk += __shfl_xor_sync(0xffffffffu, rk, o);
-    T best = T(-1);
-    int bidx = 0;
-    for (int k = lane; k < N; k += 32) {
-      const T a = fabs(Q[(size_t)j * N + k]);
-      if (a > best) {
-        best = a;
-        bidx = k;
-      }
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const T ob = __shfl_xor_sync(0xffffffffu, best, o);
-      const int oi = __shfl_xor_sync(0xffffffffu, bidx, o);
-      if (ob > best || (ob == best && oi < bidx)) {
-        best = ob;
-        bidx = oi;
-      }
-    }
-    const T sgn = Q[(size_t)j * N + bidx] < T(0) ? T(-1) : T(1);
-    if (lane == 0) w_out[rk] = mine;
-    for (int k = lane; k < N; k += 32) B[(size_t)k * N + rk] = sgn * Q[(size_t)j * N + k];
   }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    al += __shfl_xor_sync(0xffffffffu, al, o);
+    be += __shfl_xor_sync(0xffffffffu, be, o);
+    ga += __shfl_xor_sync(0xffffffffu, ga, o);
+  }
+  const T prod = al * be;  // |ga| > tol sqrt(al be), without the square root
+  if (!(ga * ga > tol * tol * prod) || !(prod > T(0))) return 0.0f;
+  T cs, sn;
+  const float ratio = jacobi_angle(al, be, ga, prod, &cs, &sn);
+  if (REGS) {
+#pragma unroll
+    for (int u = 0; u < kJacobiRegs; ++u) {
+      const int k = lane + 32 * u;
+      if (k < N) {
+        wp[k] = cs * ra[u] - sn * rb[u];
+        wq[k] = sn * ra[u] + cs * rb[u];
+      }
+    }
+  } else {
+    for (int k = lane; k < N; k += 32) {
+      const T a = wp[k], b = wq[k];
+      wp[k] = cs * a - sn * b;
+      wq[k] = sn * a + cs * b;
+    }
+  }
+  return ratio;
 }
 
-// Block Jacobi for matrices beyond one SM: the rows are cut into blocks of b rows; in an
-// outer round every CTA of the (single) cluster loads one PAIR of blocks (2b rows of W and
-// of Q) into shared memory, runs a complete inner round-robin sweep over those 2b rows
-// there (b warps, one pair per warp, __syncthreads between inner rounds), and writes the
-// rows back; outer rounds follow the same circle-method tournament over the blocks and are
-// separated by the hardware cluster barrier.  Compared with one global barrier per scalar
-// round this needs (2 N / b - 1) barriers per sweep instead of (N - 1) and keeps the
-// rotations in shared memory.  A sweep whose largest |cos| was tiny ends the iteration
-// without a separate all-quiet sweep (quadratic convergence).
+// circle-method tournament: pair i of round r among n (even) players
 __device__ __forceinline__ void circle_pair(int n, int r, int i, int* p, int* q) {
   if (i == 0) {
     *p = n - 1;
@@ -486,134 +246,50 @@ __device__ __forceinline__ void circle_pair(int n, int r, int i, int* p, int* q)
   }
 }
 
+// W0 = Q0 C without materialising Q0: W0[j][c] = sum_k B[k][j] C[k][c] (warm) or C (cold).
+// Threads e -> (j, c) with c fastest: B[k][j] is a broadcast, C[k][c] is coalesced.
 template <typename T>
-__global__ void __launch_bounds__(512)
-jacobi_block_kernel(T* __restrict__ C, int N, T* __restrict__ w_out, T* __restrict__ B, T* __restrict__ W,
-                    T* __restrict__ Q, T* __restrict__ lam, unsigned int* __restrict__ off, int warm, int b, int nblk,
-                    const int* __restrict__ gate, const int* __restrict__ status_gate, int* __restrict__ sweeps_out) {
-  namespace cg = cooperative_groups;
-  extern __shared__ __align__(16) unsigned char jbs[];
-  if (gate != nullptr && *gate == 0) return;
-  if (status_gate != nullptr && *status_gate != SP_RUNNING) return;
-  cg::cluster_group cl = cg::this_cluster();
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int gthreads = gridDim.x * blockDim.x, gtid = blockIdx.x * blockDim.x + tid;
-  const int gwarp = gtid >> 5, gwarps = gthreads >> 5;
-  T* sW = reinterpret_cast<T*>(jbs);     // [2b][N]
-  T* sQ = sW + (size_t)2 * b * N;        // [2b][N]
-
-  for (int e = gtid; e < N * N; e += gthreads) {  // C = triu(C) + triu(C,1)^T (_cmaes.py:303)
-    const int r = e / N, c = e - r * N;
-    if (r > c) C[e] = C[c * N + r];
-  }
-  if (gtid < 64) off[gtid] = 0u;
-  cl.sync();
-  if (warm) {
-    for (int e = gtid; e < N * N; e += gthreads) {
-      const int j = e / N, r = e - j * N;
-      Q[e] = B[r * N + j];
-    }
-    cl.sync();
-    for (int e = gtid; e < N * N; e += gthreads) {  // W = Q C
-      const int j = e / N, c = e - j * N;
-      T acc = 0;
-      for (int k = 0; k < N; ++k) acc += Q[j * N + k] * C[k * N + c];
-      W[e] = acc;
-    }
-  } else {
-    for (int e = gtid; e < N * N; e += gthreads) {
-      const int r = e / N, c = e - r * N;
-      W[e] = C[e];
-      Q[e] = r == c ? T(1) : T(0);
-    }
-  }
-  cl.sync();
-
-  const T tol = T(4) * JacobiEps<T>::eps() * sqrt((T)(N < 16 ? 16 : N));
-  const float quiet = 0.25f * sqrtf((float)tol);  // a sweep below this needs no follow-up sweep
-  const int m = nblk / 2, n2 = 2 * b;
-  int sweep = 0;
-  for (; sweep < 60; ++sweep) {
-    for (int R = 0; R < nblk - 1; ++R) {
-      for (int bp = blockIdx.x; bp < m; bp += gridDim.x) {
-        int I, J;
-        circle_pair(nblk, R, bp, &I, &J);
-        // load the 2b rows (rows past N are zero)
-        for (int e = tid; e < n2 * N; e += blockDim.x) {
-          const int lr = e / N, k = e - lr * N;
-          const int gr = (lr < b ? I * b + lr : J * b + (lr - b));
-          sW[e] = gr < N ? W[(size_t)gr * N + k] : T(0);
-          sQ[e] = gr < N ? Q[(size_t)gr * N + k] : T(0);
-        }
-        __syncthreads();
-        for (int r = 0; r < n2 - 1; ++r) {
-          if (warp < b) {
-            int p, q;
-            circle_pair(n2, r, warp, &p, &q);
-            const int gp = (p < b ? I * b + p : J * b + (p - b)), gq = (q < b ? I * b + q : J * b + (q - b));
-            if (gp < N && gq < N) {
-              T* wp = sW + (size_t)p * N;
-              T* wq = sW + (size_t)q * N;
-              T al = 0, be = 0, ga = 0;
-              for (int k = lane; k < N; k += 32) {
-                const T a = wp[k], c = wq[k];
-                al += a * a;
-                be += c * c;
-                ga += a * c;
-              }
-#pragma unroll
-              for (int o = 16; o > 0; o >>= 1) {
-                al += __shfl_xor_sync(0xffffffffu, al, o);
-                be += __shfl_xor_sync(0xffffffffu, be, o);
-                ga += __shfl_xor_sync(0xffffffffu, ga, o);
-              }
-              const T nrm = sqrt(al * be);
-              if (fabs(ga) > tol * nrm && al > T(0) && be > T(0)) {
-                if (lane == 0) atomicMax(&off[sweep], __float_as_uint((float)(fabs(ga) / nrm)));
-                const T zeta = (be - al) / (T(2) * ga);
-                const T t = (zeta >= T(0) ? T(1) : T(-1)) / (fabs(zeta) + sqrt(T(1) + zeta * zeta));
-                const T cs = T(1) / sqrt(T(1) + t * t), sn = cs * t;
-                T* qp = sQ + (size_t)p * N;
-                T* qq = sQ + (size_t)q * N;
-                for (int k = lane; k < N; k += 32) {
-                  const T a = wp[k], c = wq[k];
-                  wp[k] = cs * a - sn * c;
-                  wq[k] = sn * a + cs * c;
-                  const T d = qp[k], f = qq[k];
-                  qp[k] = cs * d - sn * f;
-                  qq[k] = sn * d + cs * f;
-                }
-              }
-            }
-          }
-          __syncthreads();
-        }
-        for (int e = tid; e < n2 * N; e += blockDim.x) {  // write the rows back
-          const int lr = e / N, k = e - lr * N;
-          const int gr = (lr < b ? I * b + lr : J * b + (lr - b));
-          if (gr < N) {
-            W[(size_t)gr * N + k] = sW[e];
-            Q[(size_t)gr * N + k] = sQ[e];
-          }
-        }
-        __syncthreads();
+__device__ __forceinline__ void jacobi_start(const T* __restrict__ C, const T* __restrict__ B, T* __restrict__ W, int N,
+                                             int warm, int first, int stride) {
+  for (int e = first; e < N * N; e += stride) {
+    const int j = e / N, c = e - j * N;
+    T acc;
+    if (warm) {
+      T a0 = 0, a1 = 0;
+      int k = 0;
+      for (; k + 1 < N; k += 2) {
+        a0 += B[k * N + j] * C[k * N + c];
+        a1 += B[(k + 1) * N + j] * C[(k + 1) * N + c];
       }
-      cl.sync();
+      if (k < N) a0 += B[k * N + j] * C[k * N + c];
+      acc = a0 + a1;
+    } else {
+      acc = C[e];
     }
-    const unsigned int worst = *reinterpret_cast<volatile unsigned int*>(&off[sweep]);
-    if (worst == 0u || __uint_as_float(worst) < quiet) break;
+    W[e] = acc;
   }
-  if (gtid == 0 && sweeps_out != nullptr) *sweeps_out = sweep + 1;
+}
 
-  for (int j = gwarp; j < N; j += gwarps) {  // signed eigenvalues
+// rows of W (orthogonal) -> eigenvalues (ascending, stable) and sign-normalised eigenvectors
+// in the columns of B.  Phase 1 (norms) and phase 2 (rank, sign, scatter) are separated by
+// the caller's barrier; `lam` is N scalars of scratch visible to all participating warps.
+template <typename T>
+__device__ __forceinline__ void jacobi_norms(const T* __restrict__ W, int N, T* lam, int warp0, int nwarps, int lane) {
+  for (int j = warp0; j < N; j += nwarps) {
     T acc = 0;
-    for (int k = lane; k < N; k += 32) acc += W[(size_t)j * N + k] * Q[(size_t)j * N + k];
+    for (int k = lane; k < N; k += 32) {
+      const T a = W[(size_t)j * N + k];
+      acc += a * a;
+    }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if (lane == 0) lam[j] = acc;
+    if (lane == 0) lam[j] = sqrt(acc);
   }
-  cl.sync();
-  for (int j = gwarp; j < N; j += gwarps) {  // ascending stable rank, sign rule, scatter
+}
+template <typename T>
+__device__ __forceinline__ void jacobi_scatter(const T* __restrict__ W, int N, const T* lam, T* __restrict__ w_out,
+                                               T* __restrict__ B, int warp0, int nwarps, int lane) {
+  for (int j = warp0; j < N; j += nwarps) {
     const T mine = lam[j];
     int rk = 0;
     for (int k = lane; k < N; k += 32) {
@@ -622,10 +298,11 @@ jacobi_block_kernel(T* __restrict__ C, int N, T* __restrict__ w_out, T* __restri
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) rk += __shfl_xor_sync(0xffffffffu, rk, o);
+    // sign: largest |component| positive (first one on ties)
     T best = T(-1);
     int bidx = 0;
     for (int k = lane; k < N; k += 32) {
-      const T a = fabs(Q[(size_t)j * N + k]);
+      const T a = fabs(W[(size_t)j * N + k]);
       if (a > best) {
         best = a;
         bidx = k;
@@ -640,10 +317,290 @@ jacobi_block_kernel(T* __restrict__ C, int N, T* __restrict__ w_out, T* __restri
         bidx = oi;
       }
     }
-    const T sgn = Q[(size_t)j * N + bidx] < T(0) ? T(-1) : T(1);
+    const T inv = mine > T(0) ? T(1) / mine : T(0);
+    const T sgn = (W[(size_t)j * N + bidx] < T(0) ? T(-1) : T(1)) * inv;
     if (lane == 0) w_out[rk] = mine;
-    for (int k = lane; k < N; k += 32) B[(size_t)k * N + rk] = sgn * Q[(size_t)j * N + k];
+    for (int k = lane; k < N; k += 32) B[(size_t)k * N + rk] = sgn * W[(size_t)j * N + k];
   }
+}
+
+// One CTA of 1024 threads, W in shared memory (N^2 scalars fit); a warp owns one (p, q)
+// pair of the round-robin round.
+template <typename T>
+__global__ void __launch_bounds__(kJacobiThreads, 1)
+jacobi_eigh_kernel(T* __restrict__ C, int N, T* __restrict__ w_out, T* __restrict__ B, T* __restrict__ lam_g,
+                   int warm, const int* __restrict__ gate, const int* __restrict__ status_gate,
+                   int* __restrict__ sweeps_out) {
+  extern __shared__ __align__(16) unsigned char jsm[];
+  __shared__ unsigned int s_off;
+  if (gate != nullptr && *gate == 0) return;
+  if (status_gate != nullptr && *status_gate != SP_RUNNING) return;
+  T* W = reinterpret_cast<T*>(jsm);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = kJacobiThreads / 32;
+
+  // symmetrise from the upper triangle (_cmaes.py:303): C = triu(C) + triu(C,1)^T
+  for (int e = tid; e < N * N; e += kJacobiThreads) {
+    const int r = e / N, c = e - r * N;
+    if (r > c) C[e] = C[c * N + r];
+  }
+  __syncthreads();
+  jacobi_start<T>(C, B, W, N, warm, tid, kJacobiThreads);
+  __syncthreads();
+
+  const T tol = jacobi_tol<T>(N);
+  const float quiet = 0.25f * sqrtf((float)tol);  // a sweep below this needs no follow-up sweep
+  const int n = N + (N & 1);  // even player count; index N (if any) is a bye
+  const int half = n / 2;
+  const bool regs = N <= 32 * kJacobiRegs;
+  int sweep = 0;
+  for (; sweep < 60; ++sweep) {
+    if (tid == 0) s_off = 0u;
+    __syncthreads();
+    float worst = 0.0f;
+    for (int r = 0; r < n - 1; ++r) {
+      for (int i = warp; i < half; i += nwarps) {
+        int p, q;
+        circle_pair(n, r, i, &p, &q);
+        if (p >= N || q >= N) continue;
+        const float c = regs ? jacobi_rotate<T, true>(W + (size_t)p * N, W + (size_t)q * N, N, lane, tol)
+                             : jacobi_rotate<T, false>(W + (size_t)p * N, W + (size_t)q * N, N, lane, tol);
+        worst = fmaxf(worst, c);
+      }
+      __syncthreads();
+    }
+    if (lane == 0 && worst > 0.0f) atomicMax(&s_off, __float_as_uint(worst));
+    __syncthreads();
+    const unsigned int off = s_off;
+    __syncthreads();
+    if (off == 0u || __uint_as_float(off) < quiet) break;
+  }
+  if (tid == 0 && sweeps_out != nullptr) *sweeps_out = sweep + 1;
+  jacobi_norms<T>(W, N, lam_g, warp, nwarps, lane);
+  __syncthreads();
+  jacobi_scatter<T>(W, N, lam_g, w_out, B, warp, nwarps, lane);
+}
+
+// Fixed-shape fast path of the block kernel: rows of exactly CH * 32 sixteen-byte vectors
+// (N = CH * 32 * VEC), every row valid.  Lane l owns vectors l, l + 32, ... of a row, so the
+// loads/stores are 128-bit, there are no bounds predicates and all addresses are constants
+// off the row base (the generic path spends ~640 warp instructions per pair, mostly
+// predicates and address arithmetic; this one ~190).
+template <typename T, int CH>
+__device__ __forceinline__ float jacobi_rotate_v(T* __restrict__ wp, T* __restrict__ wq, int lane, T tol) {
+  using V = typename Num<T>::vec_t;
+  constexpr int VEC = Num<T>::VEC;
+  T ra[CH][VEC], rb[CH][VEC];
+#pragma unroll
+  for (int c = 0; c < CH; ++c) {
+    const V a = reinterpret_cast<const V*>(wp)[lane + 32 * c];
+    const V b = reinterpret_cast<const V*>(wq)[lane + 32 * c];
+    const T* pa = reinterpret_cast<const T*>(&a);
+    const T* pb = reinterpret_cast<const T*>(&b);
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) {
+      ra[c][e] = pa[e];
+      rb[c][e] = pb[e];
+    }
+  }
+  T al = 0, be = 0, ga = 0;
+#pragma unroll
+  for (int c = 0; c < CH; ++c)
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) {
+      al += ra[c][e] * ra[c][e];
+      be += rb[c][e] * rb[c][e];
+      ga += ra[c][e] * rb[c][e];
+    }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    al += __shfl_xor_sync(0xffffffffu, al, o);
+    be += __shfl_xor_sync(0xffffffffu, be, o);
+    ga += __shfl_xor_sync(0xffffffffu, ga, o);
+  }
+  const T prod = al * be;  // |ga| > tol sqrt(al be), without the square root
+  if (!(ga * ga > tol * tol * prod) || !(prod > T(0))) return 0.0f;
+  T cs, sn;
+  const float ratio = jacobi_angle(al, be, ga, prod, &cs, &sn);
+#pragma unroll
+  for (int c = 0; c < CH; ++c) {
+    V a, b;
+    T* pa = reinterpret_cast<T*>(&a);
+    T* pb = reinterpret_cast<T*>(&b);
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) {
+      pa[e] = cs * ra[c][e] - sn * rb[c][e];
+      pb[e] = sn * ra[c][e] + cs * rb[c][e];
+    }
+    reinterpret_cast<V*>(wp)[lane + 32 * c] = a;
+    reinterpret_cast<V*>(wq)[lane + 32 * c] = b;
+  }
+  return ratio;
+}
+
+// one outer round of the block kernel on the fast path: load the 2b rows of blocks (I, J)
+// (warp w owns rows w and w + b: 2 CH independent 128-bit loads per lane, all in flight), a
+// complete inner round-robin sweep (pair indices advance by one modulo 2b - 1 per round, so
+// no division), write the rows back.
+template <typename T, int CH>
+__device__ __forceinline__ float jacobi_block_round_v(T* __restrict__ W, T* __restrict__ sW, int b, int I, int J,
+                                                      T tol) {
+  using V = typename Num<T>::vec_t;
+  constexpr int N = CH * 32 * Num<T>::VEC;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int n2 = 2 * b;
+  V* g0 = reinterpret_cast<V*>(W + (size_t)(I * b + warp) * N);
+  V* g1 = reinterpret_cast<V*>(W + (size_t)(J * b + warp) * N);
+  V* s0 = reinterpret_cast<V*>(sW + (size_t)warp * N);
+  V* s1 = reinterpret_cast<V*>(sW + (size_t)(warp + b) * N);
+  {
+    V t0[CH], t1[CH];
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
+      t0[c] = __ldcg(g0 + lane + 32 * c);
+      t1[c] = __ldcg(g1 + lane + 32 * c);
+    }
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
+      s0[lane + 32 * c] = t0[c];
+      s1[lane + 32 * c] = t1[c];
+    }
+  }
+  __syncthreads();
+  float worst = 0.0f;
+  int p = warp == 0 ? n2 - 1 : warp, q = warp == 0 ? 0 : n2 - 1 - warp;
+  for (int r = 0; r < n2 - 1; ++r) {
+    worst = fmaxf(worst, jacobi_rotate_v<T, CH>(sW + (size_t)p * N, sW + (size_t)q * N, lane, tol));
+    __syncthreads();
+    if (warp != 0) p = p + 1 == n2 - 1 ? 0 : p + 1;
+    q = q + 1 == n2 - 1 ? 0 : q + 1;
+  }
+#pragma unroll
+  for (int c = 0; c < CH; ++c) {
+    __stcg(g0 + lane + 32 * c, s0[lane + 32 * c]);
+    __stcg(g1 + lane + 32 * c, s1[lane + 32 * c]);
+  }
+  __syncthreads();
+  return worst;
+}
+
+// Block Jacobi for matrices beyond one SM: the rows are cut into blocks of b rows; in an
+// outer round every CTA of the (single) cluster loads one PAIR of blocks (2b rows of W)
+// into shared memory, runs a complete inner round-robin sweep over those 2b rows there
+// (b warps, one pair per warp, __syncthreads between inner rounds), and writes the rows
+// back; outer rounds follow the same circle-method tournament over the blocks and are
+// separated by the hardware cluster barrier.  Compared with one global barrier per scalar
+// round this needs (2 N / b - 1) barriers per sweep instead of (N - 1) and keeps the
+// rotations in shared memory.  A sweep whose largest |cos| was tiny ends the iteration
+// without a separate all-quiet sweep (quadratic convergence).
+template <typename T>
+__global__ void __launch_bounds__(512, 1)
+jacobi_block_kernel(T* __restrict__ C, int N, T* __restrict__ w_out, T* __restrict__ B, T* __restrict__ W,
+                    T* __restrict__ lam, unsigned int* __restrict__ off, int warm, int b, int nblk,
+                    const int* __restrict__ gate, const int* __restrict__ status_gate, int* __restrict__ sweeps_out) {
+  namespace cg = cooperative_groups;
+  extern __shared__ __align__(16) unsigned char jbs[];
+  if (gate != nullptr && *gate == 0) return;
+  if (status_gate != nullptr && *status_gate != SP_RUNNING) return;
+  cg::cluster_group cl = cg::this_cluster();
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int gthreads = gridDim.x * blockDim.x, gtid = blockIdx.x * blockDim.x + tid;
+  const int gwarp = gtid >> 5, gwarps = gthreads >> 5;
+  T* sW = reinterpret_cast<T*>(jbs);  // [2b][N]
+
+  for (int e = gtid; e < N * N; e += gthreads) {  // C = triu(C) + triu(C,1)^T (_cmaes.py:303)
+    const int r = e / N, c = e - r * N;
+    if (r > c) C[e] = C[c * N + r];
+  }
+  if (gtid < 64) off[gtid] = 0u;
+  cl.sync();
+  jacobi_start<T>(C, B, W, N, warm, gtid, gthreads);
+  cl.sync();
+
+  const T tol = jacobi_tol<T>(N);
+  const float quiet = 0.25f * sqrtf((float)tol);
+  const int m = nblk / 2, n2 = 2 * b;
+  const bool regs = N <= 32 * kJacobiRegs;
+  const int nv = N / Num<T>::VEC;  // rows are copied in 16-byte vectors when N allows it
+  const bool vec_ok = (N % Num<T>::VEC) == 0;
+  using V = typename Num<T>::vec_t;
+  const int row_vecs = N / (32 * Num<T>::VEC);
+  const int fast_ch = (N % (32 * Num<T>::VEC) == 0 && row_vecs <= 4 && N % b == 0 && nblk * b == N &&
+                       (int)blockDim.x == 32 * b) ? row_vecs : 0;
+  int sweep = 0;
+  for (; sweep < 60; ++sweep) {
+    float worst = 0.0f;
+    for (int R = 0; R < nblk - 1; ++R) {
+      for (int bp = blockIdx.x; bp < m; bp += gridDim.x) {
+        int I, J;
+        circle_pair(nblk, R, bp, &I, &J);
+        if (fast_ch != 0) {  // N = fast_ch * 32 * VEC, b divides N, one warp per row pair
+          float c = 0.0f;
+          switch (fast_ch) {
+            case 1: c = jacobi_block_round_v<T, 1>(W, sW, b, I, J, tol); break;
+            case 2: c = jacobi_block_round_v<T, 2>(W, sW, b, I, J, tol); break;
+            case 3: c = jacobi_block_round_v<T, 3>(W, sW, b, I, J, tol); break;
+            default: c = jacobi_block_round_v<T, 4>(W, sW, b, I, J, tol); break;
+          }
+          worst = fmaxf(worst, c);
+          continue;
+        }
+        // load the 2b rows (rows past N are zero)
+        if (vec_ok) {
+          for (int e = tid; e < n2 * nv; e += blockDim.x) {
+            const int lr = e / nv, k = e - lr * nv;
+            const int gr = (lr < b ? I * b + lr : J * b + (lr - b));
+            V v;
+            if (gr < N) v = __ldcg(reinterpret_cast<const V*>(W + (size_t)gr * N) + k);
+            else memset(&v, 0, sizeof(V));
+            reinterpret_cast<V*>(sW + (size_t)lr * N)[k] = v;
+          }
+        } else {
+          for (int e = tid; e < n2 * N; e += blockDim.x) {
+            const int lr = e / N, k = e - lr * N;
+            const int gr = (lr < b ? I * b + lr : J * b + (lr - b));
+            sW[e] = gr < N ? __ldcg(W + (size_t)gr * N + k) : T(0);
+          }
+        }
+        __syncthreads();
+        for (int r = 0; r < n2 - 1; ++r) {
+          if (warp < b) {
+            int p, q;
+            circle_pair(n2, r, warp, &p, &q);
+            const int gp = (p < b ? I * b + p : J * b + (p - b)), gq = (q < b ? I * b + q : J * b + (q - b));
+            if (gp < N && gq < N) {
+              const float c = regs ? jacobi_rotate<T, true>(sW + (size_t)p * N, sW + (size_t)q * N, N, lane, tol)
+                                   : jacobi_rotate<T, false>(sW + (size_t)p * N, sW + (size_t)q * N, N, lane, tol);
+              worst = fmaxf(worst, c);
+            }
+          }
+          __syncthreads();
+        }
+        if (vec_ok) {
+          for (int e = tid; e < n2 * nv; e += blockDim.x) {  // write the rows back
+            const int lr = e / nv, k = e - lr * nv;
+            const int gr = (lr < b ? I * b + lr : J * b + (lr - b));
+            if (gr < N) __stcg(reinterpret_cast<V*>(W + (size_t)gr * N) + k, reinterpret_cast<const V*>(sW + (size_t)lr * N)[k]);
+          }
+        } else {
+          for (int e = tid; e < n2 * N; e += blockDim.x) {
+            const int lr = e / N, k = e - lr * N;
+            const int gr = (lr < b ? I * b + lr : J * b + (lr - b));
+            if (gr < N) __stcg(W + (size_t)gr * N + k, sW[e]);
+          }
+        }
+        __syncthreads();
+      }
+      cl.sync();
+    }
+    if (lane == 0 && worst > 0.0f) atomicMax(&off[sweep], __float_as_uint(worst));
+    cl.sync();
+    const unsigned int w = __ldcg(&off[sweep]);
+    if (w == 0u || __uint_as_float(w) < quiet) break;
+  }
+  if (gtid == 0 && sweeps_out != nullptr) *sweeps_out = sweep + 1;
+  jacobi_norms<T>(W, N, lam, gwarp, gwarps, lane);
+  cl.sync();
+  jacobi_scatter<T>(W, N, lam, w_out, B, gwarp, gwarps, lane);
 }
 
 // scratch scalars needed behind `work` for an N x N decomposition
@@ -652,68 +609,54 @@ inline size_t jacobi_work_scalars(int N) { return 2 * (size_t)N * N + (size_t)N 
 template <typename T>
 inline cudaError_t jacobi_launch(T* C, int N, T* w, T* B, T* work, int warm, const int* gate,
                                  const int* status_gate, int* sweeps, cudaStream_t s) {
-  const size_t need = 2 * (size_t)N * N * sizeof(T);
-  if (need <= 200 * 1024) {  // whole problem in one SM's shared memory
+  T* W = work;
+  T* lam = work + 2 * (size_t)N * N;
+  unsigned int* off = reinterpret_cast<unsigned int*>(lam + N);
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) dev = 0;
+  const size_t need = (size_t)N * N * sizeof(T);
+  static const char* env_one = getenv("SP_EIGH_ONE_CTA");  // profiling switch: largest N on the one-CTA kernel
+  const int one_cta_max = env_one != nullptr ? atoi(env_one) : 64;
+  // up to 64 rows one CTA holds a whole round (32 pairs, one per warp); beyond that several SMs
+  // working on block pairs beat one SM making several passes per round
+  if (need <= 200 * 1024 && N <= one_cta_max) {
     auto kern = jacobi_eigh_kernel<T>;
     static thread_local bool configured[64];
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (dev < 0 || dev >= 64) dev = 0;
     if (!configured[dev]) {
       cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
       if (e != cudaSuccess) return e;
       configured[dev] = true;
     }
-    kern<<<1, kJacobiThreads, need, s>>>(C, N, w, B, work, work + (size_t)N * N, 1, warm, gate, status_gate, sweeps);
+    kern<<<1, kJacobiThreads, need, s>>>(C, N, w, B, lam, warm, gate, status_gate, sweeps);
     return cudaGetLastError();
   }
-  T* W = work;
-  T* Q = work + (size_t)N * N;
-  T* lam = Q + (size_t)N * N;
-  unsigned int* off = reinterpret_cast<unsigned int*>(lam + N);
-  static const bool scalar_rounds = getenv("SP_EIGH_SCALAR") != nullptr;  // profiling switch
-  if (!scalar_rounds) {
-    int b = 16;
-    while (b > 2 && 4 * (size_t)b * N * sizeof(T) > 200 * 1024) b >>= 1;
-    int nblk = (N + b - 1) / b;
-    nblk += nblk & 1;
-    const int m = nblk / 2;
-    const int ctas = m < 8 ? m : 8;
-    const size_t smem = 4 * (size_t)b * N * sizeof(T);
-    auto kern = jacobi_block_kernel<T>;
-    static thread_local bool configured[64];
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (dev < 0 || dev >= 64) dev = 0;
-    if (!configured[dev]) {
-      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-      if (e != cudaSuccess) return e;
-      configured[dev] = true;
-    }
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(ctas);
-    cfg.blockDim = dim3(b * 32 < 128 ? 128 : b * 32);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = s;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = ctas;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, kern, C, N, w, B, W, Q, lam, off, warm, b, nblk, gate, status_gate, sweeps);
+  static const char* env_b = getenv("SP_EIGH_BLOCK");  // profiling switch: rows per block
+  int b = 16;
+  while (b > 2 && N <= 8 * b) b >>= 1;  // aim at >= 8 block pairs (one per CTA) per outer round
+  if (env_b != nullptr) b = atoi(env_b);
+  if (b < 2) b = 2;
+  if (b > 16) b = 16;
+  while (b > 2 && 2 * (size_t)b * N * sizeof(T) > 200 * 1024) b >>= 1;
+  int nblk = (N + b - 1) / b;
+  nblk += nblk & 1;
+  const int m = nblk / 2;
+  static const char* env_c = getenv("SP_EIGH_CTAS");  // profiling switch: 8 = portable cluster size only
+  const int cmax = env_c != nullptr && atoi(env_c) == 8 ? 8 : 16;
+  const int ctas = m < cmax ? m : cmax;
+  const size_t smem = 2 * (size_t)b * N * sizeof(T);
+  auto kern = jacobi_block_kernel<T>;
+  static thread_local bool configured[64];
+  if (!configured[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    if (e != cudaSuccess) return e;
+    configured[dev] = true;
   }
-  const int pairs = (N + 1) / 2;
-  // one cluster: 8 CTAs (portable) up to 512 pairs' worth of warps, 16 CTAs beyond
-  int ctas = pairs <= 8 * 32 ? 8 : 16;
-  int warps = (pairs + ctas - 1) / ctas;
-  if (warps > 32) warps = 32;
-  const int threads = warps * 32;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(ctas);
-  cfg.blockDim = dim3(threads);
-  cfg.dynamicSmemBytes = 0;
+  cfg.blockDim = dim3(b * 32 < 128 ? 128 : b * 32);
+  cfg.dynamicSmemBytes = smem;
   cfg.stream = s;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -722,19 +665,7 @@ inline cudaError_t jacobi_launch(T* C, int N, T* w, T* B, T* work, int warm, con
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t e;
-  if (threads <= 512) {
-    auto kern = jacobi_grid_kernel<T, true, 512>;
-    e = cudaLaunchKernelEx(&cfg, kern, C, N, w, B, W, Q, lam, off, warm, gate, status_gate, sweeps);
-  } else {
-    auto kern = jacobi_grid_kernel<T, true, 1024>;
-    if (ctas > 8) {
-      e = cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
-      if (e != cudaSuccess) return e;
-    }
-    e = cudaLaunchKernelEx(&cfg, kern, C, N, w, B, W, Q, lam, off, warm, gate, status_gate, sweeps);
-  }
-  return e;
+  return cudaLaunchKernelEx(&cfg, kern, C, N, w, B, W, lam, off, warm, b, nblk, gate, status_gate, sweeps);
 }
 
 }  // namespace sp
