@@ -242,6 +242,20 @@ int sp_peer_free(void* d_mailbox);
 int sp_pso_run_sharded(const sp_pso_state* st, int it_first, int n, int32_t* d_rank_all, void* stream);
 
 
+/* ---- 8f-3: user objectives compiled at run time (NVRTC) ------------------------------
+ * The reference's fun(x, *args) -> float contract (_common.py:27-106) keeps arbitrary
+ * Python callables on the host.  An objective given as CUDA C source that defines
+ *     __device__ real objective(const real* x, int n)      (real = float or double)
+ * is compiled for sm_100a and evaluated on the device: f[i] = objective(X[i] * scale + shift)
+ * (scale/shift optional, _cmaes.py:168-173), one thread per individual on rows staged
+ * through shared memory.  sp_jit_check only compiles (no GPU needed) and reports the
+ * compiler log through sp_last_error(). */
+int sp_jit_check(const char* source, int dtype, int64_t* cubin_bytes);
+int sp_jit_compile(const char* source, int dtype, void** handle);
+int sp_jit_eval(void* handle, int dtype, const void* d_X, int64_t P, int N, int64_t ld, const void* d_scale,
+                const void* d_shift, void* d_f, void* stream);
+int sp_jit_free(void* handle);
+
 /* ---- counter-based draws as a buffer: out[row][j] = U[0,1) (normal = 0) or N(0,1)
  * (normal = 1) of Philox counter (j / (16/sizeof(T)), row, it, purpose); the same
  * streams the generation kernels consume in place (csrc/philox.cuh). */

@@ -155,6 +155,10 @@ SIGNATURES = {
     "sp_peer_close": (_i, [vp]),
     "sp_peer_free": (_i, [vp]),
     "sp_pso_run_sharded": (_i, [C.POINTER(PsoState), _i, _i, vp, vp]),
+    "sp_jit_check": (_i, [C.c_char_p, _i, C.POINTER(_i64)]),
+    "sp_jit_compile": (_i, [C.c_char_p, _i, C.POINTER(vp)]),
+    "sp_jit_eval": (_i, [vp, _i, vp, _i64, _i, _i64, vp, vp, vp, vp]),
+    "sp_jit_free": (_i, [vp]),
     "sp_random_fill": (_i, [_i, vp, _i64, _i, _i64, _i, _i, _u64, _i, vp]),
     "sp_fitness_rank": (_i, [_i, vp, _i64, vp, vp]),
     "sp_sym_eigh": (_i, [_i, vp, _i, vp, vp, vp, _i, vp, vp]),

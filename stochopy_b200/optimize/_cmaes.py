@@ -188,7 +188,8 @@ def minimize(
                 src = arx.clamp(-1.0, 1.0) if penal else arx
                 eng.evaluate(fun, args, obj, src, P, N, arfit, bufs["xscale"], bufs["xshift"])
             else:
-                eng.evaluate(fun, args, None, arx, P, N, arfit, to_user=lambda X: unstd(valid_rows(X)))
+                eng.evaluate(fun, args, None, arx, P, N, arfit, bufs["xscale"], bufs["xshift"],
+                             to_user=lambda X: unstd(valid_rows(X)), clip=penal)
             L.call("sp_cma_update", C.byref(st), it, eng.stream)
             if eigh == "host":
                 if eng.read_ctrl(ctrl, L.EsCtrl).do_eig:  # _cmaes.py:301-309 with numpy's LAPACK

@@ -140,13 +140,20 @@ class Engine:
         return torch.from_numpy(raw).to(self.device)
 
     # -- population evaluation (the reference's `fun(X)` wrapper) -----------------------
-    def evaluate(self, fun, args, obj, X, p, n, out, scale=None, shift=None, to_user=None):
-        """out[:p] = fun(X[i]).  Device kernel for factory objectives; otherwise the
-        reference's per-individual Python contract via a host round trip."""
+    def evaluate(self, fun, args, obj, X, p, n, out, scale=None, shift=None, to_user=None, clip=False):
+        """out[:p] = fun(X[i]).  Device kernel for factory objectives and for objectives
+        compiled from CUDA source (jit.py); otherwise the reference's per-individual
+        Python contract via a host round trip.  scale/shift (device) and clip describe on
+        the device what ``to_user`` does on the host: x -> clip(x, -1, 1) * scale + shift."""
         if obj is not None:
             L.call("sp_eval", obj, self.sp_dt, X.data_ptr(), p, n, X.shape[1],
                    None if scale is None else scale.data_ptr(), None if shift is None else shift.data_ptr(),
                    out.data_ptr(), self.stream)
+            return
+        if getattr(fun, "_sp_jit", False):
+            if args:
+                raise ValueError()
+            fun.evaluate_rows(self, X.clamp(-1.0, 1.0) if clip else X, p, n, out, scale, shift)
             return
         host = self.download_rows(X, p, n)
         if to_user is not None:

@@ -154,7 +154,8 @@ def minimize(
             L.call("sp_vd_generation", C.byref(st), it, eng.stream)
         else:
             L.call("sp_vd_sample", C.byref(st), it, 0, eng.stream)
-            eng.evaluate(fun, args, None, arx, P, N, arfit, to_user=lambda X: unstd(valid_rows(X)))
+            eng.evaluate(fun, args, None, arx, P, N, arfit, bufs["xscale"], bufs["xshift"],
+                         to_user=lambda X: unstd(valid_rows(X)), clip=penal)
             L.call("sp_vd_update", C.byref(st), it, eng.stream)
         c = eng.read_ctrl(ctrl, L.EsCtrl)
         if observe:

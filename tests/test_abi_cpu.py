@@ -98,3 +98,22 @@ def test_result_type():
     assert r.fun == 1.0 and "xall" not in repr(r) and "fun" in dir(r)
     with pytest.raises(AttributeError):
         r.nothing
+
+
+def test_jit_objective_compiles_without_a_device():
+    """8f-3: NVRTC turns the user's CUDA source into an sm_100a cubin here (no GPU needed);
+    compile errors come back with the compiler log."""
+    ok = stochopy_b200.jit_objective(
+        "__device__ real objective(const real* x, int n) { real s = 0; for (int i = 0; i < n; ++i) s += x[i] * x[i]; return s; }")
+    assert ok.check("float64") > 1000 and ok.check("float32") > 1000
+    bad = stochopy_b200.jit_objective("__device__ real objective(const real* x, int n) { return undefined_name; }")
+    with pytest.raises(L.EngineError, match="undefined"):
+        bad.check()
+    with pytest.raises(ValueError):
+        stochopy_b200.jit_objective("int f();")
+
+
+def test_sizes_of_state_structs_match_the_header_layout():
+    # pointers / int64 / double are 8-byte aligned: the ctypes mirrors must not be packed differently
+    assert C.sizeof(L.PsoState) % 8 == 0 and C.sizeof(L.DeState) % 8 == 0
+    assert L.PsoState.peers.offset == L.PsoState.mailbox.offset + 8
