@@ -228,6 +228,66 @@ class History:
             res.update({"xall": self.xall[:it], "funall": self.funall[:it]})
 
 
+class HistoryStreamer:
+    """`return_all` without stalling the generation loop (reference
+    `_de.py:221-234,270-278`, `_cpso.py:231-244`): after every generation the first `nout`
+    rows and their fitness are snapshotted device-to-device into a small ring on the
+    launching stream, and a side stream moves the ring slots to pinned host memory while
+    the next generations run.  An event per slot keeps a slot from being overwritten
+    before its copy has left the device.  Nothing here synchronises with the host until
+    ``finish``."""
+
+    SLOTS = 4
+    PIN_LIMIT = 2 << 30  # bytes of pinned history we are willing to allocate
+
+    @classmethod
+    def maybe(cls, eng, hist, callback, P, N):
+        if not hist.enabled or callback is not None or hist.nout <= 0:
+            return None
+        if hist.xall.shape[0] * hist.nout * (N + 1) * eng.np_dt.itemsize > cls.PIN_LIMIT:
+            return None
+        return cls(eng, hist, N)
+
+    def __init__(self, eng, hist, N):
+        self.eng, self.N, self.nout = eng, N, hist.nout
+        self.main = torch.cuda.current_stream(eng.device)
+        self.side = torch.cuda.Stream(device=eng.device)
+        maxiter = hist.xall.shape[0]
+        self.slotX = [eng.empty(self.nout, N) for _ in range(self.SLOTS)]
+        self.slotF = [eng.empty(self.nout) for _ in range(self.SLOTS)]
+        self.hX = torch.empty((maxiter, self.nout, N), dtype=eng.t_dt, pin_memory=True)
+        self.hF = torch.empty((maxiter, self.nout), dtype=eng.t_dt, pin_memory=True)
+        self.free = [None] * self.SLOTS
+        self.first = None
+
+    def push(self, it, X, fit):
+        """Enqueue the snapshot of generation `it` (X: device rows, fit: device vector)."""
+        k = it % self.SLOTS
+        if self.free[k] is not None:
+            self.main.wait_event(self.free[k])
+        self.slotX[k].copy_(X[: self.nout, : self.N])
+        self.slotF[k].copy_(fit[: self.nout])
+        ready = torch.cuda.Event()
+        ready.record(self.main)
+        with torch.cuda.stream(self.side):
+            self.side.wait_event(ready)
+            self.hX[it - 1].copy_(self.slotX[k], non_blocking=True)
+            self.hF[it - 1].copy_(self.slotF[k], non_blocking=True)
+            done = torch.cuda.Event()
+            done.record(self.side)
+        self.free[k] = done
+        if self.first is None:
+            self.first = it
+
+    def finish(self, hist, nit):
+        """Wait for the copies and hand generations first..nit to the History arrays."""
+        self.side.synchronize()
+        if self.first is not None and nit >= self.first:
+            a, b = self.first - 1, nit
+            hist.xall[a:b] = self.hX[a:b].numpy()
+            hist.funall[a:b] = self.hF[a:b].numpy()
+
+
 def validate_common(fun, bounds, callback):
     """Checks shared by every front-end (same exception types as the reference)."""
     if not hasattr(fun, "__call__"):

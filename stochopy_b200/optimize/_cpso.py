@@ -11,7 +11,7 @@ import numpy as np
 import torch
 
 from .. import _lib as L
-from ._common import Engine, History, NumpyStream, device_objective, fresh_seed, messages, validate_common
+from ._common import Engine, History, HistoryStreamer, NumpyStream, device_objective, fresh_seed, messages, validate_common
 from ._helpers import OptimizeResult, register
 
 __all__ = ["minimize"]
@@ -137,12 +137,23 @@ def minimize(
     it = 1
     last = max(int(maxiter), 2)
     fast = obj is not None and stream is None and not observe
+    streamer = HistoryStreamer.maybe(eng, hist, callback, P, N) if obj is not None and stream is None else None
     keep = None
     rank_ptr = rank.data_ptr() if restart else None
     while c.status == L.SP_RUNNING:
         if fast:
             n = min(64 if it < 64 else 256, last - it)
             L.call("sp_pso_run", C.byref(st), it + 1, n, rank_ptr, eng.stream)
+            c = eng.read_ctrl(ctrl)
+            it = c.nit
+            continue
+        if streamer is not None:  # return_all: snapshots leave through a side stream, no per-generation sync
+            for _ in range(min(64, last - it)):
+                it += 1
+                L.call("sp_pso_generation", C.byref(st), it, eng.stream)
+                streamer.push(it, X, pfit)  # the population before the competitive restart, _cpso.py:281-307
+                if restart:
+                    L.call("sp_cpso_restart", C.byref(st), it, rank_ptr, eng.stream)
             c = eng.read_ctrl(ctrl)
             it = c.nit
             continue
@@ -172,6 +183,8 @@ def minimize(
                     eng.sync()
 
     it = c.nit
+    if streamer is not None:
+        streamer.finish(hist, it)
     res = OptimizeResult(
         x=gbest[:N].to("cpu").numpy().astype(np.float64),
         success=c.status >= 0,

@@ -12,7 +12,7 @@ import numpy as np
 import torch
 
 from .. import _lib as L
-from ._common import Engine, History, NumpyStream, device_objective, fresh_seed, messages, validate_common
+from ._common import Engine, History, HistoryStreamer, NumpyStream, device_objective, fresh_seed, messages, validate_common
 from ._helpers import OptimizeResult, register
 
 __all__ = ["minimize"]
@@ -131,11 +131,20 @@ def minimize(
     it = 1
     last = max(int(maxiter), 2)
     fast = obj is not None and stream is None and not observe
+    streamer = HistoryStreamer.maybe(eng, hist, callback, P, N) if obj is not None and stream is None else None
     keep = None
     while c.status == L.SP_RUNNING:
         if fast:  # enqueue a chunk of generations; kernels no-op once ctrl.status is set
             n = min(64 if it < 64 else 256, last - it)
             L.call("sp_de_run", C.byref(st), it + 1, n, eng.stream)
+            c = eng.read_ctrl(ctrl)
+            it = c.nit
+            continue
+        if streamer is not None:  # return_all: snapshots leave through a side stream, no per-generation sync
+            for _ in range(min(64, last - it)):
+                it += 1
+                L.call("sp_de_generation", C.byref(st), it, eng.stream)
+                streamer.push(it, X[(it & 1) ^ 1], pfit)
             c = eng.read_ctrl(ctrl)
             it = c.nit
             continue
@@ -158,6 +167,8 @@ def minimize(
         c, xbest = snapshot(it, new)
 
     it = c.nit
+    if streamer is not None:
+        streamer.finish(hist, it)
     xbest = gbest[:N].to("cpu").numpy().astype(np.float64)
     res = OptimizeResult(
         x=xbest,

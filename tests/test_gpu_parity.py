@@ -500,3 +500,23 @@ def test_na_direct_call_default_callback_quirk():
 
     with pytest.raises(ValueError):  # callback=True default is not callable (_na.py:26,113-114)
         sb.optimize.na(sb.factory.sphere, [[-1, 1]] * 2)
+
+
+# ---- 8f-1: return_all streamed through a device ring + side stream -------------------------------
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("method,opts", [("de", dict(strategy="best1bin")), ("pso", {}), ("cpso", dict(competitivity=1.0))])
+def test_return_all_streaming_equals_synchronous_history(method, opts, dtype):
+    """Without a callback the per-generation snapshots leave through HistoryStreamer (no host
+    sync per generation); with a callback the synchronous path records them.  Same arrays,
+    including a run that terminates inside a chunk (ftol) -- xall/funall are cut at nit."""
+    import stochopy_b200 as sb
+
+    b = [[-5.12, 5.12]] * 6
+    for ftol in (-1.0, 5.0e-2):
+        o = dict(opts, maxiter=90, popsize=40, seed=17, dtype=dtype, updating="deferred", return_all=True,
+                 verbosity=0.5, ftol=ftol)
+        a = sb.optimize.minimize(sb.factory.sphere, b, method=method, options=dict(o))
+        d = sb.optimize.minimize(sb.factory.sphere, b, method=method, options=dict(o), callback=lambda X, s: None)
+        assert (a.nit, a.status) == (d.nit, d.status) and (ftol < 0) == (a.nit == 90)
+        assert a.xall.shape == d.xall.shape == (a.nit, 20, 6) and a.funall.shape == (a.nit, 20)
+        assert np.array_equal(a.xall, d.xall) and np.array_equal(a.funall, d.funall)
