@@ -1,7 +1,8 @@
 // Small dense linear algebra for the CMA-ES path: tiled GEMMs with fused
 // prologues/epilogues and a one-sided Jacobi symmetric eigensolver.
 // CMA-ES matrices are N x N with N <= ~1024 and the GEMMs are <= 1 GFLOP, fp64 by
-// default (tcgen05 has no f64 kind), so these are CUDA-core DFMA/FFMA kernels.
+// default.  tcgen05.mma has no f64 kind, so the fp64 GEMMs run on the tensor cores through
+// mma.sync.m8n8k4.f64 (DMMA); the fp32 ones are CUDA-core FFMA kernels.
 #pragma once
 #include <cooperative_groups.h>
 
@@ -13,20 +14,99 @@ namespace sp {
 
 constexpr int kGemmTile = 64;  // output tile edge
 constexpr int kGemmK = 16;     // k-chunk
-// 256 threads, each owns a 4 x 4 block of the 64 x 64 tile.
+constexpr int kGemmLd = kGemmTile + 8;  // shared-memory row stride: 72 = 8 mod 32 keeps the mma fragment loads conflict-free
+
+// Inner product of one staged k-chunk, 256 threads, As[k][m] / Bs[k][n] in shared memory.
+//  * double: the fp64 tensor-core instruction mma.sync.m8n8k4.f64 (SASS DMMA; tcgen05.mma has
+//    no f64 kind).  8 warps as 2 (m) x 4 (n); a warp owns a 32 x 16 block = 4 x 2 mma tiles;
+//    fragments (PTX ISA, m8n8k4): A row = lane / 4, k = lane % 4; B k = lane % 4, col = lane / 4;
+//    C row = lane / 4, cols = 2 (lane % 4) + {0, 1}.  6 shared loads feed 8 DMMA = 2048 FMA.
+//  * float: CUDA-core FFMA, each thread a 4 x 4 block.
+template <typename T>
+struct GemmAcc;
+template <>
+struct GemmAcc<double> {
+  double c[4][2][2];
+  __device__ __forceinline__ void clear() {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 2; ++j) c[i][j][0] = c[i][j][1] = 0.0;
+  }
+  __device__ __forceinline__ void chunk(const double (*As)[kGemmLd], const double (*Bs)[kGemmLd]) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t4 = lane & 3;
+    const int wm = (warp & 1) * 32, wn = (warp >> 1) * 16;
+#pragma unroll
+    for (int kk = 0; kk < kGemmK; kk += 4) {
+      double a[4], b[2];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = As[kk + t4][wm + i * 8 + g];
+#pragma unroll
+      for (int j = 0; j < 2; ++j) b[j] = Bs[kk + t4][wn + j * 8 + g];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+          asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+                       : "+d"(c[i][j][0]), "+d"(c[i][j][1])
+                       : "d"(a[i]), "d"(b[j]));
+    }
+  }
+  template <typename F>
+  __device__ __forceinline__ void each(F f) const {  // f(m, n, value) with tile-local indices
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t4 = lane & 3;
+    const int wm = (warp & 1) * 32, wn = (warp >> 1) * 16;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 2; ++j)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) f(wm + i * 8 + g, wn + j * 8 + t4 * 2 + e, c[i][j][e]);
+  }
+};
+template <>
+struct GemmAcc<float> {
+  float c[4][4];
+  __device__ __forceinline__ void clear() {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) c[i][j] = 0.0f;
+  }
+  __device__ __forceinline__ void chunk(const float (*As)[kGemmLd], const float (*Bs)[kGemmLd]) {
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+#pragma unroll
+    for (int kk = 0; kk < kGemmK; ++kk) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = As[kk][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = Bs[kk][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) c[i][j] += a[i] * b[j];
+    }
+  }
+  template <typename F>
+  __device__ __forceinline__ void each(F f) const {
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) f(ty * 4 + i, tx * 4 + j, c[i][j]);
+  }
+};
 
 // C[m][n] = epi(sum_k A(m,k) * B(n,k))        ("NT": both operands k-contiguous)
 // LoadA / LoadB: functors (row, k) -> T (0 outside bounds handled here); Epi: (m, n, acc).
 template <typename T, typename LoadA, typename LoadB, typename Epi>
 __device__ __forceinline__ void gemm_nt_tile(int M, int Nn, int K, int m0, int n0, LoadA la, LoadB lb, Epi epi) {
-  __shared__ T As[kGemmK][kGemmTile + 4];
-  __shared__ T Bs[kGemmK][kGemmTile + 4];
-  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-  T acc[4][4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = T(0);
+  __shared__ T As[kGemmK][kGemmLd];
+  __shared__ T Bs[kGemmK][kGemmLd];
+  const int tid = threadIdx.x;
+  GemmAcc<T> acc;
+  acc.clear();
   for (int k0 = 0; k0 < K; k0 += kGemmK) {
     // 64 x 16 elements per operand, 4 per thread; k fastest so global reads are contiguous
 #pragma unroll
@@ -37,40 +117,23 @@ __device__ __forceinline__ void gemm_nt_tile(int M, int Nn, int K, int m0, int n
       Bs[kk][r] = (n < Nn && k < K) ? lb(n, k) : T(0);
     }
     __syncthreads();
-#pragma unroll
-    for (int kk = 0; kk < kGemmK; ++kk) {
-      T a[4], b[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) a[i] = As[kk][ty * 4 + i];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) b[j] = Bs[kk][tx * 4 + j];
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] += a[i] * b[j];
-    }
+    acc.chunk(As, Bs);
     __syncthreads();
   }
-#pragma unroll
-  for (int i = 0; i < 4; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int m = m0 + ty * 4 + i, n = n0 + tx * 4 + j;
-      if (m < M && n < Nn) epi(m, n, acc[i][j]);
-    }
+  acc.each([&](int i, int j, T v) {
+    const int m = m0 + i, n = n0 + j;
+    if (m < M && n < Nn) epi(m, n, v);
+  });
 }
 
 // C[r][c] = sum_i A(i, r) * B(i, c) over i in [i0, i1)   ("TN": reduction over rows)
 template <typename T, typename LoadA, typename LoadB, typename Epi>
 __device__ __forceinline__ void gemm_tn_tile(int R, int Cc, int i0, int i1, int r0, int c0, LoadA la, LoadB lb, Epi epi) {
-  __shared__ T As[kGemmK][kGemmTile + 4];
-  __shared__ T Bs[kGemmK][kGemmTile + 4];
-  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-  T acc[4][4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = T(0);
+  __shared__ T As[kGemmK][kGemmLd];
+  __shared__ T Bs[kGemmK][kGemmLd];
+  const int tid = threadIdx.x;
+  GemmAcc<T> acc;
+  acc.clear();
   for (int ib = i0; ib < i1; ib += kGemmK) {
 #pragma unroll
     for (int t = 0; t < 4; ++t) {
@@ -80,27 +143,13 @@ __device__ __forceinline__ void gemm_tn_tile(int R, int Cc, int i0, int i1, int 
       Bs[kk][cc] = (i < i1 && c0 + cc < Cc) ? lb(i, c0 + cc) : T(0);
     }
     __syncthreads();
-#pragma unroll
-    for (int kk = 0; kk < kGemmK; ++kk) {
-      T a[4], b[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) a[i] = As[kk][ty * 4 + i];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) b[j] = Bs[kk][tx * 4 + j];
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] += a[i] * b[j];
-    }
+    acc.chunk(As, Bs);
     __syncthreads();
   }
-#pragma unroll
-  for (int i = 0; i < 4; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int r = r0 + ty * 4 + i, c = c0 + tx * 4 + j;
-      if (r < R && c < Cc) epi(r, c, acc[i][j]);
-    }
+  acc.each([&](int i, int j, T v) {
+    const int r = r0 + i, c = c0 + j;
+    if (r < R && c < Cc) epi(r, c, v);
+  });
 }
 
 // ---- symmetric eigendecomposition: cyclic one-sided Jacobi on rows -----------------

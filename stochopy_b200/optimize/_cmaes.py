@@ -97,7 +97,7 @@ def minimize(
         raise ValueError()
     cons = _CONSTRAINTS[constraints]  # KeyError like _cmaes.py:177
 
-    eng = Engine(dtype, device)
+    eng = Engine(dtype, device, backend)
     bounds = np.asarray(bounds, dtype=np.float64)
     N, P = len(bounds), int(popsize)
     lower, upper = bounds[:, 0], bounds[:, 1]

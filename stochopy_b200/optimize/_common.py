@@ -63,8 +63,9 @@ def fresh_seed(seed):
 class Engine:
     """Device context of one optimiser run: device, dtype, stream, buffers."""
 
-    def __init__(self, dtype="float64", device=None):
+    def __init__(self, dtype="float64", device=None, backend=None):
         L.load()
+        self.backend = backend
         if not torch.cuda.is_available():
             raise L.EngineError("stochopy_b200 needs a CUDA device (no CPU fallback)")
         self.np_dt, self.t_dt, self.sp_dt = resolve_dtype(dtype)
@@ -158,7 +159,12 @@ class Engine:
         host = self.download_rows(X, p, n)
         if to_user is not None:
             host = to_user(host)
-        f = np.array([fun(row, *args) for row in host], dtype=np.float64)
+        if self.backend == "mpi":  # the reference's rank-strided evaluation, over torch.distributed
+            from ..parallel import evaluate_split
+
+            f = evaluate_split(fun, args, host)
+        else:
+            f = np.array([fun(row, *args) for row in host], dtype=np.float64)
         out[:p].copy_(torch.from_numpy(f.astype(self.np_dt)))
 
 

@@ -70,7 +70,7 @@ def minimize(
         raise ValueError()
     cons = _CONSTRAINTS[constraints]  # KeyError like _cpso.py:209
 
-    eng = Engine(dtype, device)
+    eng = Engine(dtype, device, backend)
     bounds = np.asarray(bounds, dtype=np.float64)
     N, P = len(bounds), int(popsize)
     lower, upper = bounds[:, 0].copy(), bounds[:, 1].copy()

@@ -52,7 +52,7 @@ def minimize(
     if rng not in {"philox", "numpy"}:
         raise ValueError()
 
-    eng = Engine(dtype, device)
+    eng = Engine(dtype, device, backend)
     bounds = np.asarray(bounds, dtype=np.float64)
     N, P = len(bounds), int(popsize)
     lower, upper = bounds[:, 0].copy(), bounds[:, 1].copy()

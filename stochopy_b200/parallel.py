@@ -23,7 +23,7 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
-__all__ = ["shard_range", "shard_seeds", "reduce_best", "minimize_seeds", "cpso_sharded", "PeerMailboxes"]
+__all__ = ["shard_range", "shard_seeds", "reduce_best", "minimize_seeds", "cpso_sharded", "PeerMailboxes", "evaluate_split"]
 
 
 def _all_gather_flat(out, part, group):
@@ -85,6 +85,29 @@ class PeerMailboxes:
             dist.barrier(group=self.group)
         self._L.call("sp_peer_free", C.c_void_p(self.own))
         self.own, self._opened = None, []
+
+
+def evaluate_split(fun, args, rows, group=None):
+    """The reference's ``backend="mpi"`` evaluation (``_common.py:58-72``: every rank holds
+    the population, evaluates the rows ``rank::size`` and an Allreduce(SUM) completes the
+    fitness vector) over ``torch.distributed`` -- for objectives that are expensive *on the
+    host* (SURVEY.md 8f-4).  All ranks run the same optimiser with the same seed, so the
+    population is already identical everywhere and nothing is broadcast; only the
+    per-generation fitness vector (P doubles) is reduced.  Without an initialised process
+    group this is the serial loop."""
+    rows = np.asarray(rows)
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    if world == 1:
+        return np.array([fun(r, *args) for r in rows], dtype=np.float64)
+    rank = dist.get_rank(group)
+    f = np.zeros(len(rows), dtype=np.float64)
+    f[rank::world] = [fun(r, *args) for r in rows[rank::world]]
+    on_gpu = dist.get_backend(group) == "nccl"
+    t = torch.from_numpy(f)
+    if on_gpu:
+        t = t.to(torch.device("cuda", torch.cuda.current_device()))
+    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return t.cpu().numpy()
 
 
 def shard_range(total, rank, world):

@@ -80,6 +80,60 @@ def test_minimize_seeds_gloo_world2(nseeds):
     assert sum(o[1][3] for o in out) == nseeds
 
 
+def _split_eval(rank, world, nrows):
+    rows = np.random.RandomState(4).uniform(-1, 1, (nrows, 3))
+    calls = []
+
+    def fun(x, shift):
+        calls.append(1)
+        return float(np.sum(x * x) + shift)
+
+    f = parallel.evaluate_split(fun, (0.5,), rows)
+    return f.tolist(), len(calls)
+
+
+@pytest.mark.parametrize("nrows", [1, 7, 10])
+def test_evaluate_split_gloo_world2(nrows):
+    """8f-4: rank-strided host evaluation + all-reduce (the reference's mpi backend)."""
+    rows = np.random.RandomState(4).uniform(-1, 1, (nrows, 3))
+    want = (rows * rows).sum(axis=1) + 0.5
+    out = _spawn(_split_eval, 2, nrows)
+    for rank, (f, ncalls) in out:
+        assert np.allclose(f, want) and ncalls == len(range(rank, nrows, 2))
+    assert np.allclose(parallel.evaluate_split(lambda x: float(x.sum()), (), rows), rows.sum(axis=1))  # no group: serial
+
+
+def _mpi_backend(rank, world, method):
+    import stochopy_b200 as sb
+
+    torch.cuda.set_device(0)
+    calls = []
+
+    def fun(x):
+        calls.append(1)
+        return float(np.sum((x - 0.3) ** 2))
+
+    r = sb.optimize.minimize(fun, [[-2.0, 2.0]] * 4, method=method,
+                             options=dict(maxiter=12, popsize=9, seed=2, backend="mpi", **({"updating": "deferred"} if method in ("de", "pso") else {})))
+    return r.x.tolist(), r.fun, r.nit, len(calls)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("method", ["de", "pso", "cmaes"])
+def test_mpi_backend_splits_host_evaluations(method):
+    import stochopy_b200 as sb
+
+    def fun(x):
+        return float(np.sum((x - 0.3) ** 2))
+
+    one = sb.optimize.minimize(fun, [[-2.0, 2.0]] * 4, method=method,
+                               options=dict(maxiter=12, popsize=9, seed=2, **({"updating": "deferred"} if method in ("de", "pso") else {})))
+    out = _spawn(_mpi_backend, 2, method)
+    for rank, (x, f, nit, ncalls) in out:
+        assert np.array_equal(np.array(x), one.x) and f == one.fun and nit == one.nit
+    assert sum(o[1][3] for o in out) == one.nfev and out[0][1][3] > out[1][1][3] > 0  # 5 + 4 rows per generation
+
+
 def _sharded(rank, world, opts):
     import stochopy_b200 as sb
 
