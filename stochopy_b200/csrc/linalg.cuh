@@ -682,7 +682,10 @@ inline cudaError_t jacobi_launch(T* C, int N, T* w, T* B, T* work, int warm, con
   }
   static const char* env_b = getenv("SP_EIGH_BLOCK");  // profiling switch: rows per block
   int b = 16;
-  while (b > 2 && N <= 8 * b) b >>= 1;  // aim at >= 8 block pairs (one per CTA) per outer round
+  // aim at 16 block pairs (one per CTA of a 16-CTA cluster) per outer round: fewer warps per SM
+  // shorten the latency-bound inner rounds (measured, N = 256 fp64 warm: b = 16 / 8 CTAs 2.23 ms,
+  // b = 8 / 16 CTAs 1.58 ms, b = 4 / 16 CTAs x 2 pairs 2.46 ms)
+  while (b > 2 && N <= 16 * b) b >>= 1;
   if (env_b != nullptr) b = atoi(env_b);
   if (b < 2) b = 2;
   if (b > 16) b = 16;
