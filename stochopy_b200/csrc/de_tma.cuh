@@ -71,7 +71,7 @@ constexpr int kPoolStages = 3;
 struct PoolLayout {
   uint32_t bars, queue, ir, don, best, fnew, ring, total;
 };
-__host__ __device__ inline PoolLayout pool_layout(int warps, int nb, int K, int64_t ld, size_t elem) {
+__host__ __device__ inline PoolLayout pool_layout(int warps, int nb, int K, int64_t ld, size_t elem, bool with_ring = true) {
   PoolLayout L;
   auto up16 = [](uint32_t v) { return (v + 15u) & ~15u; };
   uint32_t o = 16;  // [0,16): claim counter
@@ -89,13 +89,18 @@ __host__ __device__ inline PoolLayout pool_layout(int warps, int nb, int K, int6
   o = up16(o + (uint32_t)nb * (uint32_t)elem);
   o = (o + 127u) & ~127u;
   L.ring = o;
-  o += (uint32_t)warps * kPoolStages * (uint32_t)K * (uint32_t)ld * (uint32_t)elem;
+  if (with_ring) o += (uint32_t)warps * kPoolStages * (uint32_t)K * (uint32_t)ld * (uint32_t)elem;
   L.total = o;
   return L;
 }
 
 // PLAIN: no bound repair and not propose-only (the common case) -- those branches vanish.
-template <typename T, int CH, int STRAT, bool FULL, bool PLAIN>
+// RING: donor rows through the TMA ring (any shape); !RING: own row and donors prefetched one
+// row ahead with plain 16-byte loads into a second register set (CH == 1, K <= 3 only) -- the
+// ring costs ~45 warp instructions per row (mbarrier wait, elected-lane issue, uniform-register
+// traffic, queue) against ~10 for two address computations and loads, and with 32 warps per SM
+// one row of lookahead (~2000 cycles) already covers the L2 / HBM latency.
+template <typename T, int CH, int STRAT, bool FULL, bool PLAIN, bool RING>
 __global__ void __launch_bounds__(1024 / CH, 1)
 de_pool_kernel(const DeArgs<T> a, int nb, const PhiloxKeys keys) {
   using TL = Tile<T, CH, 32>;
@@ -108,7 +113,7 @@ de_pool_kernel(const DeArgs<T> a, int nb, const PhiloxKeys keys) {
   const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5, warps = blockDim.x >> 5;
   const int ld = FULL ? TL::COLS : (int)a.ld;
   const int N = FULL ? TL::COLS : a.N;
-  const PoolLayout L = pool_layout(warps, nb, K, ld, sizeof(T));
+  const PoolLayout L = pool_layout(warps, nb, K, ld, sizeof(T), RING);
   int* s_next = reinterpret_cast<int*>(smem_raw);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + L.bars) + wib * S;
   int* queue = reinterpret_cast<int*>(smem_raw + L.queue) + wib * S;
@@ -129,7 +134,7 @@ de_pool_kernel(const DeArgs<T> a, int nb, const PhiloxKeys keys) {
   // (an explicit cp.async.bulk.prefetch.L2 of the CTA's slice was measured slower when the L2 is
   // full of dirty lines: 38.3 vs 36.1 us per generation -- demand fetches are left alone)
   if (tid == 0) *s_next = 0;
-  if (lane == 0) {
+  if (RING && lane == 0) {
 #pragma unroll
     for (int s = 0; s < S; ++s) mbar_init(&bars[s], 1);
     mbar_fence_init();
@@ -172,10 +177,19 @@ de_pool_kernel(const DeArgs<T> a, int nb, const PhiloxKeys keys) {
 
   // ---- phase 1: claim / fetch / process ----------------------------------------------------
   const uint32_t s_next_addr = smem_u32(s_next);
-  auto claim = [&]() {  // raw atom.shared: one lane claims, no warp-aggregation preamble
+  auto claim = [&]() {  // one elected lane claims (elect.sync: ptxas then emits no warp-aggregation preamble)
     int r = 0;
-    if (lane == 0) asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(r) : "r"(s_next_addr) : "memory");
-    return __shfl_sync(0xffffffffu, r, 0);
+    uint32_t leader = 0;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "elect.sync %1|p, 0xffffffff;\n"
+        "@p atom.shared.add.u32 %0, [%2], 1;\n"
+        "}\n"
+        : "+r"(r), "+r"(leader)
+        : "r"(s_next_addr)
+        : "memory");
+    return __shfl_sync(0xffffffffu, r, leader);
   };
   auto issue = [&](int st, int r) {  // one elected lane fills stage `st` with the donors of row r
     if (lane == 0) {
@@ -187,61 +201,10 @@ de_pool_kernel(const DeArgs<T> a, int nb, const PhiloxKeys keys) {
       queue[st] = r;
     }
   };
-#pragma unroll
-  for (int st = 0; st < S; ++st) {
-    const int r = claim();
-    if (r < rows) issue(st, r);
-    else if (lane == 0) queue[st] = r;
-  }
-  __syncwarp();
-
-  // the individual's own row travels through registers, one row ahead (a row takes a warp
-  // a few thousand cycles on a full SM, which covers the HBM latency)
-  TL own;
-  if (queue[0] < rows) own.load(a.Xold + (b0 + queue[0]) * ld, lane, ld);
-
-  for (uint32_t n = 0;; ++n) {
-    const uint32_t st = n % S;
-    const int r = queue[st];
-    if (r >= rows) break;  // claims are monotonic: nothing further is in flight
-    TL xi = own;
-    {
-      const int rn = queue[(n + 1) % S];
-      if (rn < rows) own.load(a.Xold + (b0 + rn) * ld, lane, ld);
-    }
-    mbar_wait(&bars[st], (n / S) & 1u);
-    const T* sx = ring + (size_t)st * stage_elems;
-    auto lds = [&](TL& t, int slot) {
-#pragma unroll
-      for (int c = 0; c < CH; ++c) {
-        const int j0 = TL::col(c, lane, 0);
-        if (FULL || j0 < ld) {
-          V v = *reinterpret_cast<const V*>(sx + (size_t)slot * ld + j0);
-          const T* p = reinterpret_cast<const T*>(&v);
-#pragma unroll
-          for (int e = 0; e < VEC; ++e) t.v[c][e] = p[e];
-        } else {
-#pragma unroll
-          for (int e = 0; e < VEC; ++e) t.v[c][e] = T(0);
-        }
-      }
-    };
-    TL u;
-    {
-      RS cur;
-#pragma unroll
-      for (int k = 0; k < K; ++k) lds(cur.d[k], k);
-      mutant<T, CH, STRAT>(cur, gb, F, u);
-    }
+  // crossover, repair, objective, selection and store of one individual (u: mutant, xi: own row)
+  auto finish = [&](TL& u, const TL& xi, int r) {
     const int irand = tab_ir[r];
     const uint32_t row = (uint32_t)(b0 + r);
-    __syncwarp();  // every lane holds its part of the stage: hand it back and refill it
-    {
-      const int r2 = claim();
-      if (r2 < rows) issue(st, r2);
-      else if (lane == 0) queue[st] = r2;
-    }
-
     // binomial crossover (_de.py:339-344) and Random repair (de/_constraints.py:22-26)
 #pragma unroll
     for (int c = 0; c < CH; ++c) {
@@ -291,19 +254,101 @@ de_pool_kernel(const DeArgs<T> a, int nb, const PhiloxKeys keys) {
     T* out_row = a.Xnew + (int64_t)row * ld;
     if (!PLAIN && a.propose_only) {
       u.store(out_row, lane, ld);
-      continue;
+      return;
     }
     const T f = evaluate_tile<T, CH, 32>(a.objective, u, lane, N);
     const T old = s_best[r];
     const bool win = f < old;  // strict, _common.py:127
-#pragma unroll
-    for (int c = 0; c < CH; ++c)
-#pragma unroll
-      for (int e = 0; e < VEC; ++e) u.v[c][e] = win ? u.v[c][e] : xi.v[c][e];
-    u.store(out_row, lane, ld);
+    if (win) u.store(out_row, lane, ld);  // two predicated 16-byte stores instead of a select per scalar
+    else xi.store(out_row, lane, ld);
     if (lane == 0) {
       s_fnew[r] = f;
       if (win) s_best[r] = f;
+    }
+  };
+
+  if (RING) {
+  #pragma unroll
+    for (int st = 0; st < S; ++st) {
+      const int r = claim();
+      if (r < rows) issue(st, r);
+      else if (lane == 0) queue[st] = r;
+    }
+    __syncwarp();
+
+    // the individual's own row travels through registers, one row ahead (a row takes a warp
+    // a few thousand cycles on a full SM, which covers the HBM latency)
+    TL own;
+    if (queue[0] < rows) own.load(a.Xold + (b0 + queue[0]) * ld, lane, ld);
+
+    for (uint32_t n = 0;; ++n) {
+      const uint32_t st = n % S;
+      const int r = queue[st];
+      if (r >= rows) break;  // claims are monotonic: nothing further is in flight
+      TL xi = own;
+      {
+        const int rn = queue[(n + 1) % S];
+        if (rn < rows) own.load(a.Xold + (b0 + rn) * ld, lane, ld);
+      }
+      mbar_wait(&bars[st], (n / S) & 1u);
+      const T* sx = ring + (size_t)st * stage_elems;
+      auto lds = [&](TL& t, int slot) {
+  #pragma unroll
+        for (int c = 0; c < CH; ++c) {
+          const int j0 = TL::col(c, lane, 0);
+          if (FULL || j0 < ld) {
+            V v = *reinterpret_cast<const V*>(sx + (size_t)slot * ld + j0);
+            const T* p = reinterpret_cast<const T*>(&v);
+  #pragma unroll
+            for (int e = 0; e < VEC; ++e) t.v[c][e] = p[e];
+          } else {
+  #pragma unroll
+            for (int e = 0; e < VEC; ++e) t.v[c][e] = T(0);
+          }
+        }
+      };
+      TL u;
+      {
+        RS cur;
+  #pragma unroll
+        for (int k = 0; k < K; ++k) lds(cur.d[k], k);
+        mutant<T, CH, STRAT>(cur, gb, F, u);
+      }
+      __syncwarp();  // every lane holds its part of the stage: hand it back and refill it
+      {
+        const int r2 = claim();
+        if (r2 < rows) issue(st, r2);
+        else if (lane == 0) queue[st] = r2;
+      }
+
+      finish(u, xi, r);
+    }
+  } else {
+    // rows travel through registers: while row A is processed, row B (own + K donor rows) is in flight
+    RS A, B;
+    auto fetch = [&](RS& t, int r) {
+      t.x.load(a.Xold + (b0 + r) * ld, lane, ld);
+#pragma unroll
+      for (int k = 0; k < K; ++k) t.d[k].load(a.Xold + (int64_t)tab_d[k * nb + r] * ld, lane, ld);
+    };
+    int ra = claim();
+    if (ra < rows) fetch(A, ra);
+    while (ra < rows) {
+      int rb = claim();
+      if (rb < rows) fetch(B, rb);
+      {
+        TL u;
+        mutant<T, CH, STRAT>(A, gb, F, u);
+        finish(u, A.x, ra);
+      }
+      if (rb >= rows) break;
+      ra = claim();
+      if (ra < rows) fetch(A, ra);
+      {
+        TL u;
+        mutant<T, CH, STRAT>(B, gb, F, u);
+        finish(u, B.x, rb);
+      }
     }
   }
   if (!PLAIN && a.propose_only) return;
@@ -334,12 +379,12 @@ struct PoolShape {
   size_t smem;
 };
 template <int CH>
-inline bool pool_shape(int64_t P, int K, int64_t ld, size_t elem, PoolShape* ps) {
+inline bool pool_shape(int64_t P, int K, int64_t ld, size_t elem, PoolShape* ps, bool with_ring = true) {
   const int sms = sm_count();
   int64_t grid = P < sms ? P : sms;
   const int nb = (int)((P + grid - 1) / grid);
   for (int warps = 32 / CH; warps >= 1; warps >>= 1) {
-    const PoolLayout L = pool_layout(warps, nb, K, ld, elem);
+    const PoolLayout L = pool_layout(warps, nb, K, ld, elem, with_ring);
     if (L.total <= 220 * 1024) {
       *ps = {(int)grid, warps * 32, nb, L.total};
       return true;
@@ -348,11 +393,11 @@ inline bool pool_shape(int64_t P, int K, int64_t ld, size_t elem, PoolShape* ps)
   return false;
 }
 
-template <typename T, int CH, int STRAT, bool FULL, bool PLAIN>
-static cudaError_t de_pool_launch(const DeArgs<T>& a, cudaStream_t s) {
-  auto kern = de_pool_kernel<T, CH, STRAT, FULL, PLAIN>;
+template <typename T, int CH, int STRAT, bool FULL, bool PLAIN, bool RING>
+static cudaError_t de_pool_launch_v(const DeArgs<T>& a, cudaStream_t s) {
+  auto kern = de_pool_kernel<T, CH, STRAT, FULL, PLAIN, RING>;
   PoolShape ps;
-  if (!pool_shape<CH>(a.P, Strat<STRAT>::K, a.ld, sizeof(T), &ps)) return cudaErrorInvalidConfiguration;
+  if (!pool_shape<CH>(a.P, Strat<STRAT>::K, a.ld, sizeof(T), &ps, RING)) return cudaErrorInvalidConfiguration;
   static thread_local size_t configured[64];
   int dev = 0;
   cudaGetDevice(&dev);
@@ -373,6 +418,17 @@ static cudaError_t de_pool_launch(const DeArgs<T>& a, cudaStream_t s) {
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   return cudaLaunchKernelEx(&cfg, kern, a, ps.nb, philox_keys(a.seed));
+}
+
+// register-pipelined variant where two row sets fit the register budget, TMA ring otherwise
+// (SP_DE_RING=1 forces the ring: profiling switch)
+template <typename T, int CH, int STRAT, bool FULL, bool PLAIN>
+static cudaError_t de_pool_launch(const DeArgs<T>& a, cudaStream_t s) {
+  if constexpr (CH == 1 && Strat<STRAT>::K <= 3) {
+    static const bool force_ring = getenv("SP_DE_RING") != nullptr;
+    if (!force_ring) return de_pool_launch_v<T, CH, STRAT, FULL, PLAIN, false>(a, s);
+  }
+  return de_pool_launch_v<T, CH, STRAT, FULL, PLAIN, true>(a, s);
 }
 
 template <typename T, int CH, int STRAT>
