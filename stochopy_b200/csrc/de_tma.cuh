@@ -325,6 +325,8 @@ de_pool_kernel(const DeArgs<T> a, int nb, const PhiloxKeys keys) {
     }
   } else {
     // rows travel through registers: while row A is processed, row B (own + K donor rows) is in flight
+    // (measured: claiming two rows ahead and requesting the third row's lines with prefetch.global.L2
+    // is slower, HBM-cold 30.1 vs 28.4 us per generation -- one row of lookahead is left alone)
     RS A, B;
     auto fetch = [&](RS& t, int r) {
       t.x.load(a.Xold + (b0 + r) * ld, lane, ld);
