@@ -195,7 +195,12 @@ typedef struct {
   int32_t world, rank;
   void* mailbox;         /* this rank's own mailbox (device pointer) */
   void* const* peers;    /* DEVICE array [world]: rank r's mailbox as addressed from this process */
+  /* optional, sp_pso_chain_scalars(ld) scalars: lets sp_pso_run chain the generations of a plain
+   * PSO (gamma < 0, shard == 0) like sp_de_run does -- every CTA leaves its minimum and its best
+   * row here and the next launch resolves gbest / status in its prologue */
+  void* chain_rows;
 } sp_pso_state;
+int64_t sp_pso_chain_scalars(int64_t ld);
 int sp_pso_generation(const sp_pso_state* st, int it, void* stream);
 int sp_pso_propose(const sp_pso_state* st, int it, void* stream);
 /* competitive restart (_cpso.py:405-426), split so host-drawn positions can be

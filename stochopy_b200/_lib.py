@@ -71,7 +71,7 @@ class PsoState(C.Structure):
         ("lower", vp), ("upper", vp), ("ctrl", vp), ("scratch", vp),
         ("r1", vp), ("r2", vp),
         ("row0", C.c_int64), ("P_total", C.c_int64), ("xch", vp), ("shard", C.c_int32), ("pad2_", C.c_int32),
-        ("world", C.c_int32), ("rank", C.c_int32), ("mailbox", vp), ("peers", vp),
+        ("world", C.c_int32), ("rank", C.c_int32), ("mailbox", vp), ("peers", vp), ("chain_rows", vp),
     ]
 
 
@@ -148,6 +148,7 @@ SIGNATURES = {
     "sp_cpso_restart": (_i, [C.POINTER(PsoState), _i, vp, vp]),
     "sp_cpso_radius": (_i, [C.POINTER(PsoState), _i, vp]),
     "sp_cpso_decide": (_i, [C.POINTER(PsoState), _i, vp]),
+    "sp_pso_chain_scalars": (_i64, [_i64]),
     "sp_pso_run": (_i, [C.POINTER(PsoState), _i, _i, vp, vp]),
     "sp_peer_bytes": (_i64, [_i, _i, _i64, _i64]),
     "sp_peer_alloc": (_i, [_i64, C.POINTER(vp), vp]),

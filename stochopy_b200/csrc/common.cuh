@@ -5,6 +5,7 @@
 
 #include <atomic>
 #include <cstdio>
+#include <utility>
 
 #include "../../include/stochopy_b200.h"
 
@@ -36,6 +37,29 @@ int sm_count();
 constexpr int kThreads = 256;            // 8 warps per CTA
 constexpr int kMaxBlocks = 148 * 16;     // scratch is sized for this many per-CTA minima
 constexpr int kScratchBytes = kMaxBlocks * 16 + 256;
+
+// ---- programmatic dependent launch ---------------------------------------------------
+// A kernel launched with the programmatic-stream-serialization attribute may become resident
+// while its predecessor drains; it must not read what the predecessor wrote before pdl_wait().
+// Both are no-ops in a normally launched kernel.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, bool pdl,
+                              Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+}
 
 // ---- numeric traits ----------------------------------------------------------
 template <typename T> struct Num;
@@ -219,8 +243,50 @@ __device__ __forceinline__ bool grid_best(Best mine, Best* scratch, sp_ctrl* ctr
 // The serial tail (fence, atomic, scratch read, row read: ~9k cycles on one SM while
 // 147 idle) leaves the critical path; the scratch regions are disjoint from region 0,
 // which grid_best() uses.
-constexpr int kChainRegion = 512;  // records per region; regions 1 and 2 (parity)
+constexpr int kChainRegion = 768;  // records per region; regions 1 and 2 (parity): 3 x 768 <= kMaxBlocks
 __device__ __forceinline__ Best* chain_region(Best* scratch, int it) { return scratch + (1 + (it & 1)) * kChainRegion; }
+
+// block-level variant for grids of up to kChainRegion CTAs: best record and ITS INDEX (the CTA
+// that wrote it -- where that CTA left the winning row); valid in every thread after the call
+__device__ __forceinline__ Best chain_best_block(const Best* region, int n, int* index) {
+  __shared__ Best s_b[32];
+  __shared__ int s_i[32];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  Best b{1.0 / 0.0, 0x7fffffffffffffffLL};
+  int idx = 0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    Best o{__ldcg(&region[i].f), __ldcg(&region[i].row)};
+    if (better(o.f, o.row, b.f, b.row)) {
+      b = o;
+      idx = i;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double f = __shfl_xor_sync(0xffffffffu, b.f, o);
+    const long long r = __shfl_xor_sync(0xffffffffu, b.row, o);
+    const int i = __shfl_xor_sync(0xffffffffu, idx, o);
+    if (better(f, r, b.f, b.row)) {
+      b.f = f;
+      b.row = r;
+      idx = i;
+    }
+  }
+  if (lane == 0) {
+    s_b[warp] = b;
+    s_i[warp] = idx;
+  }
+  __syncthreads();
+  b = s_b[0];
+  idx = s_i[0];
+  for (int w = 1; w < nw; ++w)
+    if (better(s_b[w].f, s_b[w].row, b.f, b.row)) {
+      b = s_b[w];
+      idx = s_i[w];
+    }
+  *index = idx;
+  return b;
+}
 
 // warp-level read of the previous generation's per-CTA minima (valid in every lane)
 __device__ __forceinline__ Best chain_best(const Best* region, int n) {

@@ -33,6 +33,8 @@ struct PsoArgs {
   T* xch;                  // shard mode: [fit, x_0..x_{N-1}] of the local best for the exchange
   int shard;
   PeerArgs peer;           // shard == 2: exchange inside the kernel over the peer mailboxes
+  int chain;               // SP_CHAIN_IN / SP_CHAIN_OUT (plain PSO, whole swarm)
+  T* chain_rows;           // [2 parities][kChainRegion][ld]: the best row of every CTA
 };
 
 // shard == 2, last CTA of the generation kernel: local best -> every peer's mailbox (NVLink
@@ -70,17 +72,15 @@ __global__ void __launch_bounds__(kThreads)
 pso_generation_kernel(const PsoArgs<T> a, const PhiloxKeys keys) {
   using TL = Tile<T, CH, LPR>;
   constexpr int VEC = Num<T>::VEC;
+  pdl_wait();  // chained launches overlap their launch with the previous generation's drain
   if (!running(a.ctrl)) return;
+  pdl_launch_dependents();
   const int lane = threadIdx.x & 31, l = lane % LPR, sub = lane / LPR;
   const int64_t warp = (int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
   const int64_t nwarps = (int64_t)gridDim.x * (kThreads / 32);
   const int64_t groups = (a.P + TL::RPW - 1) / TL::RPW;
   const int ld = (int)a.ld;
 
-  TL gb;
-  gb.load(a.gbest, l, ld);
-
-  Best mine{1.0 / 0.0, 0x7fffffffffffffffLL};
   // software pipeline: the next row group's X, V, pbest are in flight while this one computes
   TL nx, nv, npb;
   auto fetch = [&](int64_t g) {
@@ -90,6 +90,30 @@ pso_generation_kernel(const PsoArgs<T> a, const PhiloxKeys keys) {
     nv.load(a.V + r * a.ld, l, ld);
     npb.load(a.pbest + r * a.ld, l, ld);
   };
+  bool have_first = false;
+  TL gb;
+  if (a.chain & SP_CHAIN_IN) {
+    if (warp < groups) {  // the first rows do not depend on gbest: their loads overlap the reduction below
+      fetch(warp);
+      have_first = true;
+    }
+    // chained generations (see common.cuh): reduce the previous launch's per-CTA minima here; the
+    // winning row was left by its CTA in chain_rows (pbest itself is updated in place below)
+    int idx;
+    const Best top = chain_best_block(chain_region(a.scratch, a.it - 1), (int)gridDim.x, &idx);
+    const T* win = a.chain_rows + ((size_t)((a.it - 1) & 1) * kChainRegion + idx) * a.ld;
+    if (blockIdx.x == 0 && (threadIdx.x >> 5) == (kThreads / 32) - 1) {  // one warp: gbest / dist / nit / status
+      Best rec{top.f, 0};
+      finalize_generation_warp<T>(rec, win, a.ld, a.N, a.gbest, a.ctrl, a.it - 1, a.maxiter, a.xtol, a.ftol);
+      if (lane == 0) a.ctrl->gbest_row = top.row;
+    }
+    if (chain_stops(top.f, a.it - 1, a.maxiter, a.ftol)) return;
+    gb.load(win, l, ld);
+  } else {
+    gb.load(a.gbest, l, ld);
+  }
+
+  Best mine{1.0 / 0.0, 0x7fffffffffffffffLL};
   // measured on B200 (C3, fp32 N=64): prefetching one group ahead costs 26 registers and a resident
   // CTA per SM and is slower (21.3 vs 17.0 us per generation) -- the state is L2 resident; keep it off
   constexpr bool kPrefetch = false;
@@ -99,7 +123,8 @@ pso_generation_kernel(const PsoArgs<T> a, const PhiloxKeys keys) {
     const bool live = row < a.P;
     if (!live) row = a.P - 1;
 
-    if (!kPrefetch) fetch(g);
+    if (!kPrefetch && !have_first) fetch(g);
+    have_first = false;
     TL x = nx, v = nv;
     {
       TL pb = npb;
@@ -178,6 +203,22 @@ pso_generation_kernel(const PsoArgs<T> a, const PhiloxKeys keys) {
     }
   }
   if (a.propose_only) return;
+  if (a.chain & SP_CHAIN_OUT) {  // leave the CTA's minimum and its row for the next launch's prologue
+    __shared__ Best s_red[32];
+    __shared__ long long s_row;
+    const Best b = block_best(mine, s_red);
+    if (threadIdx.x == 0) {
+      chain_region(a.scratch, a.it)[blockIdx.x] = b;
+      s_row = b.row;
+    }
+    __syncthreads();
+    if (s_row < a.P) {  // a CTA without rows keeps the +inf record
+      const T* src = a.pbest + s_row * a.ld;
+      T* dst = a.chain_rows + ((size_t)(a.it & 1) * kChainRegion + blockIdx.x) * a.ld;
+      for (int j = threadIdx.x; j < ld; j += blockDim.x) dst[j] = src[j];
+    }
+    return;
+  }
   Best top;
   if (grid_best(mine, a.scratch, a.ctrl, &top)) {
     if (a.shard == 2) {
@@ -328,8 +369,13 @@ static PeerArgs peer_args(const sp_pso_state* st) {
   return p;
 }
 
+static bool pso_chainable(const sp_pso_state* st) {
+  return st != nullptr && st->chain_rows != nullptr && st->shard == 0 && st->gamma < 0.0 && st->r1 == nullptr &&
+         st->objective >= SP_OBJ_ACKLEY && st->objective <= SP_OBJ_STYBLINSKI_TANG;
+}
+
 template <typename T>
-static int pso_launch(const sp_pso_state* st, int it, int propose_only, cudaStream_t s) {
+static int pso_launch(const sp_pso_state* st, int it, int propose_only, cudaStream_t s, int chain = 0) {
   Shape sh;
   if (!pick_shape(st->N, Num<T>::VEC, &sh)) {
     set_error("sp_pso_generation: ndim %d exceeds the compiled row shapes", st->N);
@@ -367,13 +413,17 @@ static int pso_launch(const sp_pso_state* st, int it, int propose_only, cudaStre
   a.xch = (T*)st->xch;
   a.shard = st->shard;
   a.peer = peer_args<T>(st);
+  a.chain = propose_only ? 0 : chain;
+  a.chain_rows = (T*)st->chain_rows;
   const bool philox = st->r1 == nullptr;
   const PhiloxKeys keys = philox_keys(st->seed);
-  const int grid = grid_for_rows(st->P, sh.lpr, sh.ch >= 4 ? 2 : 4);
-#define SP_CALL(TT, C, L)                                                         \
-  do {                                                                            \
-    if (philox) pso_generation_kernel<TT, C, L, true><<<grid, kThreads, 0, s>>>(a, keys); \
-    else pso_generation_kernel<TT, C, L, false><<<grid, kThreads, 0, s>>>(a, keys);     \
+  int grid = grid_for_rows(st->P, sh.lpr, sh.ch >= 4 ? 2 : 4);
+  if (a.chain != 0 && grid > kChainRegion) grid = kChainRegion;  // one record + row slot per CTA
+  const bool pdl = (a.chain & SP_CHAIN_IN) != 0;  // follows another generation kernel directly
+#define SP_CALL(TT, C, L)                                                                                          \
+  do {                                                                                                             \
+    if (philox) launch_pdl(pso_generation_kernel<TT, C, L, true>, dim3(grid), dim3(kThreads), 0, s, pdl, a, keys); \
+    else launch_pdl(pso_generation_kernel<TT, C, L, false>, dim3(grid), dim3(kThreads), 0, s, pdl, a, keys);       \
   } while (0)
   SP_DISPATCH_SHAPE(T, sh, SP_CALL);
 #undef SP_CALL
@@ -529,8 +579,21 @@ int sp_cpso_restart(const sp_pso_state* st, int it, int32_t* rank, void* stream)
   return sp_cpso_restart_apply(st, it, rank, nullptr, stream);
 }
 
+int64_t sp_pso_chain_scalars(int64_t ld) { return 2 * (int64_t)kChainRegion * ld; }
+
 int sp_pso_run(const sp_pso_state* st, int it_first, int n, int32_t* rank, void* stream) {
   SP_CHECK_ARG(st != nullptr && st->r1 == nullptr, "sp_pso_run needs in-kernel draws");
+  if (pso_chainable(st)) {  // plain PSO: only the last generation of the chunk runs the last-CTA epilogue
+    int rc = pso_check(st, it_first);
+    if (rc) return rc;
+    for (int g = 0; g < n; ++g) {
+      const int flags = (g > 0 ? SP_CHAIN_IN : 0) | (g < n - 1 ? SP_CHAIN_OUT : 0);
+      rc = st->dtype == SP_F32 ? pso_launch<float>(st, it_first + g, 0, (cudaStream_t)stream, flags)
+                               : pso_launch<double>(st, it_first + g, 0, (cudaStream_t)stream, flags);
+      if (rc) return rc;
+    }
+    return SP_OK;
+  }
   for (int g = 0; g < n; ++g) {
     int rc = sp_pso_generation(st, it_first + g, stream);
     if (rc) return rc;

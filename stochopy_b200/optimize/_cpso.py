@@ -86,6 +86,8 @@ def minimize(
     d_lower, d_upper = eng.upload_vec(lower, ld), eng.upload_vec(upper, ld)
     ctrl, scratch = eng.new_ctrl()
     rank = eng.zeros(P, dtype=torch.int32) if restart else None
+    # plain PSO: scratch that lets sp_pso_run chain its generations (no last-CTA tail per generation)
+    chain_rows = None if restart else eng.zeros(int(L.load().sp_pso_chain_scalars(ld)))
 
     st = L.PsoState()
     st.dtype, st.objective, st.constraint = eng.sp_dt, (obj if obj is not None else L.SP_OBJ_HOST), cons
@@ -93,6 +95,7 @@ def minimize(
     st.w, st.c1, st.c2 = float(inertia), float(cognitivity), float(sociability)
     st.xtol, st.ftol = float(xtol), float(ftol)
     st.gamma = float(gamma) if restart else -1.0
+    st.chain_rows = None if chain_rows is None else chain_rows.data_ptr()
     # swarm radius threshold, _cpso.py:216
     st.delta = float(np.log(1.0 + 0.003 * P) / np.max((0.2, np.log(0.01 * maxiter)))) if restart else 0.0
     st.seed = fresh_seed(seed)

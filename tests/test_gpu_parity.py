@@ -520,3 +520,21 @@ def test_return_all_streaming_equals_synchronous_history(method, opts, dtype):
         assert (a.nit, a.status) == (d.nit, d.status) and (ftol < 0) == (a.nit == 90)
         assert a.xall.shape == d.xall.shape == (a.nit, 20, 6) and a.funall.shape == (a.nit, 20)
         assert np.array_equal(a.xall, d.xall) and np.array_equal(a.funall, d.funall)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("N,P,cons,ftol,maxiter", [(64, 3001, None, 2.0e2, 300), (200, 777, "Shrink", -1.0, 23),
+                                                   (64, 5000, None, 1.0e9, 40)])
+def test_pso_chained_generations_equal_unchained(N, P, cons, ftol, maxiter, dtype):
+    """sp_pso_run chains the generations of a plain PSO (per-CTA minima + best rows left for the
+    next launch's prologue).  The callback path launches one unchained generation at a time:
+    same x / fun / nit / status, incl. stops by ftol inside a chunk, at once, and by maxiter."""
+    import stochopy_b200 as sb
+
+    b = [[-5.12, 5.12]] * N
+    o = dict(maxiter=maxiter, popsize=P, seed=4, dtype=dtype, constraints=cons, ftol=ftol, updating="deferred")
+    a = sb.optimize.minimize(sb.factory.sphere, b, method="pso", options=dict(o))
+    d = sb.optimize.minimize(sb.factory.sphere, b, method="pso", options=dict(o), callback=lambda X, s: None)
+    assert (a.nit, a.status, a.nfev) == (d.nit, d.status, d.nfev)
+    assert np.array_equal(a.x, d.x) and a.fun == d.fun
+    assert (ftol < 0) == (a.status == -1)
