@@ -218,6 +218,15 @@ int sp_cpso_radius(const sp_pso_state* st, int it, void* stream);
 int sp_cpso_decide(const sp_pso_state* st, int it, void* stream);
 /* enqueue generations it_first .. it_first+n-1 (+ restart when gamma >= 0) */
 int sp_pso_run(const sp_pso_state* st, int it_first, int n, int32_t* d_rank, void* stream);
+/* CPSO with the restart taken out of the common path: per generation only the generation
+ * kernel and a fused radius + decision kernel are enqueued.  When a restart fires
+ * (_cpso.py:405-426, rare while the swarm is wide) the decision kernel parks the run with
+ * ctrl.status = SP_STATUS_RESTART_PENDING (nit = the generation whose restart is due, ctrl.flag =
+ * nw) and the rest of the chunk returns at once; the host then calls sp_cpso_restart_resume
+ * (ranking, reset of the nw worst, status back to SP_RUNNING) and continues at nit + 1. */
+#define SP_STATUS_RESTART_PENDING (-901)
+int sp_pso_run_lazy(const sp_pso_state* st, int it_first, int n, void* stream);
+int sp_cpso_restart_resume(const sp_pso_state* st, int it, int32_t* d_rank, void* stream);
 
 /* ---- 8e: one swarm row-sharded over GPUs, exchange fused into the kernels ----------
  * Reference analogue: the mpi backend's Bcast / Allreduce around the population

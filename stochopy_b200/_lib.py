@@ -12,6 +12,7 @@ LIB_PATH = os.path.join(_HERE, "libstochopy_b200.so")
 
 SP_RUNNING = -1000
 SP_STATUS_PEER_TIMEOUT = -900
+SP_STATUS_RESTART_PENDING = -901
 PEER_HANDLE_BYTES = 64
 SP_F32, SP_F64 = 0, 1
 OBJECTIVES = {
@@ -149,6 +150,8 @@ SIGNATURES = {
     "sp_cpso_radius": (_i, [C.POINTER(PsoState), _i, vp]),
     "sp_cpso_decide": (_i, [C.POINTER(PsoState), _i, vp]),
     "sp_pso_chain_scalars": (_i64, [_i64]),
+    "sp_pso_run_lazy": (_i, [C.POINTER(PsoState), _i, _i, vp]),
+    "sp_cpso_restart_resume": (_i, [C.POINTER(PsoState), _i, vp, vp]),
     "sp_pso_run": (_i, [C.POINTER(PsoState), _i, _i, vp, vp]),
     "sp_peer_bytes": (_i64, [_i, _i, _i64, _i64]),
     "sp_peer_alloc": (_i, [_i64, C.POINTER(vp), vp]),

@@ -261,6 +261,82 @@ radius_kernel(const T* __restrict__ X, const T* __restrict__ gbest, int64_t P, i
   }
 }
 
+// (1)+(2) fused for the whole-swarm fast path: 16-byte loads, a lane group per row, the last CTA
+// to finish takes the decision (no second launch).  pause != 0: a restart that fires parks the
+// optimiser (status = SP_STATUS_RESTART_PENDING, every later kernel of the chunk returns at
+// once) so that the three gated restart kernels need not be enqueued after every generation;
+// the host then runs sp_cpso_restart_resume and continues with the next generation.
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+radius_plan_kernel(const T* __restrict__ X, const T* __restrict__ gbest, int64_t P, int N, int64_t ld, sp_ctrl* ctrl,
+                   int it, int maxiter, double gamma, double delta, int lpr, int pause) {
+  using V = typename Num<T>::vec_t;
+  constexpr int VEC = Num<T>::VEC;
+  pdl_wait();
+  if (!running(ctrl)) {  // terminated: no restart; parked: ctrl->flag still holds the nw of the pending restart
+    if (blockIdx.x == 0 && threadIdx.x == 0 && ctrl->status != SP_STATUS_RESTART_PENDING) ctrl->flag = 0;
+    return;
+  }
+  pdl_launch_dependents();
+  const int lane = threadIdx.x & 31, l = lane % lpr, sub = lane / lpr, rpw = 32 / lpr;
+  const int64_t warp = (int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * (kThreads / 32);
+  const int nvec = (int)(ld / VEC);
+  const int64_t groups = (P + rpw - 1) / rpw;
+  double worst = 0.0;
+  for (int64_t g = warp; g < groups; g += nwarps) {
+    const int64_t row = g * rpw + sub;
+    double acc = 0.0;
+    if (row < P) {
+      const V* xr = reinterpret_cast<const V*>(X + row * ld);
+      for (int j = l; j < nvec; j += lpr) {
+        const V a = xr[j], b = __ldg(reinterpret_cast<const V*>(gbest) + j);
+        const T* pa = reinterpret_cast<const T*>(&a);
+        const T* pb = reinterpret_cast<const T*>(&b);
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) {
+          const double d = (double)(T)(pa[e] - pb[e]);  // padding columns are zero in both
+          acc += d * d;
+        }
+      }
+    }
+    for (int o = lpr >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    worst = fmax(worst, acc);
+  }
+  for (int o = 16; o > 0; o >>= 1) worst = fmax(worst, __shfl_xor_sync(0xffffffffu, worst, o));
+  __shared__ double s_w[kThreads / 32];
+  __shared__ bool s_last;
+  if (lane == 0) s_w[threadIdx.x >> 5] = worst;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < kThreads / 32; ++w) worst = fmax(worst, s_w[w]);
+    atomicMax(reinterpret_cast<unsigned long long*>(&ctrl->aux[0]), (unsigned long long)__double_as_longlong(worst));
+    __threadfence();
+    s_last = atomicAdd(&ctrl->done_blocks, 1u) == gridDim.x - 1;
+    if (s_last) {
+      __threadfence();
+      const double m2 = __longlong_as_double((long long)__ldcg(reinterpret_cast<const unsigned long long*>(&ctrl->aux[0])));
+      const double radius = sqrt(m2) / sqrt(4.0 * (double)N);
+      int nw = 0;
+      if (radius < delta) {
+        const double inorm = (double)it / (double)maxiter;
+        nw = (int)(((double)P - 1.0) / (1.0 + exp(1.0 / 0.09 * (inorm - gamma + 0.5))));
+        if (nw < 0) nw = 0;
+      }
+      ctrl->flag = nw;
+      ctrl->aux[1] = radius;
+      ctrl->aux[0] = 0.0;
+      ctrl->done_blocks = 0;
+      if (pause && nw > 0) ctrl->status = SP_STATUS_RESTART_PENDING;
+    }
+  }
+}
+
+__global__ void restart_resume_kernel(sp_ctrl* ctrl) {
+  if (ctrl->status == SP_STATUS_RESTART_PENDING) ctrl->status = SP_RUNNING;
+  ctrl->flag = 0;
+}
+
 // (2) decision: radius < delta -> nw rows to reset (ctrl->flag), ctrl->aux[1] = radius
 __global__ void restart_plan_kernel(sp_ctrl* ctrl, int64_t P, int N, int it, int maxiter, double gamma, double delta) {  // P = whole swarm
   if (!running(ctrl)) {
@@ -375,7 +451,8 @@ static bool pso_chainable(const sp_pso_state* st) {
 }
 
 template <typename T>
-static int pso_launch(const sp_pso_state* st, int it, int propose_only, cudaStream_t s, int chain = 0) {
+static int pso_launch(const sp_pso_state* st, int it, int propose_only, cudaStream_t s, int chain = 0,
+                      bool after_kernel = false) {
   Shape sh;
   if (!pick_shape(st->N, Num<T>::VEC, &sh)) {
     set_error("sp_pso_generation: ndim %d exceeds the compiled row shapes", st->N);
@@ -419,7 +496,7 @@ static int pso_launch(const sp_pso_state* st, int it, int propose_only, cudaStre
   const PhiloxKeys keys = philox_keys(st->seed);
   int grid = grid_for_rows(st->P, sh.lpr, sh.ch >= 4 ? 2 : 4);
   if (a.chain != 0 && grid > kChainRegion) grid = kChainRegion;  // one record + row slot per CTA
-  const bool pdl = (a.chain & SP_CHAIN_IN) != 0;  // follows another generation kernel directly
+  const bool pdl = after_kernel || (a.chain & SP_CHAIN_IN) != 0;  // follows another kernel of the chain directly
 #define SP_CALL(TT, C, L)                                                                                          \
   do {                                                                                                             \
     if (philox) launch_pdl(pso_generation_kernel<TT, C, L, true>, dim3(grid), dim3(kThreads), 0, s, pdl, a, keys); \
@@ -513,6 +590,28 @@ extern "C" int sp_pso_run_sharded(const sp_pso_state* st, int it_first, int n, i
 }
 
 namespace sp {
+template <typename T>
+static int pso_run_lazy(const sp_pso_state* st, int it_first, int n, cudaStream_t s) {
+  const int vec = Num<T>::VEC;
+  int lpr = 1;
+  while (lpr < 32 && lpr * vec < st->ld) lpr <<= 1;
+  const int grid = grid_for_rows(st->P, lpr, 4);
+  for (int g = 0; g < n; ++g) {
+    const int it = it_first + g;
+    int rc = pso_launch<T>(st, it, 0, s, 0, g > 0);
+    if (rc) return rc;
+    cudaError_t e = launch_pdl(radius_plan_kernel<T>, dim3(grid), dim3(kThreads), 0, s, true, (const T*)st->X,
+                               (const T*)st->gbest, st->P, st->N, st->ld, st->ctrl, it, st->maxiter, st->gamma,
+                               st->delta, lpr, 1);
+    if (e != cudaSuccess) {
+      set_error("sp_pso_run_lazy: %s", cudaGetErrorString(e));
+      return SP_ERR_CUDA;
+    }
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+  }
+  return SP_OK;
+}
+
 }  // namespace sp
 
 using namespace sp;
@@ -580,6 +679,35 @@ int sp_cpso_restart(const sp_pso_state* st, int it, int32_t* rank, void* stream)
 }
 
 int64_t sp_pso_chain_scalars(int64_t ld) { return 2 * (int64_t)kChainRegion * ld; }
+
+int sp_pso_run_lazy(const sp_pso_state* st, int it_first, int n, void* stream) {
+  int rc = pso_check(st, it_first);
+  if (rc) return rc;
+  SP_CHECK_ARG(st->r1 == nullptr && st->shard == 0 && st->gamma >= 0.0 && st->lower && st->upper,
+               "whole swarm, in-kernel draws, competitivity and bounds");
+  SP_CHECK_ARG(st->objective >= SP_OBJ_ACKLEY && st->objective <= SP_OBJ_STYBLINSKI_TANG, "device objective required");
+  return st->dtype == SP_F32 ? pso_run_lazy<float>(st, it_first, n, (cudaStream_t)stream)
+                             : pso_run_lazy<double>(st, it_first, n, (cudaStream_t)stream);
+}
+
+int sp_cpso_restart_resume(const sp_pso_state* st, int it, int32_t* rank, void* stream) {
+  int rc = pso_check(st, it);
+  if (rc) return rc;
+  SP_CHECK_ARG(rank != nullptr && st->lower && st->upper && st->shard == 0, "rank scratch, bounds, whole swarm");
+  cudaStream_t s = (cudaStream_t)stream;
+  cudaError_t e = st->dtype == SP_F32 ? rank_launch<float>((const float*)st->pbestfit, st->P, rank, &st->ctrl->flag, s)
+                                      : rank_launch<double>((const double*)st->pbestfit, st->P, rank, &st->ctrl->flag, s);
+  if (e != cudaSuccess) {
+    set_error("sp_cpso_restart_resume: %s", cudaGetErrorString(e));
+    return SP_ERR_CUDA;
+  }
+  rc = st->dtype == SP_F32 ? restart_apply_launch<float>(st, it, rank, nullptr, s)
+                           : restart_apply_launch<double>(st, it, rank, nullptr, s);
+  if (rc) return rc;
+  restart_resume_kernel<<<1, 1, 0, s>>>(st->ctrl);
+  SP_CHECK_LAUNCH();
+  return SP_OK;
+}
 
 int sp_pso_run(const sp_pso_state* st, int it_first, int n, int32_t* rank, void* stream) {
   SP_CHECK_ARG(st != nullptr && st->r1 == nullptr, "sp_pso_run needs in-kernel draws");

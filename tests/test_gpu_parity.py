@@ -538,3 +538,21 @@ def test_pso_chained_generations_equal_unchained(N, P, cons, ftol, maxiter, dtyp
     assert (a.nit, a.status, a.nfev) == (d.nit, d.status, d.nfev)
     assert np.array_equal(a.x, d.x) and a.fun == d.fun
     assert (ftol < 0) == (a.status == -1)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("maxiter,P,N", [(30, 500, 10), (400, 300, 6), (150, 4000, 64)])
+def test_cpso_lazy_restart_equals_eager(maxiter, P, N, dtype):
+    """Fast path: sp_pso_run_lazy parks the run when a restart fires and the host resumes it
+    (sp_cpso_restart_resume), falling back to gated in-chunk restarts when they come in runs.
+    The callback path restarts eagerly after every generation.  maxiter=30 makes delta large
+    (restart every generation), 400 / 150 give runs with rare and clustered restarts."""
+    import stochopy_b200 as sb
+
+    b = [[-5.12, 5.12]] * N
+    o = dict(maxiter=maxiter, popsize=P, seed=8, dtype=dtype, competitivity=1.0, updating="deferred", xtol=-1.0,
+             ftol=-1.0e300)
+    a = sb.optimize.minimize(sb.factory.rastrigin, b, method="cpso", options=dict(o))
+    d = sb.optimize.minimize(sb.factory.rastrigin, b, method="cpso", options=dict(o), callback=lambda X, s: None)
+    assert (a.nit, a.status, a.nfev) == (d.nit, d.status, d.nfev) == (maxiter, -1, maxiter * P)
+    assert np.array_equal(a.x, d.x) and a.fun == d.fun
