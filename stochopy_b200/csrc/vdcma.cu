@@ -96,7 +96,8 @@ vd_inject_kernel(const VdPtrs<T> a) {
 // read-only loads per chunk, so a 1024-wide row costs ~40 registers and 3-4 CTAs fit an SM.
 // (y / D) . vn is taken from t = z + fac (z.vn) vn before the multiplication by D (y = D t)
 // instead of dividing y by D again (the reference divides, _vdcma.py:428: <= 1 ulp apart).
-template <typename T, int CH, int LPR>
+// FULL: ndim == CH * LPR * VEC == ld (no padding, no bounds predicates); CLIP: Penalize is on.
+template <typename T, int CH, int LPR, bool FULL, bool CLIP>
 __global__ void __launch_bounds__(kThreads, (CH * (int)sizeof(T) <= 32 ? 3 : 2))
 vd_sample_eval_kernel(const VdPtrs<T> a) {
   using TL = Tile<T, CH, LPR>;
@@ -108,15 +109,15 @@ vd_sample_eval_kernel(const VdPtrs<T> a) {
   const int64_t warp = (int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
   const int64_t nwarps = (int64_t)gridDim.x * (kThreads / 32);
   const int64_t groups = (a.P + TL::RPW - 1) / TL::RPW;
-  const int ld = (int)a.ld, N = a.N;
+  const int ld = FULL ? TL::COLS : (int)a.ld, N = FULL ? TL::COLS : a.N;
   const T sigma = (T)c->sigma;
   const T fac = (T)(sqrt(1.0 + c->aux[0]) - 1.0);
   const bool inject = c->inject != 0;
   if (blockIdx.x == 0 && threadIdx.x == 0) const_cast<sp_es_ctrl*>(c)->sigma_gen = c->sigma;
-  const bool clip = a.constraint == SP_CONS_PENALIZE;
+  constexpr bool clip = CLIP;
   auto vec = [&](const T* __restrict__ p, int cc, T (&o)[VEC]) {
     const int j0 = TL::col(cc, l, 0);
-    if (j0 < ld) {
+    if (FULL || j0 < ld) {
       const V t = __ldg(reinterpret_cast<const V*>(p + j0));
       const T* q = reinterpret_cast<const T*>(&t);
 #pragma unroll
@@ -139,9 +140,9 @@ vd_sample_eval_kernel(const VdPtrs<T> a) {
       for (int cc = 0; cc < CH; ++cc) {
         const int j0 = TL::col(cc, l, 0);
         T z[VEC];
-        if (j0 < N) normal_block(philox4x32((uint32_t)(j0 / VEC), (uint32_t)row, (uint32_t)a.it, kEsZ, a.seed), z);
+        if (FULL || j0 < N) normal_block(philox4x32((uint32_t)(j0 / VEC), (uint32_t)row, (uint32_t)a.it, kEsZ, a.seed), z);
 #pragma unroll
-        for (int e = 0; e < VEC; ++e) y.v[cc][e] = (j0 + e < N) ? z[e] : T(0);
+        for (int e = 0; e < VEC; ++e) y.v[cc][e] = (FULL || j0 + e < N) ? z[e] : T(0);
       }
     }
     T zv = 0;
@@ -166,7 +167,7 @@ vd_sample_eval_kernel(const VdPtrs<T> a) {
 #pragma unroll
         for (int e = 0; e < VEC; ++e) {
           y.v[cc][e] = row == 0 ? dy[e] : -dy[e];
-          if (TL::col(cc, l, e) < N) yv += div_rn(y.v[cc][e], dv[e]) * vn[e];
+          if (FULL || TL::col(cc, l, e) < N) yv += div_rn(y.v[cc][e], dv[e]) * vn[e];
         }
       } else {
 #pragma unroll
@@ -588,7 +589,20 @@ static int vd_sample(const sp_vd_state* st, int it, int evaluate, cudaStream_t s
     SP_CHECK_LAUNCH();
   }
   const int grid = grid_for_rows(st->P, sh.lpr, sh.ch * (int)sizeof(T) <= 32 ? 3 : 2);
-#define SP_CALL(TT, C, L) vd_sample_eval_kernel<TT, C, L><<<grid, kThreads, 0, s>>>(a)
+  // fixed-shape instantiations only for full-warp rows (the large-N case that matters)
+  const bool full = sh.lpr == 32 && st->N == sh.ch * 32 * Num<T>::VEC && st->ld == st->N;
+  const bool clip = st->constraint == SP_CONS_PENALIZE;
+#define SP_CALL(TT, C, L)                                                                         \
+  do {                                                                                            \
+    if (L == 32 && full) {                                                                        \
+      if (clip) vd_sample_eval_kernel<TT, C, (L == 32 ? 32 : 32), true, true><<<grid, kThreads, 0, s>>>(a);  \
+      else vd_sample_eval_kernel<TT, C, (L == 32 ? 32 : 32), true, false><<<grid, kThreads, 0, s>>>(a);      \
+    } else if (clip) {                                                                            \
+      vd_sample_eval_kernel<TT, C, L, false, true><<<grid, kThreads, 0, s>>>(a);                  \
+    } else {                                                                                      \
+      vd_sample_eval_kernel<TT, C, L, false, false><<<grid, kThreads, 0, s>>>(a);                 \
+    }                                                                                             \
+  } while (0)
   SP_DISPATCH_SHAPE(T, sh, SP_CALL);
 #undef SP_CALL
   SP_CHECK_LAUNCH();
