@@ -269,7 +269,8 @@ radius_kernel(const T* __restrict__ X, const T* __restrict__ gbest, int64_t P, i
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
 radius_plan_kernel(const T* __restrict__ X, const T* __restrict__ gbest, int64_t P, int N, int64_t ld, sp_ctrl* ctrl,
-                   int it, int maxiter, double gamma, double delta, int lpr, int pause) {
+                   int it, int maxiter, double gamma, double delta, int lpr, int pause, int64_t Ptot,
+                   const PeerArgs peer) {
   using V = typename Num<T>::vec_t;
   constexpr int VEC = Num<T>::VEC;
   pdl_wait();
@@ -313,23 +314,39 @@ radius_plan_kernel(const T* __restrict__ X, const T* __restrict__ gbest, int64_t
     atomicMax(reinterpret_cast<unsigned long long*>(&ctrl->aux[0]), (unsigned long long)__double_as_longlong(worst));
     __threadfence();
     s_last = atomicAdd(&ctrl->done_blocks, 1u) == gridDim.x - 1;
-    if (s_last) {
-      __threadfence();
-      const double m2 = __longlong_as_double((long long)__ldcg(reinterpret_cast<const unsigned long long*>(&ctrl->aux[0])));
-      const double radius = sqrt(m2) / sqrt(4.0 * (double)N);
-      int nw = 0;
-      if (radius < delta) {
-        const double inorm = (double)it / (double)maxiter;
-        nw = (int)(((double)P - 1.0) / (1.0 + exp(1.0 / 0.09 * (inorm - gamma + 0.5))));
-        if (nw < 0) nw = 0;
-      }
-      ctrl->flag = nw;
-      ctrl->aux[1] = radius;
-      ctrl->aux[0] = 0.0;
-      ctrl->done_blocks = 0;
-      if (pause && nw > 0) ctrl->status = SP_STATUS_RESTART_PENDING;
-    }
+    if (s_last) __threadfence();
   }
+  __syncthreads();
+  if (!s_last) return;
+  // last CTA: this rank's maximum is complete
+  double m2 = __longlong_as_double((long long)__ldcg(reinterpret_cast<const unsigned long long*>(&ctrl->aux[0])));
+  if (peer.world > 1) {  // sharded swarm: max-reduce over the ranks through the peer mailboxes
+    const int par = it & 1;
+    for (int r = threadIdx.x; r < peer.world; r += blockDim.x) *peer_rad(peer, r, par, peer.rank) = m2;
+    const bool ok = peer_exchange_flags(peer, kPeerRadius, par, (uint32_t)it);
+    if (threadIdx.x != 0) return;
+    if (!ok) {
+      ctrl->status = SP_STATUS_PEER_TIMEOUT;
+      ctrl->flag = 0;
+      ctrl->done_blocks = 0;
+      return;
+    }
+    m2 = 0.0;
+    for (int r = 0; r < peer.world; ++r) m2 = fmax(m2, ld_volatile(peer_rad(peer, peer.rank, par, r)));
+  }
+  if (threadIdx.x != 0) return;
+  const double radius = sqrt(m2) / sqrt(4.0 * (double)N);
+  int nw = 0;
+  if (radius < delta) {
+    const double inorm = (double)it / (double)maxiter;
+    nw = (int)(((double)Ptot - 1.0) / (1.0 + exp(1.0 / 0.09 * (inorm - gamma + 0.5))));
+    if (nw < 0) nw = 0;
+  }
+  ctrl->flag = nw;
+  ctrl->aux[1] = radius;
+  ctrl->aux[0] = 0.0;
+  ctrl->done_blocks = 0;
+  if (pause && nw > 0) ctrl->status = SP_STATUS_RESTART_PENDING;
 }
 
 __global__ void restart_resume_kernel(sp_ctrl* ctrl) {
@@ -392,7 +409,7 @@ template <typename T>
 __global__ void __launch_bounds__(1024)
 peer_gather_fit_kernel(const T* __restrict__ pbestfit, int64_t P, int64_t row0, sp_ctrl* ctrl, int it,
                        const PeerArgs p) {
-  if (!running(ctrl) || ctrl->flag <= 0) return;
+  if ((!running(ctrl) && ctrl->status != SP_STATUS_RESTART_PENDING) || ctrl->flag <= 0) return;
   for (int r = 0; r < p.world; ++r) {
     T* dst = peer_fit<T>(p, r) + row0;
     for (int64_t i = threadIdx.x; i < P; i += blockDim.x) dst[i] = pbestfit[i];
@@ -590,6 +607,27 @@ extern "C" int sp_pso_run_sharded(const sp_pso_state* st, int it_first, int n, i
 }
 
 namespace sp {
+// ranking + reset of a parked restart; sharded: all-gather the pbestfit shards over the mailboxes first
+template <typename T>
+static int restart_resume(const sp_pso_state* st, int it, int32_t* rank, cudaStream_t s) {
+  const T* fit = (const T*)st->pbestfit;
+  int64_t n = st->P;
+  const int32_t* mine = rank;
+  if (st->shard == 2) {
+    const PeerArgs p = peer_args<T>(st);
+    peer_gather_fit_kernel<T><<<1, 1024, 0, s>>>((const T*)st->pbestfit, st->P, st->row0, st->ctrl, it, p);
+    SP_CHECK_LAUNCH();
+    fit = reinterpret_cast<const T*>(static_cast<const unsigned char*>(st->mailbox) + p.L.fit);
+    n = st->P_total;
+    mine = rank + st->row0;
+  }
+  if (rank_launch<T>(fit, n, rank, &st->ctrl->flag, s) != cudaSuccess) {
+    set_error("sp_cpso_restart_resume: ranking failed");
+    return SP_ERR_CUDA;
+  }
+  return restart_apply_launch<T>(st, it, mine, nullptr, s);
+}
+
 template <typename T>
 static int pso_run_lazy(const sp_pso_state* st, int it_first, int n, cudaStream_t s) {
   const int vec = Num<T>::VEC;
@@ -602,7 +640,7 @@ static int pso_run_lazy(const sp_pso_state* st, int it_first, int n, cudaStream_
     if (rc) return rc;
     cudaError_t e = launch_pdl(radius_plan_kernel<T>, dim3(grid), dim3(kThreads), 0, s, true, (const T*)st->X,
                                (const T*)st->gbest, st->P, st->N, st->ld, st->ctrl, it, st->maxiter, st->gamma,
-                               st->delta, lpr, 1);
+                               st->delta, lpr, 1, st->shard ? st->P_total : st->P, peer_args<T>(st));
     if (e != cudaSuccess) {
       set_error("sp_pso_run_lazy: %s", cudaGetErrorString(e));
       return SP_ERR_CUDA;
@@ -683,8 +721,8 @@ int64_t sp_pso_chain_scalars(int64_t ld) { return 2 * (int64_t)kChainRegion * ld
 int sp_pso_run_lazy(const sp_pso_state* st, int it_first, int n, void* stream) {
   int rc = pso_check(st, it_first);
   if (rc) return rc;
-  SP_CHECK_ARG(st->r1 == nullptr && st->shard == 0 && st->gamma >= 0.0 && st->lower && st->upper,
-               "whole swarm, in-kernel draws, competitivity and bounds");
+  SP_CHECK_ARG(st->r1 == nullptr && (st->shard == 0 || st->shard == 2) && st->gamma >= 0.0 && st->lower && st->upper,
+               "whole swarm or peer-sharded swarm, in-kernel draws, competitivity and bounds");
   SP_CHECK_ARG(st->objective >= SP_OBJ_ACKLEY && st->objective <= SP_OBJ_STYBLINSKI_TANG, "device objective required");
   return st->dtype == SP_F32 ? pso_run_lazy<float>(st, it_first, n, (cudaStream_t)stream)
                              : pso_run_lazy<double>(st, it_first, n, (cudaStream_t)stream);
@@ -693,16 +731,10 @@ int sp_pso_run_lazy(const sp_pso_state* st, int it_first, int n, void* stream) {
 int sp_cpso_restart_resume(const sp_pso_state* st, int it, int32_t* rank, void* stream) {
   int rc = pso_check(st, it);
   if (rc) return rc;
-  SP_CHECK_ARG(rank != nullptr && st->lower && st->upper && st->shard == 0, "rank scratch, bounds, whole swarm");
+  SP_CHECK_ARG(rank != nullptr && st->lower && st->upper && (st->shard == 0 || st->shard == 2),
+               "rank scratch (P_total entries when sharded), bounds, whole or peer-sharded swarm");
   cudaStream_t s = (cudaStream_t)stream;
-  cudaError_t e = st->dtype == SP_F32 ? rank_launch<float>((const float*)st->pbestfit, st->P, rank, &st->ctrl->flag, s)
-                                      : rank_launch<double>((const double*)st->pbestfit, st->P, rank, &st->ctrl->flag, s);
-  if (e != cudaSuccess) {
-    set_error("sp_cpso_restart_resume: %s", cudaGetErrorString(e));
-    return SP_ERR_CUDA;
-  }
-  rc = st->dtype == SP_F32 ? restart_apply_launch<float>(st, it, rank, nullptr, s)
-                           : restart_apply_launch<double>(st, it, rank, nullptr, s);
+  rc = st->dtype == SP_F32 ? restart_resume<float>(st, it, rank, s) : restart_resume<double>(st, it, rank, s);
   if (rc) return rc;
   restart_resume_kernel<<<1, 1, 0, s>>>(st->ctrl);
   SP_CHECK_LAUNCH();
