@@ -5,6 +5,8 @@
 //
 // Per particle (row-local, in place): read X, V, pbest; write X, V and, on
 // improvement only, pbest.  Algorithmic HBM bytes per particle: 5 * N * s + 3 * s.
+#include <type_traits>
+
 #include "peer.cuh"
 #include "rows.cuh"
 
@@ -67,7 +69,9 @@ __device__ __forceinline__ void peer_best_exchange(const PsoArgs<T>& a, Best top
                                a.gbest, a.ctrl, a.it, a.maxiter, a.xtol, a.ftol);
 }
 
-template <typename T, int CH, int LPR, bool PHILOX>
+// CHAIN: compiled with the chained-generation prologue / epilogue (fp32 whole-swarm PSO); the
+// plain instantiation keeps the register footprint of the unchained kernel.
+template <typename T, int CH, int LPR, bool PHILOX, bool CHAIN>
 __global__ void __launch_bounds__(kThreads)
 pso_generation_kernel(const PsoArgs<T> a, const PhiloxKeys keys) {
   using TL = Tile<T, CH, LPR>;
@@ -92,7 +96,7 @@ pso_generation_kernel(const PsoArgs<T> a, const PhiloxKeys keys) {
   };
   bool have_first = false;
   TL gb;
-  if (a.chain & SP_CHAIN_IN) {
+  if (CHAIN && (a.chain & SP_CHAIN_IN)) {
     if (warp < groups) {  // the first rows do not depend on gbest: their loads overlap the reduction below
       fetch(warp);
       have_first = true;
@@ -123,7 +127,7 @@ pso_generation_kernel(const PsoArgs<T> a, const PhiloxKeys keys) {
     const bool live = row < a.P;
     if (!live) row = a.P - 1;
 
-    if (!kPrefetch && !have_first) fetch(g);
+    if (!kPrefetch && !(CHAIN && have_first)) fetch(g);
     have_first = false;
     TL x = nx, v = nv;
     {
@@ -203,7 +207,7 @@ pso_generation_kernel(const PsoArgs<T> a, const PhiloxKeys keys) {
     }
   }
   if (a.propose_only) return;
-  if (a.chain & SP_CHAIN_OUT) {  // leave the CTA's minimum and its row for the next launch's prologue
+  if (CHAIN && (a.chain & SP_CHAIN_OUT)) {  // leave the CTA's minimum and its row for the next launch's prologue
     __shared__ Best s_red[32];
     __shared__ long long s_row;
     const Best b = block_best(mine, s_red);
@@ -463,7 +467,10 @@ static PeerArgs peer_args(const sp_pso_state* st) {
 }
 
 static bool pso_chainable(const sp_pso_state* st) {
-  return st != nullptr && st->chain_rows != nullptr && st->shard == 0 && st->gamma < 0.0 && st->r1 == nullptr &&
+  // fp32 only: the fp64 kernel (76-80 registers, 3 CTAs per SM, two waves) measured slower chained
+  // (C3 fp64: 1.28e9 -> 1.15e9 evals/s), the fp32 one faster (1.83e9 -> 2.04e9)
+  return st != nullptr && st->dtype == SP_F32 && st->chain_rows != nullptr && st->shard == 0 && st->gamma < 0.0 &&
+         st->r1 == nullptr &&
          st->objective >= SP_OBJ_ACKLEY && st->objective <= SP_OBJ_STYBLINSKI_TANG;
 }
 
@@ -514,10 +521,15 @@ static int pso_launch(const sp_pso_state* st, int it, int propose_only, cudaStre
   int grid = grid_for_rows(st->P, sh.lpr, sh.ch >= 4 ? 2 : 4);
   if (a.chain != 0 && grid > kChainRegion) grid = kChainRegion;  // one record + row slot per CTA
   const bool pdl = after_kernel || (a.chain & SP_CHAIN_IN) != 0;  // follows another kernel of the chain directly
-#define SP_CALL(TT, C, L)                                                                                          \
-  do {                                                                                                             \
-    if (philox) launch_pdl(pso_generation_kernel<TT, C, L, true>, dim3(grid), dim3(kThreads), 0, s, pdl, a, keys); \
-    else launch_pdl(pso_generation_kernel<TT, C, L, false>, dim3(grid), dim3(kThreads), 0, s, pdl, a, keys);       \
+#define SP_CALL(TT, C, L)                                                                                    \
+  do {                                                                                                       \
+    if (a.chain != 0 && std::is_same<TT, float>::value)                                                      \
+      launch_pdl(pso_generation_kernel<float, C, L, true, true>, dim3(grid), dim3(kThreads), 0, s, pdl,      \
+                 reinterpret_cast<const PsoArgs<float>&>(a), keys);                                          \
+    else if (philox)                                                                                         \
+      launch_pdl(pso_generation_kernel<TT, C, L, true, false>, dim3(grid), dim3(kThreads), 0, s, pdl, a, keys);  \
+    else                                                                                                     \
+      launch_pdl(pso_generation_kernel<TT, C, L, false, false>, dim3(grid), dim3(kThreads), 0, s, pdl, a, keys); \
   } while (0)
   SP_DISPATCH_SHAPE(T, sh, SP_CALL);
 #undef SP_CALL

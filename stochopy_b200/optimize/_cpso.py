@@ -143,18 +143,20 @@ def minimize(
     streamer = HistoryStreamer.maybe(eng, hist, callback, P, N) if obj is not None and stream is None else None
     keep = None
     rank_ptr = rank.data_ptr() if restart else None
-    eager_left = 0
+    eager_left, last_restart = 0, -(1 << 30)
     while c.status == L.SP_RUNNING:
         if fast:
             n = min(64 if it < 64 else 256, last - it)
             if restart and eager_left <= 0:
-                # restart out of the common path: a firing restart parks the chunk, the host resumes it
-                L.call("sp_pso_run_lazy", C.byref(st), it + 1, n, eng.stream)
+                # restart out of the common path: a firing restart parks the chunk, the host resumes it.
+                # Chunks are short: what is enqueued behind a parked generation still drains as no-ops.
+                L.call("sp_pso_run_lazy", C.byref(st), it + 1, min(n, 32), eng.stream)
                 c = eng.read_ctrl(ctrl)
                 if c.status == L.SP_STATUS_RESTART_PENDING:
                     L.call("sp_cpso_restart_resume", C.byref(st), c.nit, rank_ptr, eng.stream)
-                    if c.nit - it < 4:  # restarts come in runs once the swarm has collapsed: gated kernels
-                        eager_left = 64  # inside the chunks are then cheaper than a host round trip each
+                    if c.nit - last_restart < 16:  # restarts come in runs once the swarm has collapsed: the
+                        eager_left = 64            # gated in-chunk kernels are then cheaper than parking
+                    last_restart = c.nit
                     c.status = L.SP_RUNNING
                 it = c.nit
                 continue

@@ -262,18 +262,19 @@ def cpso_sharded(fun, bounds, maxiter=100, popsize=10, inertia=0.7298, cognitivi
         st.shard, st.world, st.rank = 2, world, rank
         st.mailbox, st.peers = box.own, box.table.data_ptr()
         try:
-            eager_left = 0
+            eager_left, last_restart = 0, -(1 << 30)
             while c.status == L.SP_RUNNING:
                 n = min(32 if it < 64 else 128, max(int(maxiter), 2) - it)
                 if restart and eager_left <= 0:
                     # restart out of the common path (see optimize/_cpso.py): every rank parks at the same
                     # generation (the decision comes from the exchanged radius) and resumes collectively
-                    L.call("sp_pso_run_lazy", C.byref(st), it + 1, n, eng.stream)
+                    L.call("sp_pso_run_lazy", C.byref(st), it + 1, min(n, 32), eng.stream)
                     c = eng.read_ctrl(ctrl)
                     if c.status == L.SP_STATUS_RESTART_PENDING:
                         L.call("sp_cpso_restart_resume", C.byref(st), c.nit, rank_all.data_ptr(), eng.stream)
-                        if c.nit - it < 4:
+                        if c.nit - last_restart < 16:
                             eager_left = 64
+                        last_restart = c.nit
                         c.status = L.SP_RUNNING
                     it = c.nit
                     continue
