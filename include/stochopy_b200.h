@@ -285,11 +285,14 @@ int sp_fitness_rank(int dtype, const void* d_fit, int64_t P, int32_t* d_rank, vo
 /* ---- dense symmetric eigendecomposition (np.linalg.eigh, _cmaes.py:304) -------
  * d_C (N x N, ld = N) is symmetrised from its upper triangle in place
  * (_cmaes.py:303); eigenvalues ascending into d_w (N), eigenvectors into the
- * columns of d_B (N x N).  Cyclic one-sided Jacobi on the device; every
- * eigenvector is normalised so that its largest-magnitude component is positive
- * (LAPACK's sign is implementation defined).  One CTA with the problem in shared memory
- * when 2 N^2 scalars fit, otherwise a cooperative multi-CTA kernel (one pair per warp,
- * grid barriers between rounds).  d_work: sp_sym_eigh_work_scalars(N) scalars. */
+ * columns of d_B (N x N).  Cyclic one-sided Jacobi on the rows of W = Q0 C (Q0 = I or,
+ * warm, the eigenvectors already in d_B); for the positive semi-definite covariance the
+ * eigenpairs are lambda_j = |w_j|, q_j = w_j / |w_j| at convergence, so only W is rotated.
+ * Every eigenvector is normalised so that its largest-magnitude component is positive
+ * (LAPACK's sign is implementation defined).  N <= 64: one CTA, W in shared memory;
+ * larger N: block Jacobi in one thread-block cluster of up to 16 CTAs (block pairs in
+ * shared memory, hardware cluster barrier between outer rounds).
+ * d_work: sp_sym_eigh_work_scalars(N) scalars. */
 int64_t sp_sym_eigh_work_scalars(int N);
 /* warm != 0: d_B holds an approximate eigenbasis to start from (few sweeps when C moved
  * little).  d_sweeps (optional, device int32): number of Jacobi sweeps performed. */
