@@ -323,6 +323,8 @@ de_pool_kernel(const DeArgs<T> a, int nb, const PhiloxKeys keys) {
     }
   } else {
     // rows travel through registers: while row A is processed, row B (own + K donor rows) is in flight
+    // (measured: a compile-time objective -- no jump table in evaluate_tile -- makes ptxas spill at the
+    // 64-register cap and is slower, 34.6 vs 28.1 us HBM-cold; the run-time switch stays)
     // (measured: claiming two rows ahead and requesting the third row's lines with prefetch.global.L2
     // is slower, HBM-cold 30.1 vs 28.4 us per generation -- one row of lookahead is left alone)
     RS A, B;
