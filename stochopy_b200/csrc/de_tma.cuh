@@ -385,7 +385,10 @@ inline bool pool_shape(int64_t P, int K, int64_t ld, size_t elem, PoolShape* ps,
   const int sms = sm_count();
   int64_t grid = P < sms ? P : sms;
   const int nb = (int)((P + grid - 1) / grid);
-  for (int warps = 32 / CH; warps >= 1; warps >>= 1) {
+  static const char* env_w = getenv("SP_DE_WARPS");  // profiling switch: warps per CTA (<= 32 / CH)
+  int wmax = 32 / CH;
+  if (env_w != nullptr && atoi(env_w) >= 1 && atoi(env_w) < wmax) wmax = atoi(env_w);
+  for (int warps = wmax; warps >= 1; warps = warps > 1 && (warps & (warps - 1)) ? warps - 1 : warps >> 1) {
     const PoolLayout L = pool_layout(warps, nb, K, ld, elem, with_ring);
     if (L.total <= 220 * 1024) {
       *ps = {(int)grid, warps * 32, nb, L.total};
