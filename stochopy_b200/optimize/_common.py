@@ -285,12 +285,14 @@ class HistoryStreamer:
         if self.first is None:
             self.first = it
 
-    def finish(self, hist, nit):
-        """Wait for the copies and hand generations first..nit to the History arrays."""
+    def finish(self, hist, nit, transform=None):
+        """Wait for the copies and hand generations first..nit to the History arrays
+        (`transform`: host map applied to the float64 rows, e.g. un-standardisation)."""
         self.side.synchronize()
         if self.first is not None and nit >= self.first:
             a, b = self.first - 1, nit
-            hist.xall[a:b] = self.hX[a:b].numpy()
+            X = self.hX[a:b].numpy().astype(np.float64)
+            hist.xall[a:b] = X if transform is None else transform(X)
             hist.funall[a:b] = self.hF[a:b].numpy()
 
 

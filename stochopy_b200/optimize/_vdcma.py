@@ -14,7 +14,7 @@ import torch
 
 from .. import _lib as L
 from ._cmaes import EsHistory, selection_weights
-from ._common import Engine, NumpyStream, device_objective, fresh_seed, messages, validate_common
+from ._common import HistoryStreamer, Engine, NumpyStream, device_objective, fresh_seed, messages, validate_common
 from ._helpers import OptimizeResult, register
 
 __all__ = ["minimize"]
@@ -135,6 +135,7 @@ def minimize(
     valid_rows = (lambda r: np.clip(r, -1.0, 1.0)) if penal else (lambda r: r)
 
     fast = obj is not None and stream is None and not observe
+    streamer = HistoryStreamer.maybe(eng, hist, callback, P, N) if obj is not None and stream is None else None
     it = 0
     last = max(int(maxiter), 1)
     c = eng.read_ctrl(ctrl, L.EsCtrl)
@@ -142,6 +143,14 @@ def minimize(
         if fast:
             n = min(16 if it < 16 else 64, last - it)
             L.call("sp_vd_run", C.byref(st), it + 1, n, eng.stream)
+            c = eng.read_ctrl(ctrl, L.EsCtrl)
+            it = c.base.nit
+            continue
+        if streamer is not None:  # return_all: snapshots leave through a side stream, no per-generation sync
+            for _ in range(min(16, last - it)):
+                it += 1
+                L.call("sp_vd_generation", C.byref(st), it, eng.stream)
+                streamer.push(it, arx, arfit)
             c = eng.read_ctrl(ctrl, L.EsCtrl)
             it = c.base.nit
             continue
@@ -168,6 +177,8 @@ def minimize(
                 callback(Xh, res)
 
     it = c.base.nit
+    if streamer is not None:
+        streamer.finish(hist, it, transform=lambda X: unstd(valid_rows(X)))
     best = arx[c.base.gbest_row, :N].to("cpu").numpy().astype(np.float64)
     res = OptimizeResult(
         x=unstd(valid_rows(best)),

@@ -556,3 +556,22 @@ def test_cpso_lazy_restart_equals_eager(maxiter, P, N, dtype):
     d = sb.optimize.minimize(sb.factory.rastrigin, b, method="cpso", options=dict(o), callback=lambda X, s: None)
     assert (a.nit, a.status, a.nfev) == (d.nit, d.status, d.nfev) == (maxiter, -1, maxiter * P)
     assert np.array_equal(a.x, d.x) and a.fun == d.fun
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("method,opts", [("cmaes", {}), ("cmaes", dict(constraints="Penalize")), ("vdcma", {}),
+                                         ("vdcma", dict(constraints="Penalize"))])
+def test_return_all_streaming_es_methods(method, opts, dtype):
+    """CMA-ES / VD-CMA: the streamed history (standardised rows un-standardised and clipped on the
+    host at the end) equals the synchronous per-generation history."""
+    import stochopy_b200 as sb
+
+    b = [[-3.0, 5.0]] * 7
+    for ftol in (-1.0, 1.0e-3):
+        o = dict(opts, maxiter=60, popsize=16, seed=5, dtype=dtype, return_all=True, verbosity=0.5, ftol=ftol)
+        a = sb.optimize.minimize(sb.factory.sphere, b, method=method, options=dict(o))
+        d = sb.optimize.minimize(sb.factory.sphere, b, method=method, options=dict(o), callback=lambda X, s: None)
+        assert (a.nit, a.status) == (d.nit, d.status)
+        assert a.xall.shape == d.xall.shape == (a.nit, 8, 7)
+        assert np.array_equal(a.xall, d.xall) and np.array_equal(a.funall, d.funall)
+        assert np.array_equal(a.x, d.x) and a.fun == d.fun
