@@ -117,6 +117,21 @@ struct Tile {
       }
     }
   }
+  // streaming variant (st.global.cs, evict-first): for arrays larger than the L2 that are not re-read soon
+  __device__ __forceinline__ void store_cs(T* __restrict__ row, int l, int ld) const {
+    using V = typename Num<T>::vec_t;
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
+      int j0 = col(c, l, 0);
+      if (j0 < ld) {
+        V t;
+        T* p = reinterpret_cast<T*>(&t);
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) p[e] = v[c][e];
+        __stcs(reinterpret_cast<V*>(row + j0), t);
+      }
+    }
+  }
   __device__ __forceinline__ void store(T* __restrict__ row, int l, int ld) const {
     using V = typename Num<T>::vec_t;
 #pragma unroll

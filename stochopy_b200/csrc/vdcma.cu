@@ -9,6 +9,8 @@
 //   vd_update        mean, sigma (rank gap of rows 0/1), pc, natural gradient on (v, D), ladder,
 //                    then |v|^2, vn, diagC and the injection dy of the next generation   one CTA
 //   (vd_inject / vd_refresh stand alone only for host-provided draws and the first generation)
+#include <cstdlib>
+
 #include "es_common.cuh"
 
 namespace sp {
@@ -21,7 +23,7 @@ struct VdPtrs {
       *xshift, *besthist, *work, *bnd_weights, *dfithist;
   int32_t* rank;
   sp_es_ctrl* ctrl;
-  int N, mu, maxiter, ilim, hist_cap, constraint, objective, it, host_z, evaluate, chunks;
+  int N, mu, maxiter, ilim, hist_cap, constraint, objective, it, host_z, evaluate, chunks, stream_stores;
   int64_t P, ld;
   double cc, c1, cmu, mueff, wsum, xtol, ftol, insigma;
   uint64_t seed;
@@ -180,7 +182,8 @@ vd_sample_eval_kernel(const VdPtrs<T> a) {
     }
     yv = group_sum<LPR>(yv);
     if (live) {
-      y.store(a.ary + row * a.ld, l, ld);
+      if (a.stream_stores) y.store_cs(a.ary + row * a.ld, l, ld);
+      else y.store(a.ary + row * a.ld, l, ld);
       if (l == 0) a.yvn[row] = yv;
     }
 #pragma unroll
@@ -190,7 +193,10 @@ vd_sample_eval_kernel(const VdPtrs<T> a) {
 #pragma unroll
       for (int e = 0; e < VEC; ++e) y.v[cc][e] = add_rn(xm[e], mul_rn(sigma, y.v[cc][e]));
     }
-    if (live) y.store(a.arx + row * a.ld, l, ld);
+    if (live) {
+      if (a.stream_stores) y.store_cs(a.arx + row * a.ld, l, ld);
+      else y.store(a.arx + row * a.ld, l, ld);
+    }
     if (!a.evaluate) continue;
 #pragma unroll
     for (int cc = 0; cc < CH; ++cc) {
@@ -561,6 +567,10 @@ static VdPtrs<T> vd_ptrs(const sp_vd_state* st, int it, int evaluate) {
   a.it = it;
   a.host_z = st->host_z;
   a.evaluate = evaluate;
+  // y and x of a population larger than the L2 are stored evict-first (st.global.cs); SP_VD_PLAIN_STORES=1
+  // keeps normal stores (profiling switch)
+  static const bool plain_stores = getenv("SP_VD_PLAIN_STORES") != nullptr;
+  a.stream_stores = !plain_stores && 2 * (size_t)st->P * st->ld * sizeof(T) > ((size_t)96 << 20) ? 1 : 0;
   a.chunks = vd_chunks(st->P);
   a.P = st->P;
   a.ld = st->ld;
