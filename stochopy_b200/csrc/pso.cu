@@ -474,6 +474,14 @@ static bool pso_chainable(const sp_pso_state* st) {
          st->objective >= SP_OBJ_ACKLEY && st->objective <= SP_OBJ_STYBLINSKI_TANG;
 }
 
+// the chained instantiation exists for fp32 only (pso_chainable)
+template <int C, int L>
+static void launch_chained(const PsoArgs<float>& a, int grid, cudaStream_t s, bool pdl, const PhiloxKeys& keys) {
+  launch_pdl(pso_generation_kernel<float, C, L, true, true>, dim3(grid), dim3(kThreads), 0, s, pdl, a, keys);
+}
+template <int C, int L>
+static void launch_chained(const PsoArgs<double>&, int, cudaStream_t, bool, const PhiloxKeys&) {}
+
 template <typename T>
 static int pso_launch(const sp_pso_state* st, int it, int propose_only, cudaStream_t s, int chain = 0,
                       bool after_kernel = false) {
@@ -523,9 +531,8 @@ static int pso_launch(const sp_pso_state* st, int it, int propose_only, cudaStre
   const bool pdl = after_kernel || (a.chain & SP_CHAIN_IN) != 0;  // follows another kernel of the chain directly
 #define SP_CALL(TT, C, L)                                                                                    \
   do {                                                                                                       \
-    if (a.chain != 0 && std::is_same<TT, float>::value)                                                      \
-      launch_pdl(pso_generation_kernel<float, C, L, true, true>, dim3(grid), dim3(kThreads), 0, s, pdl,      \
-                 reinterpret_cast<const PsoArgs<float>&>(a), keys);                                          \
+    if (a.chain != 0)  /* pso_chainable(): fp32 only */                                                      \
+      launch_chained<C, L>(a, grid, s, pdl, keys);                                                           \
     else if (philox)                                                                                         \
       launch_pdl(pso_generation_kernel<TT, C, L, true, false>, dim3(grid), dim3(kThreads), 0, s, pdl, a, keys);  \
     else                                                                                                     \
