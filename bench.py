@@ -110,52 +110,41 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-# ---- reference arm / cpu baseline: the oracle port on host cores ---------------------
-def oracle_de_rate(p_sample, steps, warmup, seed=0):
-    """evals/s of the oracle's DE (reference algorithm, serial fun(x) loop) on a
-    population sample; steps timed after `warmup` generations via the callback."""
-    from oracle import de as ode
-    from oracle import objectives as oobj
+# ---- reference arm / cpu baseline: the reference's own DE on host cores ----------------
+def cpu_legs(steps, warmup, full):
+    """baseline/cpu_arm.py: the unmodified reference from baseline/_ref (oracle port only
+    when that install is missing), serial / loky / threading legs and the raw fun(x) loop."""
+    sys.path.insert(0, os.path.join(ROOT, "baseline"))
+    import cpu_arm
 
-    rs = np.random.RandomState(seed)
-    x0 = rs.uniform(-BOUND, BOUND, (p_sample, N))
-    stamps = []
-    ode.minimize(oobj.rosenbrock, [[-BOUND, BOUND]] * N, x0=x0, maxiter=steps + warmup + 1, popsize=p_sample,
-                 mutation=0.5, recombination=0.9, strategy="best1bin", seed=seed, xtol=-1.0, ftol=-1.0e300,
-                 updating="deferred", callback=lambda X, s: stamps.append(time.perf_counter()))
-    # stamps[0] = initial population; stamps[i] = end of generation i+1
-    t = stamps[-1] - stamps[-1 - steps]
-    return p_sample * steps / t, t / steps
+    return cpu_arm.run_legs(steps, warmup, full=full)
 
 
-def pick_sample(steps, warmup, budget_s):
-    """Largest population sample whose (steps+warmup) generations fit the time budget."""
-    rate, per = oracle_de_rate(256, 2, 1)
-    best = 256
-    for p in (512, 1024, 2048, 4096):
-        # reference cost per generation grows ~ p (evaluation) + p^2 (donor permutations)
-        est = per * (p / 256.0) * (1.0 + 0.35 * p / 1024.0)
-        if est * (steps + warmup + 1) <= budget_s:
-            best = p
-    return best
+def cpu_baseline_block(legs):
+    name, rate, per, cores, p_s, gens = legs["best"]
+    what = ("stochopy.optimize.minimize(rosenbrock, bounds, x0, method='de', options={updating: 'deferred', ...}) from "
+            "baseline/_ref (unmodified reference)") if legs["kind"] == "reference" else "oracle port of the reference DE"
+    return {
+        "value": rate, "unit": UNIT, "cores": cores, "kind": legs["kind"],
+        "sample": f"{what}; leg {name}: {p_s} of {P} rows x {gens} generations (the reference's (P-1)xP donor index "
+                  f"matrix is 34 GB at P={P}); fastest of the legs below",
+        "host_cpus": legs["host_cpus"], "cpu_model": legs["cpu_model"], "legs": legs["legs"]}
 
 
 def reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    p_s = pick_sample(args.steps, args.warmup, 150.0)
-    rate, per = oracle_de_rate(p_s, args.steps, args.warmup)
-    sample = (f"oracle port of the reference DE (serial fun(x) loop, numpy MT19937 draws incl. its per-individual "
-              f"donor permutations); population sample {p_s} of {P} rows x {args.steps} generations "
-              f"(reference cannot allocate its (P-1)xP donor matrix at P={P})")
+    legs = cpu_legs(args.steps, args.warmup, full=True)
+    name, rate, per, cores, p_s, gens = legs["best"]
     line = {
         "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": per * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"DE best1bin, Rosenbrock ndim={N}, popsize={P} (sampled at {p_s}), bounds +-{BOUND}",
-                   "popsize": P, "ndim": N, "sample_popsize": p_s},
-        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample},
+        "config": {"workload": f"DE best1bin, Rosenbrock ndim={N}, popsize={P} (reference timed at {p_s} rows: its donor "
+                               f"index matrix is O(P^2)), bounds +-{BOUND}",
+                   "popsize": P, "ndim": N, "sample_popsize": p_s, "leg": name},
+        "cpu_baseline": cpu_baseline_block(legs),
         "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -315,14 +304,7 @@ def our_arm(args):
             "clocks": clocks.summary(),
         }
         if world == 1 and not args.no_cpu:
-            p_s, gens = 4096, 24
-            t0 = time.perf_counter()
-            rate, per = oracle_de_rate(p_s, gens, 1)
-            line["cpu_baseline"] = {
-                "value": rate, "unit": UNIT, "cores": 1, "kind": "port",
-                "sample": f"oracle port of the reference DE on {p_s} of {P} rows x {gens} generations "
-                          f"({time.perf_counter() - t0:.1f} s); the reference's serial mode is its fastest (SURVEY.md 6)",
-                "host_cpus": os.cpu_count()}
+            line["cpu_baseline"] = cpu_baseline_block(cpu_legs(12, 1, full=False))
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
