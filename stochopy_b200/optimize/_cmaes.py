@@ -81,6 +81,7 @@ def minimize(
     device=None,
     rng="philox",
     eigh="device",
+    _probe=None,
 ):
     """CMA-ES on the GPU; arguments as stochopy.optimize.cmaes.minimize (_cmaes.py:12-30)."""
     validate_common(fun, bounds, None)
@@ -166,9 +167,9 @@ def minimize(
     def valid_rows(rows):  # arxvalid: the clipped population under Penalize (cmaes/_constraints.py:30-31)
         return np.clip(rows, -1.0, 1.0) if penal else rows
 
-    fast = obj is not None and stream is None and eigh == "device" and not observe
+    fast = obj is not None and stream is None and eigh == "device" and not observe and _probe is None
     streamer = (HistoryStreamer.maybe(eng, hist, callback, P, N)
-                if obj is not None and stream is None and eigh == "device" else None)
+                if obj is not None and stream is None and eigh == "device" and _probe is None else None)
     it = 0
     last = max(int(maxiter), 1)
     c = eng.read_ctrl(ctrl, L.EsCtrl)
@@ -212,6 +213,8 @@ def minimize(
                     bufs["D"].copy_(torch.from_numpy(vals[order].astype(eng.np_dt)))
                 L.call("sp_cma_finish_generation", C.byref(st), it, eng.stream)
         c = eng.read_ctrl(ctrl, L.EsCtrl)
+        if _probe is not None:  # test hook: device state after every generation (tests/test_gpu_sizes.py)
+            _probe(it, bufs, c)
         if observe:
             Xh = unstd(valid_rows(eng.download_rows(arx, P, N)))
             fh = arfit.to("cpu").numpy().astype(np.float64)

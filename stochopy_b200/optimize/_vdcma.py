@@ -43,6 +43,7 @@ def minimize(
     dtype="float64",
     device=None,
     rng="philox",
+    _probe=None,
 ):
     """VD-CMA on the GPU; arguments as stochopy.optimize.vdcma.minimize (_vdcma.py:13-31)."""
     validate_common(fun, bounds, None)
@@ -134,8 +135,8 @@ def minimize(
     arx, arfit = bufs["arx"], bufs["arfit"]
     valid_rows = (lambda r: np.clip(r, -1.0, 1.0)) if penal else (lambda r: r)
 
-    fast = obj is not None and stream is None and not observe
-    streamer = HistoryStreamer.maybe(eng, hist, callback, P, N) if obj is not None and stream is None else None
+    fast = obj is not None and stream is None and not observe and _probe is None
+    streamer = HistoryStreamer.maybe(eng, hist, callback, P, N) if obj is not None and stream is None and _probe is None else None
     it = 0
     last = max(int(maxiter), 1)
     c = eng.read_ctrl(ctrl, L.EsCtrl)
@@ -167,6 +168,8 @@ def minimize(
                          to_user=lambda X: unstd(valid_rows(X)), clip=penal)
             L.call("sp_vd_update", C.byref(st), it, eng.stream)
         c = eng.read_ctrl(ctrl, L.EsCtrl)
+        if _probe is not None:  # test hook: device state after every generation (tests/test_gpu_sizes.py)
+            _probe(it, bufs, c)
         if observe:
             Xh = unstd(valid_rows(eng.download_rows(arx, P, N)))
             fh = arfit.to("cpu").numpy().astype(np.float64)
