@@ -401,7 +401,8 @@ typedef struct {
   sp_es_ctrl* ctrl;
   void* scratch;
   int32_t host_z;
-  int32_t pad_;
+  int32_t lean;   /* 1: the caller never reads arx (device objective, in-kernel draws, no Penalize): the
+                   * sampling kernel stores y and the fitness only; x_i = xold + sigma_gen * y_i rebuilds a row */
 } sp_vd_state;
 int64_t sp_vd_work_scalars(int N, int64_t P);
 /* |v|^2, vn, diagC from (vvec, dvec): once after initialisation */

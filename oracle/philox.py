@@ -79,21 +79,23 @@ def uniform(rows, ncols, gen, purpose, seed, dtype):
 
 def normal(rows, ncols, gen, purpose, seed, dtype):
     """N(0,1) matrix by Box-Muller on the same blocks as ``uniform``.
-    fp32 block -> (r0 cos, r0 sin, r1 cos, r1 sin); fp64 block -> (r cos, r sin)."""
+    fp32 block -> (r0 cos, r0 sin, r1 cos, r1 sin); fp64 block -> (r cos, r sin).
+    The fp32 variant is evaluated in float64 and rounded once (the device uses the SFU
+    approximations; the stated tolerance of the comparison covers both)."""
     rows = np.asarray(rows, dtype=np.uint64)[:, None]
     if np.dtype(dtype) == np.float32:
+        # fp32 definition of csrc/philox.cuh::normal_block: 23-bit fractions k 2^-23 from the LOW bits of
+        # each word; radius from u = 1 - k 2^-23 in (0, 1], angle 2 pi t with t = k' 2^-23 - 0.5
         nb = _blocks(ncols, 4)
         o = philox4x32(np.arange(nb)[None, :], rows, gen, purpose, seed)
         f = np.float32
-        u = [((w >> np.uint64(8)).astype(f)) for w in o]
+        frac = [((w & np.uint64(0x7FFFFF)).astype(np.float64) * 2.0**-23) for w in o]
         out = np.empty((len(rows), nb, 4), dtype=f)
         for h in (0, 1):
-            u1 = (u[2 * h] + f(1.0)) * f(2.0**-24)
-            u2 = u[2 * h + 1] * f(2.0**-24)
-            r = np.sqrt(f(-2.0) * np.log(u1)).astype(f)
-            ang = (f(2.0) * u2).astype(f)
-            out[:, :, 2 * h] = r * np.cos(np.pi * ang.astype(np.float64)).astype(f)
-            out[:, :, 2 * h + 1] = r * np.sin(np.pi * ang.astype(np.float64)).astype(f)
+            r = np.sqrt(-2.0 * np.log1p(-frac[2 * h]))
+            t = frac[2 * h + 1] - 0.5
+            out[:, :, 2 * h] = (r * np.cos(2.0 * np.pi * t)).astype(f)
+            out[:, :, 2 * h + 1] = (r * np.sin(2.0 * np.pi * t)).astype(f)
         return out.reshape(len(rows), nb * 4)[:, :ncols]
     nb = _blocks(ncols, 2)
     o = philox4x32(np.arange(nb)[None, :], rows, gen, purpose, seed)

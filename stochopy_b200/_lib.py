@@ -118,7 +118,7 @@ class VdState(C.Structure):
         ("dy", vp), ("ginj", vp), ("arx", vp), ("ary", vp), ("yvn", vp), ("arfit", vp), ("weights", vp),
         ("xscale", vp), ("xshift", vp), ("besthist", vp), ("work", vp), ("rank", vp), ("bnd_weights", vp),
         ("dfithist", vp), ("ctrl", vp), ("scratch", vp),
-        ("host_z", C.c_int32), ("pad_", C.c_int32),
+        ("host_z", C.c_int32), ("lean", C.c_int32),
     ]
 
 

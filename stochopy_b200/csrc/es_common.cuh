@@ -84,7 +84,7 @@ template <typename T>
 __device__ void converge_ladder(sp_es_ctrl* c, int it, int N, int maxiter, int ilim, int64_t P, const T* xmean,
                                 const T* xold, const T* besthist, const T* arfit, const T* pc, const T* diagC,
                                 int diag_stride, const T* B, const T* D, double xtol, double ftol, double insigma,
-                                double* s_red) {
+                                double* s_red, const double* fit_range = nullptr) {
   const int tid = threadIdx.x;
   const double sigma = c->sigma;
   const double best = c->base.gfit;
@@ -107,9 +107,14 @@ __device__ void converge_ladder(sp_es_ctrl* c, int it, int N, int maxiter, int i
       dmax = fmax(dmax, (double)D[n]);
     }
   }
-  for (int64_t i = tid; i < P; i += blockDim.x) {
-    fmin_ = fmin(fmin_, (double)arfit[i]);
-    fmax_ = fmax(fmax_, (double)arfit[i]);
+  if (fit_range != nullptr) {  // this thread's share of min / max arfit was scanned by the caller
+    fmin_ = fit_range[0];
+    fmax_ = fit_range[1];
+  } else {
+    for (int64_t i = tid; i < P; i += blockDim.x) {
+      fmin_ = fmin(fmin_, (double)arfit[i]);
+      fmax_ = fmax(fmax_, (double)arfit[i]);
+    }
   }
   for (int i = tid; i < maxiter; i += blockDim.x) {  // zero padded history, all of it (_cmaes.py:424-427)
     hmin = fmin(hmin, (double)besthist[i]);

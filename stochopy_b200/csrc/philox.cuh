@@ -88,38 +88,35 @@ __device__ __forceinline__ void uniform_block(uint4 o, double (&u)[2]) {
   u[1] = __ull2double_rn(b) * 1.1102230246251565e-16;
 }
 
-// N(0,1) by Box-Muller on the same block.  fp32 uses the SFU (lg2 / sqrt / sin / cos
-// approximations, abs error ~2^-21 on reduced arguments): -ln u1 switches to the series of
-// -ln(1 - x) for u1 > 1 - 2^-6 (1 - u1 is exact there) so small radii keep their relative
-// accuracy, and the angle 2 pi u2 is centred on [-pi, pi) before sin/cos.
-// |z - exact| <= 4e-6 + 2e-6 |z| (tests/test_gpu_es.py::test_normal_draws_match_oracle).
-__device__ __forceinline__ float neg_log_u(float u) {  // -ln(u), u in (0, 1]
-  const float x = 1.0f - u;
-  const float series = x + x * x * (0.5f + x * (0.33333334f + 0.25f * x));
-  return x < 0.015625f ? series : -0.69314718f * __log2f(u);
-}
+// N(0,1) by Box-Muller on the same block.  fp32 (definition mirrored by oracle/philox.py::normal):
+// every word gives a 23-bit fraction f = as_float(0x3f800000 | (w & 0x7fffff)) in [1, 2) with ONE
+// logic instruction (no integer->float conversion: those share the 16-lane XU pipe with the MUFUs);
+//   radius   u = 2 - f in (0, 1],  x = f - 1 = 1 - u (both exact),  r = sqrt(-2 ln u)
+//   angle    t = f' - 1.5 in [-0.5, 0.5),  (z0, z1) = r (cos 2 pi t, sin 2 pi t)
+// with the SFU lg2 / sqrt / sin / cos approximations (abs error ~2^-21 on reduced arguments);
+// -2 ln u switches to the series of -2 ln(1 - x) for x < 2^-6 so small radii keep their relative
+// accuracy.  |z - exact| <= 4e-6 + 2e-6 |z| (tests/test_gpu_es.py::test_normal_draws_match_oracle).
 __device__ __forceinline__ float fast_sqrt(float x) {
   float r;
   asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
   return r;
 }
-__device__ __forceinline__ void fast_sincos_2pi(float u, float* sn, float* cs) {  // u in [0, 1)
-  const float a = 6.2831855f * (u - (u >= 0.5f ? 1.0f : 0.0f));  // same angle mod 2 pi, in [-pi, pi)
-  *sn = __sinf(a);
-  *cs = __cosf(a);
+__device__ __forceinline__ float unit_fraction(uint32_t w) { return __uint_as_float(0x3f800000u | (w & 0x007fffffu)); }
+__device__ __forceinline__ float radius_from(uint32_t w) {  // sqrt(-2 ln u), u = 2 - f
+  const float f = unit_fraction(w), x = f - 1.0f;
+  const float series = x * (2.0f + x * (1.0f + x * (0.66666669f + 0.5f * x)));
+  const float viaLog = -1.3862944f * __log2f(2.0f - f);
+  return fast_sqrt(x < 0.015625f ? series : viaLog);
+}
+__device__ __forceinline__ void normal_pair(uint32_t wr, uint32_t wa, float* z0, float* z1) {
+  const float r = radius_from(wr);
+  const float a = 6.2831855f * (unit_fraction(wa) - 1.5f);  // [-pi, pi)
+  *z0 = r * __cosf(a);
+  *z1 = r * __sinf(a);
 }
 __device__ __forceinline__ void normal_block(uint4 o, float (&z)[4]) {
-  const float s = 5.9604644775390625e-08f;
-  float u1 = (__uint2float_rn(o.x >> 8) + 1.0f) * s, u2 = __uint2float_rn(o.y >> 8) * s;
-  float u3 = (__uint2float_rn(o.z >> 8) + 1.0f) * s, u4 = __uint2float_rn(o.w >> 8) * s;
-  float r0 = fast_sqrt(2.0f * neg_log_u(u1)), r1 = fast_sqrt(2.0f * neg_log_u(u3));
-  float sn, cs;
-  fast_sincos_2pi(u2, &sn, &cs);
-  z[0] = r0 * cs;
-  z[1] = r0 * sn;
-  fast_sincos_2pi(u4, &sn, &cs);
-  z[2] = r1 * cs;
-  z[3] = r1 * sn;
+  normal_pair(o.x, o.y, &z[0], &z[1]);
+  normal_pair(o.z, o.w, &z[2], &z[3]);
 }
 __device__ __forceinline__ void normal_block(uint4 o, double (&z)[2]) {
   unsigned long long a = ((unsigned long long)o.x << 21) | (o.y >> 11);

@@ -5,9 +5,10 @@
 //   vd_sample_eval   z -> y -> x, (y/d).vn, objective               row tiles, HBM: write 2 rows
 //   [Penalize]       rank -> percentiles -> weights -> arfit += penalty
 //   rank             chunk sort + merge (rank.cuh)
-//   vd_wsum/wreduce  S_x, S_y, P_mu, Q_mu over the mu best           column-parallel, read mu rows of y
-//   vd_update        mean, sigma (rank gap of rows 0/1), pc, natural gradient on (v, D), ladder,
-//                    then |v|^2, vn, diagC and the injection dy of the next generation   one CTA
+//   vd_wsum          S_x, S_y, P_mu, Q_mu over the mu best           column-parallel, read mu rows of y
+//   vd_update        chunk partials -> sums (all CTAs), then in the last CTA: mean, sigma (rank gap of rows
+//                    0/1), pc, natural gradient on (v, D), ladder, |v|^2, vn, diagC, fused sampling
+//                    constants and the injection dy of the next generation
 //   (vd_inject / vd_refresh stand alone only for host-provided draws and the first generation)
 #include <cstdlib>
 
@@ -23,7 +24,7 @@ struct VdPtrs {
       *xshift, *besthist, *work, *bnd_weights, *dfithist;
   int32_t* rank;
   sp_es_ctrl* ctrl;
-  int N, mu, maxiter, ilim, hist_cap, constraint, objective, it, host_z, evaluate, chunks, stream_stores;
+  int N, mu, maxiter, ilim, hist_cap, constraint, objective, it, host_z, evaluate, chunks, stream_stores, lean;
   int64_t P, ld;
   double cc, c1, cmu, mueff, wsum, xtol, ftol, insigma;
   uint64_t seed;
@@ -32,6 +33,11 @@ struct VdPtrs {
   __host__ __device__ T* tmp() const { return coef() + N; }                           // 8 * N
   __host__ __device__ T* sorted() const { return tmp() + 8 * (size_t)N; }             // P
   __host__ __device__ T* sums() const { return sorted() + P; }                        // 4 * N reduced partials
+  // fused per-column constants of the lean sampling kernel (vd_refresh_body): the objective sees
+  //   (xmean + sigma D t) xscale + xshift = t * fuse_a + fuse_b,  fuse_a = sigma D xscale, fuse_b = xmean xscale + xshift
+  __host__ __device__ T* fuse_a() const { return sums() + 4 * (size_t)N; }            // N + 4
+  __host__ __device__ T* fuse_b() const { return fuse_a() + N + 4; }                  // N + 4
+  __host__ __device__ T* hpart() const { return fuse_b() + N + 4; }                   // kVdChunks (vd_wsum's scalar partials)
 };
 
 // ctrl->aux: [0] |v|^2, [1] |v|
@@ -45,6 +51,9 @@ __device__ void vd_refresh_body(const VdPtrs<T>& a, double* s_red) {
     const T v = a.vvec[n], d = a.dvec[n];
     a.vn[n] = div_rn(v, (T)nv);
     a.diagC[n] = mul_rn(mul_rn(d, add_rn(T(1), mul_rn(v, v))), d);  // _vdcma.py:251-256
+    const T sc = a.xscale[n];
+    a.fuse_a()[n] = ((T)c->sigma * d) * sc;
+    a.fuse_b()[n] = a.xmean[n] * sc + a.xshift[n];
   }
   if (threadIdx.x == 0) {
     c->aux[0] = nv2;
@@ -93,31 +102,53 @@ vd_inject_kernel(const VdPtrs<T> a) {
   vd_inject_body<T>(a, a.it, c->aux[0], s_red);
 }
 
-// row-local sampling + objective, _vdcma.py:239-277.  One register tile per row (z, then y,
-// then x in place); the N-vectors (vn, D, mean, scale, shift) are re-read from L1 as 16-byte
-// read-only loads per chunk, so a 1024-wide row costs ~40 registers and 3-4 CTAs fit an SM.
-// (y / D) . vn is taken from t = z + fac (z.vn) vn before the multiplication by D (y = D t)
-// instead of dividing y by D again (the reference divides, _vdcma.py:428: <= 1 ulp apart).
-// FULL: ndim == CH * LPR * VEC == ld (no padding, no bounds predicates); CLIP: Penalize is on.
+// row-local sampling + objective, _vdcma.py:239-277.  One register tile per row (z, then the
+// un-standardised x in place); the four N-vectors of the inner loop -- vn, D and the fused
+// constants fuse_a = sigma D xscale, fuse_b = xmean xscale + xshift that vd_refresh_body prepared --
+// are staged once per CTA in shared memory, so an element costs three fused multiply-adds and a product
+//   t = z + (fac z.vn) vn,   (y/D).vn += t vn,   y = D t,   x_user = t fuse_a + fuse_b
+// ((y/D).vn is taken from t before the multiplication by D instead of dividing y by D again as the
+// reference does, _vdcma.py:428; all of it within 2 ulp of numpy's operation order).
+// a.lean (device-resident loop: in-kernel draws, device objective, nobody reads arx): only y, (y/D).vn
+// and the fitness are written -- x_i = xold + sigma_gen y_i rebuilds a row when one is wanted (vd_wsum
+// does, and the front-end for the result); otherwise arx = xmean + sigma y is stored too.
+// FULL: ndim == CH * LPR * VEC == ld (no padding, no bounds predicates); CLIP: Penalize is on (the
+// objective then sees clip(xmean + sigma y, -1, 1) xscale + xshift, cmaes/_constraints.py:30-32).
 template <typename T, int CH, int LPR, bool FULL, bool CLIP>
 __global__ void __launch_bounds__(kThreads, (CH * (int)sizeof(T) <= 32 ? 3 : 2))
 vd_sample_eval_kernel(const VdPtrs<T> a) {
   using TL = Tile<T, CH, LPR>;
   using V = typename Num<T>::vec_t;
   constexpr int VEC = Num<T>::VEC;
+  constexpr int COLS = TL::COLS;
+  __shared__ __align__(16) T s_vn[COLS], s_dv[COLS], s_fa[COLS], s_fb[COLS];
   const sp_es_ctrl* c = a.ctrl;
   if (!es_running(c)) return;
   const int lane = threadIdx.x & 31, l = lane % LPR, sub = lane / LPR;
   const int64_t warp = (int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
   const int64_t nwarps = (int64_t)gridDim.x * (kThreads / 32);
   const int64_t groups = (a.P + TL::RPW - 1) / TL::RPW;
-  const int ld = FULL ? TL::COLS : (int)a.ld, N = FULL ? TL::COLS : a.N;
+  const int ld = FULL ? COLS : (int)a.ld, N = FULL ? COLS : a.N;
+  for (int j = threadIdx.x; j < COLS; j += kThreads) {
+    const bool ok = FULL || j < N;
+    s_vn[j] = ok ? a.vn[j] : T(0);
+    s_dv[j] = ok ? a.dvec[j] : T(0);
+    s_fa[j] = ok ? a.fuse_a()[j] : T(0);
+    s_fb[j] = ok ? a.fuse_b()[j] : T(0);
+  }
   const T sigma = (T)c->sigma;
   const T fac = (T)(sqrt(1.0 + c->aux[0]) - 1.0);
   const bool inject = c->inject != 0;
+  const bool store_x = !a.lean;
   if (blockIdx.x == 0 && threadIdx.x == 0) const_cast<sp_es_ctrl*>(c)->sigma_gen = c->sigma;
-  constexpr bool clip = CLIP;
-  auto vec = [&](const T* __restrict__ p, int cc, T (&o)[VEC]) {
+  __syncthreads();
+  auto svec = [&](const T* p, int cc, T (&o)[VEC]) {  // shared memory: always in bounds (COLS wide)
+    const V t = *reinterpret_cast<const V*>(p + TL::col(cc, l, 0));
+    const T* q = reinterpret_cast<const T*>(&t);
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) o[e] = q[e];
+  };
+  auto gvec = [&](const T* __restrict__ p, int cc, T (&o)[VEC]) {
     const int j0 = TL::col(cc, l, 0);
     if (FULL || j0 < ld) {
       const V t = __ldg(reinterpret_cast<const V*>(p + j0));
@@ -129,99 +160,114 @@ vd_sample_eval_kernel(const VdPtrs<T> a) {
       for (int e = 0; e < VEC; ++e) o[e] = T(0);
     }
   };
+  auto put = [&](T* __restrict__ rowp, int cc, const T (&val)[VEC]) {
+    const int j0 = TL::col(cc, l, 0);
+    if (FULL || j0 < ld) {
+      V t;
+      T* q = reinterpret_cast<T*>(&t);
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) q[e] = val[e];
+      if (a.stream_stores) __stcs(reinterpret_cast<V*>(rowp + j0), t);
+      else *reinterpret_cast<V*>(rowp + j0) = t;
+    }
+  };
 
   for (int64_t g = warp; g < groups; g += nwarps) {
     int64_t row = g * TL::RPW + sub;
     const bool live = row < a.P;
     if (!live) row = a.P - 1;
     TL y;
-    if (a.host_z) {
-      y.load(a.ary + row * a.ld, l, ld);
-    } else {
+    if (a.host_z) y.load(a.ary + row * a.ld, l, ld);
+    T zv = 0;
 #pragma unroll
-      for (int cc = 0; cc < CH; ++cc) {
-        const int j0 = TL::col(cc, l, 0);
+    for (int cc = 0; cc < CH; ++cc) {
+      const int j0 = TL::col(cc, l, 0);
+      if (!a.host_z) {
         T z[VEC];
         if (FULL || j0 < N) normal_block(philox4x32((uint32_t)(j0 / VEC), (uint32_t)row, (uint32_t)a.it, kEsZ, a.seed), z);
 #pragma unroll
         for (int e = 0; e < VEC; ++e) y.v[cc][e] = (FULL || j0 + e < N) ? z[e] : T(0);
       }
-    }
-    T zv = 0;
-#pragma unroll
-    for (int cc = 0; cc < CH; ++cc) {
       T vn[VEC];
-      vec(a.vn, cc, vn);
+      svec(s_vn, cc, vn);
 #pragma unroll
       for (int e = 0; e < VEC; ++e) zv += y.v[cc][e] * vn[e];
     }
     zv = group_sum<LPR>(zv);
+    const T k = fac * zv;
     const bool inj_row = inject && row < 2;
     T yv = 0;
+    T* __restrict__ yrow = a.ary + row * a.ld;
+    T* __restrict__ xrow = a.arx + row * a.ld;
 #pragma unroll
     for (int cc = 0; cc < CH; ++cc) {
-      T vn[VEC], dv[VEC];
-      vec(a.vn, cc, vn);
-      vec(a.dvec, cc, dv);
-      if (inj_row) {  // rows 0 / 1 carry +-dy (_vdcma.py:247-248)
+      const int j0 = TL::col(cc, l, 0);
+      T vn[VEC], dv[VEC], yy[VEC], tt[VEC];
+      svec(s_vn, cc, vn);
+      svec(s_dv, cc, dv);
+      if (inj_row) {  // rows 0 / 1 carry +-dy (_vdcma.py:247-248); t = y / D
         T dy[VEC];
-        vec(a.dy, cc, dy);
+        gvec(a.dy, cc, dy);
 #pragma unroll
         for (int e = 0; e < VEC; ++e) {
-          y.v[cc][e] = row == 0 ? dy[e] : -dy[e];
-          if (FULL || TL::col(cc, l, e) < N) yv += div_rn(y.v[cc][e], dv[e]) * vn[e];
+          yy[e] = row == 0 ? dy[e] : -dy[e];
+          tt[e] = (FULL || j0 + e < N) ? div_rn(yy[e], dv[e]) : T(0);
         }
       } else {
 #pragma unroll
         for (int e = 0; e < VEC; ++e) {
-          const T t = add_rn(y.v[cc][e], mul_rn(fac, mul_rn(zv, vn[e])));
-          yv += t * vn[e];
-          y.v[cc][e] = mul_rn(dv[e], t);
+          tt[e] = k * vn[e] + y.v[cc][e];
+          yy[e] = dv[e] * tt[e];
         }
+      }
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) yv += tt[e] * vn[e];
+      if (live) put(yrow, cc, yy);
+      if (CLIP || store_x) {  // the standardised x itself is needed
+        T xm[VEC], xs[VEC];
+        gvec(a.xmean, cc, xm);
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) xs[e] = add_rn(xm[e], mul_rn(sigma, yy[e]));
+        if (live && store_x) put(xrow, cc, xs);
+        if (CLIP) {
+          T sc[VEC], sh[VEC];
+          gvec(a.xscale, cc, sc);
+          gvec(a.xshift, cc, sh);
+#pragma unroll
+          for (int e = 0; e < VEC; ++e) {
+            const T v = xs[e] < T(-1) ? T(-1) : (xs[e] > T(1) ? T(1) : xs[e]);
+            y.v[cc][e] = add_rn(mul_rn(v, sc[e]), sh[e]);
+          }
+        }
+      }
+      if (!CLIP) {
+        T fa[VEC], fb[VEC];
+        svec(s_fa, cc, fa);
+        svec(s_fb, cc, fb);
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) y.v[cc][e] = tt[e] * fa[e] + fb[e];
       }
     }
     yv = group_sum<LPR>(yv);
-    if (live) {
-      if (a.stream_stores) y.store_cs(a.ary + row * a.ld, l, ld);
-      else y.store(a.ary + row * a.ld, l, ld);
-      if (l == 0) a.yvn[row] = yv;
-    }
-#pragma unroll
-    for (int cc = 0; cc < CH; ++cc) {
-      T xm[VEC];
-      vec(a.xmean, cc, xm);
-#pragma unroll
-      for (int e = 0; e < VEC; ++e) y.v[cc][e] = add_rn(xm[e], mul_rn(sigma, y.v[cc][e]));
-    }
-    if (live) {
-      if (a.stream_stores) y.store_cs(a.arx + row * a.ld, l, ld);
-      else y.store(a.arx + row * a.ld, l, ld);
-    }
+    if (live && l == 0) a.yvn[row] = yv;
     if (!a.evaluate) continue;
-#pragma unroll
-    for (int cc = 0; cc < CH; ++cc) {
-      T sc[VEC], sh[VEC];
-      vec(a.xscale, cc, sc);
-      vec(a.xshift, cc, sh);
-#pragma unroll
-      for (int e = 0; e < VEC; ++e) {
-        T v = y.v[cc][e];
-        if (clip) v = v < T(-1) ? T(-1) : (v > T(1) ? T(1) : v);
-        y.v[cc][e] = add_rn(mul_rn(v, sc[e]), sh[e]);
-      }
-    }
     const T f = evaluate_tile<T, CH, LPR>(a.objective, y, l, N);
     if (live && l == 0) a.arfit[row] = f;
   }
 }
 
-// weighted sums over the mu best; part[chunk][0..3][n] = S_x, S_y, P_mu, Q_mu
-// (_vdcma.py:291, 313, 426-441).  A CTA owns 256 x VEC columns and one chunk of rows: the
-// selected rows of the chunk are compacted (in row order, so the sums are deterministic) into
-// shared memory, then streamed 4 rows at a time with 16-byte loads by two thread groups that
-// take alternate batches and are folded in a fixed order.  x is rebuilt from y (x = mean +
-// sigma y, the very operations of the sampling kernel), so only y is read.
-constexpr int kWsTile = 512, kWsUnroll = 4, kWsThreads = 512;
+// weighted sums over the mu best (_vdcma.py:291, 313, 426-441), factored so that a row costs four
+// instructions per element.  With yd = y / D, yn = yd . vn and h = (yn^2 + 1 + |v|^2) / 2 the reference needs
+//   S_y  = sum w y                                       (evolution path; and dx = sum w x - (sum w) xmean = sigma S_y)
+//   P_mu = sum w (yd^2 - k1 yn vn yd - 1) = A / D^2 - k1 vn B / D - sum w
+//   Q_mu = sum w (yn yd - h vn)           = B / D - vn H
+// where  A = sum w y^2,  B = sum (w yn) y  are column sums and  H = sum w h  is one scalar.
+// part[chunk][0..2][n] = S_y, A, B of the chunk's selected rows, hpart[chunk] = its share of H.
+// A CTA owns 256 x VEC columns and one chunk of rows: the selected rows of the chunk are compacted
+// (in row order, so the sums are deterministic) into shared memory, then streamed kWsUnroll rows at a
+// time with 16-byte loads by two thread groups that take alternate batches and are folded in a fixed
+// order.  Only y is read: x is never needed.
+constexpr int kWsTile = 512, kWsUnroll = 8, kWsThreads = 512;
 template <typename T>
 __global__ void __launch_bounds__(kWsThreads, 2)
 vd_wsum_kernel(const VdPtrs<T> a) {
@@ -229,46 +275,47 @@ vd_wsum_kernel(const VdPtrs<T> a) {
   constexpr int VEC = Num<T>::VEC;
   if (!es_running(a.ctrl)) return;
   __shared__ int s_row[kWsTile];
-  __shared__ T s_w[kWsTile], s_yv[kWsTile];
+  __shared__ T s_w[kWsTile], s_wyn[kWsTile];
   __shared__ int s_cnt[kWsThreads / 32];
-  __shared__ T s_acc[4 * VEC][256];
+  __shared__ T s_h[kWsThreads / 32];
+  __shared__ T s_acc[3 * VEC][256];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, t = tid & 255, grp = tid >> 8;
   const int j0 = (blockIdx.x * 256 + t) * VEC;
   const bool col_ok = j0 < (int)a.ld;
   const int64_t per = (a.P + gridDim.y - 1) / gridDim.y;
   const int64_t i0 = blockIdx.y * per, i1 = (i0 + per < a.P) ? i0 + per : a.P;
-  const double nv2 = a.ctrl->aux[0];
-  const T k1 = (T)(nv2 / (1.0 + nv2)), nv2t = (T)nv2;
-  const T sigma = (T)a.ctrl->sigma_gen;
-  const bool with_mu = a.cmu != 0.0;
-  T vn[VEC], inv[VEC], xm[VEC], sx[VEC], sy[VEC], pm[VEC], qm[VEC];
+  const T nv2t = (T)a.ctrl->aux[0];
+  T sy[VEC], sa[VEC], sb[VEC];
 #pragma unroll
-  for (int e = 0; e < VEC; ++e) {
-    const bool ok = col_ok && j0 + e < a.N;
-    vn[e] = ok ? a.vn[j0 + e] : T(0);
-    inv[e] = ok ? div_rn(T(1), a.dvec[j0 + e]) : T(0);
-    xm[e] = ok ? a.xmean[j0 + e] : T(0);
-    sx[e] = sy[e] = pm[e] = qm[e] = T(0);
-  }
+  for (int e = 0; e < VEC; ++e) sy[e] = sa[e] = sb[e] = T(0);
+  T hsum = 0;
   for (int64_t t0 = i0; t0 < i1; t0 += kWsTile) {
     __syncthreads();
     const int64_t i = t0 + tid;
     const int r = i < i1 ? a.rank[i] : a.mu;
     const bool sel = r < a.mu;
+    const T w = sel ? a.weights[r] : T(0), yn = sel ? a.yvn[i] : T(0);
     const unsigned m = __ballot_sync(0xffffffffu, sel);
-    if (lane == 0) s_cnt[warp] = __popc(m);
+    T h = w * (T(0.5) * (yn * yn + T(1) + nv2t));  // 0 for the rows not selected
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) h += __shfl_xor_sync(0xffffffffu, h, o);
+    if (lane == 0) {
+      s_cnt[warp] = __popc(m);
+      s_h[warp] = h;
+    }
     __syncthreads();
     int off = 0, cnt = 0;
 #pragma unroll
-    for (int w = 0; w < kWsThreads / 32; ++w) {
-      off += w < warp ? s_cnt[w] : 0;
-      cnt += s_cnt[w];
+    for (int q = 0; q < kWsThreads / 32; ++q) {
+      off += q < warp ? s_cnt[q] : 0;
+      cnt += s_cnt[q];
+      hsum += s_h[q];  // same order in every thread
     }
     if (sel) {
       off += __popc(m & ((1u << lane) - 1u));
       s_row[off] = (int)(i - i0);
-      s_w[off] = a.weights[r];
-      s_yv[off] = a.yvn[i];
+      s_w[off] = w;
+      s_wyn[off] = w * yn;
     }
     __syncthreads();
     if (!col_ok) continue;
@@ -281,18 +328,14 @@ vd_wsum_kernel(const VdPtrs<T> a) {
 #pragma unroll
       for (int u = 0; u < kWsUnroll; ++u) {
         if (k + u < cnt) {
-          const T w = s_w[k + u], yn = s_yv[k + u];
+          const T w = s_w[k + u], wyn = s_wyn[k + u];
           const T* yy = reinterpret_cast<const T*>(&yv[u]);
 #pragma unroll
           for (int e = 0; e < VEC; ++e) {
-            const T y = yy[e];
-            sx[e] += w * add_rn(xm[e], mul_rn(sigma, y));
-            sy[e] += w * y;
-            if (with_mu) {
-              const T yd = y * inv[e];
-              pm[e] += w * (yd * yd - k1 * (yn * (yd * vn[e])) - T(1));
-              qm[e] += w * (yn * yd - (T(0.5) * (yn * yn + T(1) + nv2t)) * vn[e]);
-            }
+            const T y = yy[e], wy = w * y;
+            sy[e] += wy;
+            sa[e] += wy * y;
+            sb[e] += wyn * y;
           }
         }
       }
@@ -303,78 +346,111 @@ vd_wsum_kernel(const VdPtrs<T> a) {
   if (grp == 1) {
 #pragma unroll
     for (int e = 0; e < VEC; ++e) {
-      s_acc[e][t] = sx[e];
-      s_acc[VEC + e][t] = sy[e];
-      s_acc[2 * VEC + e][t] = pm[e];
-      s_acc[3 * VEC + e][t] = qm[e];
+      s_acc[e][t] = sy[e];
+      s_acc[VEC + e][t] = sa[e];
+      s_acc[2 * VEC + e][t] = sb[e];
     }
   }
   __syncthreads();
   if (grp != 0) return;
-  T* out = a.part() + (size_t)blockIdx.y * 4 * a.N;
+  if (blockIdx.x == 0 && tid == 0) a.hpart()[blockIdx.y] = hsum;
+  T* out = a.part() + (size_t)blockIdx.y * 3 * a.N;
 #pragma unroll
   for (int e = 0; e < VEC; ++e)
     if (col_ok && j0 + e < a.N) {
-      out[j0 + e] = sx[e] + s_acc[e][t];
-      out[a.N + j0 + e] = sy[e] + s_acc[VEC + e][t];
-      out[2 * a.N + j0 + e] = pm[e] + s_acc[2 * VEC + e][t];
-      out[3 * a.N + j0 + e] = qm[e] + s_acc[3 * VEC + e][t];
+      out[j0 + e] = sy[e] + s_acc[e][t];
+      out[a.N + j0 + e] = sa[e] + s_acc[VEC + e][t];
+      out[2 * a.N + j0 + e] = sb[e] + s_acc[2 * VEC + e][t];
     }
 }
 
-// chunk partials -> sums[q][n], fixed order: a CTA owns 32 outputs, 8 thread groups take
-// every 8th chunk, then the 8 group sums are added in order
-template <typename T>
-__global__ void __launch_bounds__(256)
-vd_wreduce_kernel(const VdPtrs<T> a) {
-  if (!es_running(a.ctrl)) return;
-  __shared__ T s_p[8][32];
-  const int o = threadIdx.x & 31, g = threadIdx.x >> 5;
-  const int e = blockIdx.x * 32 + o;
-  T acc = 0;
-  if (e < 4 * a.N) {
-    const T* p = a.part() + e;
-#pragma unroll 8
-    for (int c = g; c < a.chunks; c += 8) acc += p[(size_t)c * 4 * a.N];
-  }
-  s_p[g][o] = acc;
-  __syncthreads();
-  if (g == 0 && e < 4 * a.N) {
-    T tot = s_p[0][o];
-#pragma unroll
-    for (int k = 1; k < 8; ++k) tot += s_p[k][o];
-    a.sums()[e] = tot;
-  }
-}
-
-// mean, step size, paths, natural gradient, termination: one CTA (_vdcma.py:290-396).
-// The N-vectors live in registers (kVdNpt elements per thread, 256 threads: the scalar fp64
-// algebra between the reductions is replicated per warp, so few warps) and every dependent step
-// is one combined block reduction: ~10 barrier rounds instead of ~30 global round trips.
+// mean, step size, paths, natural gradient, termination (_vdcma.py:290-396), fused with the
+// reduction of the chunk partials of vd_wsum.
+//   phase 1 (every CTA of the grid): sums[q][n] = sum over the chunks of part[chunk][q][n] in a fixed
+//     order -- a CTA owns kUpOut outputs, 8 thread groups take every 8th chunk with all their loads in
+//     flight at once, then the 8 group sums are added in order; the LAST CTA to finish goes on;
+//   phase 2 (that one CTA, 1024 threads, one column each for N <= 1024): the N-vectors live in
+//     registers and every dependent step is one combined block reduction; the scans over the
+//     population (row of rank 0, min / max fitness for the ladder) are unrolled so their loads overlap.
+constexpr int kUpThreads = 1024, kUpOut = kUpThreads / 8;
 template <typename T, int kVdNpt>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kUpThreads)
 vd_update_kernel(const VdPtrs<T> a) {
   __shared__ double s_red[kRedDoubles];
+  __shared__ T s_p[8][kUpOut];
   __shared__ int s_best;
+  __shared__ bool s_last;
   sp_es_ctrl* c = a.ctrl;
   if (!es_running(c)) return;
   const int N = a.N, tid = threadIdx.x, nt = blockDim.x;
+  {
+    const int o = tid % kUpOut, g = tid / kUpOut;
+    const int e = blockIdx.x * kUpOut + o;
+    T acc = 0;
+    if (e < 3 * N) {
+      const T* p = a.part() + e;
+      T v[kVdChunks / 8];
+#pragma unroll
+      for (int k = 0; k < kVdChunks / 8; ++k) v[k] = (g + 8 * k < a.chunks) ? __ldcg(p + (size_t)(g + 8 * k) * 3 * N) : T(0);
+#pragma unroll
+      for (int k = 0; k < kVdChunks / 8; ++k) acc += v[k];
+    }
+    s_p[g][o] = acc;
+    __syncthreads();
+    if (g == 0 && e < 3 * N) {
+      T tot = s_p[0][o];
+#pragma unroll
+      for (int k = 1; k < 8; ++k) tot += s_p[k][o];
+      a.sums()[e] = tot;
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+      const unsigned prev = atomicAdd(&c->base.done_blocks, 1u);
+      s_last = prev == gridDim.x - 1;
+      if (s_last) c->base.done_blocks = 0;  // ready for the next launch
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+  }
   const double nv2 = c->aux[0], nv = c->aux[1];
   // ---- everything this generation reads, issued up front ------------------------------------------
   bool ok[kVdNpt];
-  T xm[kVdNpt], pc[kVdNpt], vnT[kVdNpt], dv[kVdNpt], vv[kVdNpt], Sx[kVdNpt], Sy[kVdNpt], Pm[kVdNpt], Qm[kVdNpt];
+  T xm[kVdNpt], pc[kVdNpt], vnT[kVdNpt], dv[kVdNpt], vv[kVdNpt], Sy[kVdNpt], Sa[kVdNpt], Sb[kVdNpt];
 #pragma unroll
   for (int k = 0; k < kVdNpt; ++k) {
     const int n = tid + k * nt;
     ok[k] = n < N;
     const int m = ok[k] ? n : 0;
     const T* p = a.sums();
-    Sx[k] = p[m], Sy[k] = p[N + m], Pm[k] = p[2 * N + m], Qm[k] = p[3 * N + m];
+    Sy[k] = __ldcg(p + m), Sa[k] = __ldcg(p + N + m), Sb[k] = __ldcg(p + 2 * N + m);
     xm[k] = a.xmean[m], pc[k] = a.pc[m], vnT[k] = a.vn[m], dv[k] = a.dvec[m], vv[k] = a.vvec[m];
   }
   const int r0 = a.rank[0], r1 = a.P > 1 ? a.rank[1] : 0;
-  for (int64_t i = tid; i < a.P; i += nt)
-    if (a.rank[i] == 0) s_best = (int)i;
+  // row of rank 0 (ties by index: the stable rank's first minimum) and the fitness range of the ladder
+  double fext[2] = {1.0 / 0.0, -1.0 / 0.0};
+  {
+    int best = -1;
+    constexpr int U = 4;
+    for (int64_t i0 = tid; i0 < a.P; i0 += (int64_t)U * nt) {
+      int rk[U];
+      T fv[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int64_t i = i0 + (int64_t)u * nt;
+        rk[u] = i < a.P ? a.rank[i] : -1;
+        fv[u] = i < a.P ? a.arfit[i] : a.arfit[0];
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (rk[u] == 0) best = (int)(i0 + (int64_t)u * nt);
+        fext[0] = fmin(fext[0], (double)fv[u]);
+        fext[1] = fmax(fext[1], (double)fv[u]);
+      }
+    }
+    if (best >= 0) s_best = best;
+  }
   // sigma from the rank gap of the injected pair, _vdcma.py:299-307
   bool hsig = true;
   double sigma = c->sigma_gen, ps_new = c->vd_ps;
@@ -388,10 +464,11 @@ vd_update_kernel(const VdPtrs<T> a) {
   // mean, _vdcma.py:291; evolution path, :310-315
   const T kpc = (T)sqrt(a.cc * (2.0 - a.cc) * a.mueff);
   T dx[kVdNpt];
-  double red2[2] = {0.0, 0.0};  // max vn^2, (pc / D) . vn
+  double red2[3] = {0.0, 0.0, 0.0};  // max vn^2, (pc / D) . vn, H = sum of vd_wsum's scalar partials
+  if (tid < a.chunks) red2[2] = (double)__ldcg(a.hpart() + tid);
 #pragma unroll
   for (int k = 0; k < kVdNpt; ++k) {
-    dx[k] = sub_rn(Sx[k], mul_rn((T)a.wsum, xm[k]));
+    dx[k] = mul_rn((T)c->sigma_gen, Sy[k]);  // = w . x[top mu] - (sum w) xmean (_vdcma.py:291), without the cancellation
     T v = mul_rn(pc[k], (T)(1.0 - a.cc));
     if (hsig) v = add_rn(v, mul_rn(kpc, Sy[k]));
     pc[k] = v;
@@ -407,10 +484,10 @@ vd_update_kernel(const VdPtrs<T> a) {
     }
   }
   {
-    const int op[2] = {RED_MAX, RED_SUM};
-    block_reduce<2>(red2, op, s_red);
+    const int op[3] = {RED_MAX, RED_SUM, RED_SUM};
+    block_reduce<3>(red2, op, s_red);
   }
-  const double vmax = red2[0], yv1 = red2[1];
+  const double vmax = red2[0], yv1 = red2[1], hmu = red2[2];
   // alpha and friends, _vdcma.py:318-329
   const double gamma = 1.0 / sqrt(1.0 + nv2);
   double alpha = sqrt(nv2 * nv2 + (1.0 + nv2) / vmax * (2.0 - gamma)) / (2.0 + nv2), beta = 0.0;
@@ -424,8 +501,12 @@ vd_update_kernel(const VdPtrs<T> a) {
 #pragma unroll
   for (int k = 0; k < kVdNpt; ++k) {
     const double vn = (double)vnT[k];
-    double p = a.cmu == 0.0 ? 0.0 : a.cmu * (double)Pm[k];
-    double q = a.cmu == 0.0 ? 0.0 : a.cmu * (double)Qm[k];
+    double p = 0.0, q = 0.0;
+    if (a.cmu != 0.0) {  // rank-mu vectors from the factored sums (see vd_wsum_kernel)
+      const double inv = 1.0 / (double)dv[k], bq = (double)Sb[k] * inv;
+      p = a.cmu * ((double)Sa[k] * inv * inv - k1 * (vn * bq) - a.wsum);
+      q = a.cmu * (bq - vn * hmu);
+    }
     if (hsig && a.c1 != 0.0) {
       const double y1 = (double)div_rn(pc[k], dv[k]);
       p += a.c1 * (y1 * y1 - k1 * (yv1 * y1 * vn) - 1.0);
@@ -508,7 +589,7 @@ vd_update_kernel(const VdPtrs<T> a) {
   __syncthreads();
   // diagC still describes the population just evaluated (_vdcma.py:380-396: no B, D)
   converge_ladder<T>(c, a.it, N, a.maxiter, a.ilim, a.P, a.xmean, a.xold, a.besthist, a.arfit, a.pc, a.diagC, 1,
-                     (const T*)nullptr, (const T*)nullptr, a.xtol, a.ftol, a.insigma, s_red);
+                     (const T*)nullptr, (const T*)nullptr, a.xtol, a.ftol, a.insigma, s_red, fext);
   // next generation's |v|^2, vn, diagC and (in-kernel draws) its injected direction dy
   __syncthreads();
   vd_refresh_body<T>(a, s_red);
@@ -566,6 +647,7 @@ static VdPtrs<T> vd_ptrs(const sp_vd_state* st, int it, int evaluate) {
   a.objective = st->objective;
   a.it = it;
   a.host_z = st->host_z;
+  a.lean = st->lean;
   a.evaluate = evaluate;
   // y and x of a population larger than the L2 are stored evict-first (st.global.cs); SP_VD_PLAIN_STORES=1
   // keeps normal stores (profiling switch)
@@ -637,13 +719,11 @@ static int vd_update(const sp_vd_state* st, int it, cudaStream_t s) {
   if (rank_launch<T>(a.arfit, P, a.rank, nullptr, s) != cudaSuccess) return SP_ERR_CUDA;
   vd_wsum_kernel<T><<<dim3(cdiv(st->ld, 256 * Num<T>::VEC), a.chunks), kWsThreads, 0, s>>>(a);
   SP_CHECK_LAUNCH();
-  vd_wreduce_kernel<T><<<cdiv(4 * N, 32), 256, 0, s>>>(a);
-  SP_CHECK_LAUNCH();
-  // also refreshes vn / diagC (and dy) for the next generation
-  if (N <= 256) vd_update_kernel<T, 1><<<1, 256, 0, s>>>(a);
-  else if (N <= 512) vd_update_kernel<T, 2><<<1, 256, 0, s>>>(a);
-  else if (N <= 1024) vd_update_kernel<T, 4><<<1, 256, 0, s>>>(a);
-  else vd_update_kernel<T, 8><<<1, 256, 0, s>>>(a);
+  // chunk partials -> sums, then (last CTA) the update itself; also refreshes vn / diagC / fuse_a / fuse_b
+  // (and dy) for the next generation
+  const int ups = cdiv(3 * (int64_t)N, kUpOut);
+  if (N <= kUpThreads) vd_update_kernel<T, 1><<<ups, kUpThreads, 0, s>>>(a);
+  else vd_update_kernel<T, 2><<<ups, kUpThreads, 0, s>>>(a);
   SP_CHECK_LAUNCH();
   return SP_OK;
 }
@@ -670,7 +750,7 @@ using namespace sp;
 
 extern "C" {
 
-int64_t sp_vd_work_scalars(int N, int64_t P) { return (int64_t)kVdChunks * 4 * N + 13LL * N + P; }
+int64_t sp_vd_work_scalars(int N, int64_t P) { return (int64_t)kVdChunks * 4 * N + 15LL * N + 8 + P + kVdChunks; }
 
 int sp_vd_refresh(const sp_vd_state* st, void* stream) {
   int rc = vd_check(st, 1);

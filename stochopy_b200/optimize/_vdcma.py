@@ -127,11 +127,15 @@ def minimize(
         setattr(st, k, t.data_ptr())
     st.dfithist, st.ctrl = dfithist.data_ptr(), ctrl.data_ptr()
     st.host_z = int(stream is not None)
-    L.call("sp_vd_refresh", C.byref(st), eng.stream)
 
     hist = EsHistory(return_all, maxiter, P, N, verbosity)
     observe = hist.enabled or callback is not None
     penal = cons == L.CONS_PENALIZE
+    # nobody reads the population: the sampling kernel keeps only y and the fitness (the result row is
+    # rebuilt below as xold + sigma_gen * y)
+    lean = obj is not None and stream is None and not observe and _probe is None and not penal
+    st.lean = int(lean)
+    L.call("sp_vd_refresh", C.byref(st), eng.stream)
     arx, arfit = bufs["arx"], bufs["arfit"]
     valid_rows = (lambda r: np.clip(r, -1.0, 1.0)) if penal else (lambda r: r)
 
@@ -182,7 +186,12 @@ def minimize(
     it = c.base.nit
     if streamer is not None:
         streamer.finish(hist, it, transform=lambda X: unstd(valid_rows(X)))
-    best = arx[c.base.gbest_row, :N].to("cpu").numpy().astype(np.float64)
+    if lean:  # x = xmean_old + sigma * y in the working precision, as the exact kernel stores it (_vdcma.py:249)
+        yb = bufs["ary"][c.base.gbest_row, :N].to("cpu").numpy()
+        xo = bufs["xold"][:N].to("cpu").numpy()
+        best = (xo + eng.np_dt.type(c.sigma_gen) * yb).astype(np.float64)
+    else:
+        best = arx[c.base.gbest_row, :N].to("cpu").numpy().astype(np.float64)
     res = OptimizeResult(
         x=unstd(valid_rows(best)),
         success=c.base.status >= 0,

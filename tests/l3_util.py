@@ -42,10 +42,10 @@ def compare(name, ref_runs, got_runs):
     lo, hi = np.percentile(r[:, 3], [10.0, 90.0])
     med_g, med_r = float(np.median(g[:, 3])), float(np.median(r[:, 3]))
     nit_g, nit_r = float(np.median(g[:, 1])), float(np.median(r[:, 1]))
-    stats = dict(config=name, tv_status=tv, ks_fun=d_fun, ks_nit=d_nit, fun_median=(med_g, med_r),
+    stats = dict(config=name, tv_status=float(tv), ks_fun=d_fun, ks_nit=d_nit, fun_median=(med_g, med_r),
                  ref_p10_p90=(float(lo), float(hi)), nit_median=(nit_g, nit_r),
-                 status_ref={c: int((r[:, 0] == c).sum()) for c in codes},
-                 status_got={c: int((g[:, 0] == c).sum()) for c in codes})
+                 status_ref={int(c): int((r[:, 0] == c).sum()) for c in codes},
+                 status_got={int(c): int((g[:, 0] == c).sum()) for c in codes})
     ok = (tv <= TV_MAX and d_fun <= KS_MAX and d_nit <= KS_MAX and lo - 1e-12 <= med_g <= hi + 1e-12
           and abs(nit_g - nit_r) <= max(3.0, 0.25 * nit_r))
     assert ok, stats

@@ -72,8 +72,8 @@ def test_cmaes_generation_steps_match_oracle(dtype, N, P, fun):
             sigma=c.sigma, sigma_gen=c.sigma_gen, hsig=c.hsig, nfev=int(c.nfev), status=c.base.status,
             gbest_row=int(c.base.gbest_row), gfit=c.base.gfit, do_eig=c.do_eig))
 
-    r = sb.optimize.minimize(getattr(sb.factory, fun), [[-BOUND, BOUND]] * N, method="cmaes", _probe=probe,
-                             options=dict(maxiter=gens, popsize=P, seed=seed, sigma=sigma0, xtol=-1.0, ftol=-1e300,
+    r = sb.optimize.minimize(getattr(sb.factory, fun), [[-BOUND, BOUND]] * N, method="cmaes",
+                             options=dict(_probe=probe, maxiter=gens, popsize=P, seed=seed, sigma=sigma0, xtol=-1.0, ftol=-1e300,
                                           dtype=dtype))
     assert r.nit == gens and r.status == -1 and len(snaps) == gens
 
@@ -166,8 +166,8 @@ def test_vdcma_generation_steps_match_oracle(dtype, N, P, fun):
             sigma_gen=c.sigma_gen, vd_ps=c.vd_ps, nfev=int(c.nfev), status=c.base.status,
             gbest_row=int(c.base.gbest_row), gfit=c.base.gfit))
 
-    r = sb.optimize.minimize(getattr(sb.factory, fun), [[-BOUND, BOUND]] * N, method="vdcma", _probe=probe,
-                             options=dict(maxiter=gens, popsize=P, seed=seed, sigma=sigma0, xtol=-1.0, ftol=-1e300,
+    r = sb.optimize.minimize(getattr(sb.factory, fun), [[-BOUND, BOUND]] * N, method="vdcma",
+                             options=dict(_probe=probe, maxiter=gens, popsize=P, seed=seed, sigma=sigma0, xtol=-1.0, ftol=-1e300,
                                           dtype=dtype))
     assert r.nit == gens and r.status == -1 and len(snaps) == gens
 
