@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define SP_ABI_VERSION 1
+#define SP_ABI_VERSION 2
 
 /* error codes */
 #define SP_OK 0
@@ -334,11 +334,11 @@ typedef struct {
   void* C;         /* (N x N) */
   void* B;         /* (N x N) eigenvectors in columns */
   void* D;         /* (N) sqrt of eigenvalues */
-  void* BD;        /* reserved (unused) */
   void* invsqrtC;  /* (N x N) */
   void* arx;       /* (P x ld) population (standardised, unclipped) */
   void* arfit;     /* (P) fitness (penalised when constraint = Penalize) */
-  void* Z;         /* (P x ld) N(0,I) draws of the generation */
+  void* Z;         /* (P x ld) N(0,I) draws of the generation; after the sampling GEMM its first mu rows hold
+                    * the mu best individuals in rank order (panel of the mean / rank-mu update) */
   void* weights;   /* (mu) */
   void* xscale;    /* (ld) 0.5 (upper - lower) */
   void* xshift;    /* (ld) 0.5 (upper + lower) */

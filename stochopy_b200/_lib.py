@@ -98,7 +98,7 @@ class CmaState(C.Structure):
         ("chind", C.c_double), ("mueff", C.c_double), ("xtol", C.c_double), ("ftol", C.c_double),
         ("insigma", C.c_double),
         ("seed", C.c_uint64),
-        ("xmean", vp), ("xold", vp), ("pc", vp), ("ps", vp), ("C", vp), ("B", vp), ("D", vp), ("BD", vp),
+        ("xmean", vp), ("xold", vp), ("pc", vp), ("ps", vp), ("C", vp), ("B", vp), ("D", vp),
         ("invsqrtC", vp), ("arx", vp), ("arfit", vp), ("Z", vp), ("weights", vp), ("xscale", vp), ("xshift", vp),
         ("besthist", vp), ("work", vp), ("rank", vp), ("bnd_weights", vp), ("dfithist", vp), ("ctrl", vp),
         ("scratch", vp),

@@ -8,7 +8,8 @@
 //   eval             arfit = fun(clip?(arx) * xscale + xshift)
 //   [Penalize]       rank -> percentiles -> weights -> arfit += penalty
 //   rank             np.argsort(arfit) as a rank per individual
-//   cma_mean         xmean' = sum_i w[rank_i] arx_i                 (deterministic two-stage)
+//   cma_gather       the mu best rows in rank order -> contiguous panel (reuses Z), best row
+//   cma_mean         xmean' = sum_r w[r] panel_r                    (deterministic two-stage)
 //   cma_paths        ps, hsig, pc, sigma', eigen-update decision    one CTA
 //   cma_cov          C' = (1-c1-cmu) C + cmu A^T diag(w) A + ...    GEMM TN  2 mu N^2 flop
 //   [jacobi + post]  C = B diag(D^2) B^T, invsqrtC                  when due
@@ -23,7 +24,7 @@ constexpr int kCovSplits = 8;
 
 template <typename T>
 struct CmaPtrs {
-  T *xmean, *xold, *pc, *ps, *C, *B, *D, *BD, *invsqrtC, *arx, *arfit, *Z, *weights, *xscale, *xshift, *besthist,
+  T *xmean, *xold, *pc, *ps, *C, *B, *D, *invsqrtC, *arx, *arfit, *Z, *weights, *xscale, *xshift, *besthist,
       *work, *bnd_weights, *dfithist;
   int32_t* rank;
   sp_es_ctrl* ctrl;
@@ -35,6 +36,7 @@ struct CmaPtrs {
   __host__ __device__ T* cov_part() const { return work + (size_t)kMeanChunks * N; }          // kCovSplits * N * N
   __host__ __device__ T* jac() const { return cov_part() + (size_t)kCovSplits * N * N; }      // 2 N^2 + N + 64
   __host__ __device__ T* vec() const { return jac() + 2 * (size_t)N * N + N + 64; }           // 8 * N (diff, coef, ...)
+  __host__ __device__ T* inv_d() const { return vec() + 4 * (size_t)N; }                      // N: 1 / D of the last decomposition
   __host__ __device__ T* sorted() const { return vec() + 8 * (size_t)N; }                     // P (Penalize percentiles)
 };
 
@@ -57,19 +59,38 @@ cma_sample_kernel(const CmaPtrs<T> a) {
                   [=] __device__(int m, int n, T acc) { a.arx[(int64_t)m * ld + n] = add_rn(a.xmean[n], mul_rn(sigma, acc)); });
 }
 
-// ---- weighted mean of the mu best, stage 1 (_cmaes.py:274) ---------------------------------
+// ---- the mu best rows, in rank order, as a contiguous panel (_cmaes.py:272-274) ------------------
+// panel[r][:] = arx[i][:] for r = rank[i] < mu.  Z is dead once the sampling GEMM has run, so it holds
+// the panel; the mean and the rank-mu GEMM then stream mu contiguous rows instead of testing the rank
+// of all P.  The warp that meets rank 0 records the best row of the generation.
+template <typename T>
+__global__ void __launch_bounds__(256)
+cma_gather_kernel(const CmaPtrs<T> a) {
+  using V = typename Num<T>::vec_t;
+  if (!es_running(a.ctrl)) return;
+  const int lane = threadIdx.x & 31, nv = (int)(a.ld / Num<T>::VEC);
+  const int64_t gw = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t i = gw; i < a.P; i += nw) {
+    const int r = a.rank[i];
+    if (r == 0 && lane == 0) a.ctrl->base.gbest_row = i;
+    if (r >= a.mu) continue;
+    const V* __restrict__ src = reinterpret_cast<const V*>(a.arx + i * a.ld);
+    V* __restrict__ dst = reinterpret_cast<V*>(a.Z + (int64_t)r * a.ld);
+    for (int k = lane; k < nv; k += 32) dst[k] = src[k];
+  }
+}
+
+// ---- weighted mean of the mu best, stage 1 (_cmaes.py:274): chunk c sums its panel rows in rank order
 template <typename T>
 __global__ void __launch_bounds__(256)
 cma_mean_partial_kernel(const CmaPtrs<T> a) {
   if (!es_running(a.ctrl)) return;
-  const int64_t per = (a.P + kMeanChunks - 1) / kMeanChunks;
-  const int64_t i0 = blockIdx.x * per, i1 = (i0 + per < a.P) ? i0 + per : a.P;
+  const int per = (a.mu + kMeanChunks - 1) / kMeanChunks;
+  const int r0 = blockIdx.x * per, r1 = (r0 + per < a.mu) ? r0 + per : a.mu;
   for (int n = threadIdx.x; n < a.N; n += blockDim.x) {
     T acc = 0;
-    for (int64_t i = i0; i < i1; ++i) {
-      const int r = a.rank[i];
-      if (r < a.mu) acc += a.weights[r] * a.arx[i * a.ld + n];
-    }
+#pragma unroll 8
+    for (int r = r0; r < r1; ++r) acc += a.weights[r] * a.Z[(int64_t)r * a.ld + n];
     a.mean_part()[(size_t)blockIdx.x * a.N + n] = acc;
   }
 }
@@ -79,16 +100,11 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 cma_paths_kernel(const CmaPtrs<T> a) {
   __shared__ double s_red[kRedDoubles];
-  __shared__ int s_best;
   sp_es_ctrl* c = a.ctrl;
   if (!es_running(c)) return;
   const int N = a.N, tid = threadIdx.x;
   T* diff = a.vec();
   const T sigma = (T)c->sigma_gen;
-  if (tid == 0) s_best = 0x7fffffff;
-  __syncthreads();
-  for (int64_t i = tid; i < a.P; i += blockDim.x)
-    if (a.rank[i] == 0) s_best = (int)i;
   // xold = xmean; xmean = sum of the chunk partials (fixed order)
   for (int n = tid; n < N; n += blockDim.x) {
     T acc = 0;
@@ -103,9 +119,11 @@ cma_paths_kernel(const CmaPtrs<T> a) {
   const T kps = (T)sqrt(a.cs * (2.0 - a.cs) * a.mueff);
   double sq = 0.0;
   for (int n = tid; n < N; n += blockDim.x) {
+    // invsqrtC = B diag(1/D) B^T is symmetric: column n read with unit stride across the threads
     T dot = 0;
-    const T* row = a.invsqrtC + (size_t)n * N;
-    for (int k = 0; k < N; ++k) dot += row[k] * diff[k];
+    const T* col = a.invsqrtC + n;
+#pragma unroll 8
+    for (int k = 0; k < N; ++k) dot += col[(size_t)k * N] * diff[k];
     const T v = add_rn(mul_rn((T)(1.0 - a.cs), a.ps[n]), div_rn(mul_rn(kps, dot), sigma));
     a.ps[n] = v;
     sq += (double)v * (double)v;
@@ -120,9 +138,7 @@ cma_paths_kernel(const CmaPtrs<T> a) {
     a.pc[n] = v;
   }
   if (tid == 0) {
-    const int b = s_best;
-    const double best = (double)a.arfit[b];
-    c->base.gbest_row = b;
+    const double best = (double)a.arfit[c->base.gbest_row];  // row of rank 0 (cma_gather_kernel)
     c->base.gfit = best;
     a.besthist[a.it - 1] = (T)best;
     c->ps_norm = psn;
@@ -135,27 +151,24 @@ cma_paths_kernel(const CmaPtrs<T> a) {
   }
 }
 
-// ---- rank-mu partial products (_cmaes.py:290-293) ---------------------------------------------
+// ---- rank-mu partial products (_cmaes.py:290-293) over the panel of the mu best rows ------------
+// artmp_r = (x_r - xold) / sigma (as a multiplication by 1 / sigma: <= 1 ulp from the reference's quotient)
 template <typename T>
 __global__ void __launch_bounds__(256)
 cma_cov_partial_kernel(const CmaPtrs<T> a) {
   if (!es_running(a.ctrl)) return;
-  const T sigma = (T)a.ctrl->sigma_gen;
+  const T inv_sigma = div_rn(T(1), (T)a.ctrl->sigma_gen);
   const int N = a.N;
-  const int64_t per = (a.P + kCovSplits - 1) / kCovSplits;
-  const int64_t i0 = blockIdx.z * per, i1 = (i0 + per < a.P) ? i0 + per : a.P;
+  const int per = (a.mu + kCovSplits - 1) / kCovSplits;
+  const int i0 = blockIdx.z * per, i1 = (i0 + per < a.mu) ? i0 + per : a.mu;
   T* out = a.cov_part() + (size_t)blockIdx.z * N * N;
   const int64_t ld = a.ld;
-  gemm_tn_tile<T>(N, N, (int)i0, (int)i1, blockIdx.y * kGemmTile, blockIdx.x * kGemmTile,
+  const T* __restrict__ panel = a.Z;
+  gemm_tn_tile<T>(N, N, i0, i1, blockIdx.y * kGemmTile, blockIdx.x * kGemmTile,
                   [=] __device__(int i, int r) {
-                    const int rk = a.rank[i];
-                    if (rk >= a.mu) return T(0);
-                    return mul_rn(div_rn(sub_rn(a.arx[(int64_t)i * ld + r], a.xold[r]), sigma), a.weights[rk]);
+                    return mul_rn(mul_rn(sub_rn(panel[(int64_t)i * ld + r], a.xold[r]), inv_sigma), a.weights[i]);
                   },
-                  [=] __device__(int i, int cc) {
-                    if (a.rank[i] >= a.mu) return T(0);
-                    return div_rn(sub_rn(a.arx[(int64_t)i * ld + cc], a.xold[cc]), sigma);
-                  },
+                  [=] __device__(int i, int cc) { return mul_rn(sub_rn(panel[(int64_t)i * ld + cc], a.xold[cc]), inv_sigma); },
                   [=] __device__(int r, int cc, T acc) { out[(size_t)r * N + cc] = acc; });
 }
 
@@ -183,8 +196,11 @@ __global__ void cma_cov_combine_kernel(const CmaPtrs<T> a) {
 template <typename T>
 __global__ void cma_sqrt_d_kernel(const CmaPtrs<T> a) {
   if (!es_running(a.ctrl) || a.ctrl->do_eig == 0) return;
-  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < a.N; k += gridDim.x * blockDim.x)
-    a.D[k] = (T)sqrt((double)a.D[k]);  // no negative guard, like the reference
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < a.N; k += gridDim.x * blockDim.x) {
+    const T d = (T)sqrt((double)a.D[k]);  // no negative guard, like the reference
+    a.D[k] = d;
+    a.inv_d()[k] = div_rn(T(1), d);
+  }
 }
 // invsqrtC = (B diag(1/D)) B^T  (_cmaes.py:309)
 template <typename T>
@@ -193,7 +209,7 @@ cma_invsqrt_kernel(const CmaPtrs<T> a) {
   if (!es_running(a.ctrl) || a.ctrl->do_eig == 0) return;
   const int N = a.N;
   gemm_nt_tile<T>(N, N, N, blockIdx.y * kGemmTile, blockIdx.x * kGemmTile,
-                  [=] __device__(int m, int k) { return mul_rn(a.B[(size_t)m * N + k], div_rn(T(1), a.D[k])); },
+                  [=] __device__(int m, int k) { return mul_rn(a.B[(size_t)m * N + k], a.inv_d()[k]); },
                   [=] __device__(int n, int k) { return a.B[(size_t)n * N + k]; },
                   [=] __device__(int m, int n, T acc) { a.invsqrtC[(size_t)m * N + n] = acc; });
 }
@@ -226,7 +242,6 @@ static CmaPtrs<T> cma_ptrs(const sp_cma_state* st, int it) {
   a.C = (T*)st->C;
   a.B = (T*)st->B;
   a.D = (T*)st->D;
-  a.BD = (T*)st->BD;
   a.invsqrtC = (T*)st->invsqrtC;
   a.arx = (T*)st->arx;
   a.arfit = (T*)st->arfit;
@@ -294,7 +309,8 @@ static int cma_sample(const sp_cma_state* st, int it, cudaStream_t s) {
 template <typename T>
 static int cma_eval(const sp_cma_state* st, int it, cudaStream_t s) {
   const int clip = st->constraint == SP_CONS_PENALIZE ? 1 : 0;
-  return eval_launch<T>(st->objective, st->arx, st->P, st->N, st->ld, st->xscale, st->xshift, st->arfit, clip, s);
+  return eval_launch<T>(st->objective, st->arx, st->P, st->N, st->ld, st->xscale, st->xshift, st->arfit, clip, s,
+                        &st->ctrl->base.status);
 }
 
 // phase C: penalty, selection, paths, covariance, eigenbasis, termination
@@ -304,7 +320,7 @@ static int cma_update(const sp_cma_state* st, int it, cudaStream_t s) {
   const int N = st->N, tiles = cdiv(N, kGemmTile);
   const int64_t P = st->P;
   if (st->constraint == SP_CONS_PENALIZE) {
-    if (rank_launch<T>(a.arfit, P, a.rank, nullptr, s) != cudaSuccess) return SP_ERR_CUDA;
+    if (rank_launch<T>(a.arfit, P, a.rank, nullptr, s, &st->ctrl->base.status) != cudaSuccess) return SP_ERR_CUDA;
     scatter_sorted_kernel<T><<<cdiv(P, 256) < 1024 ? cdiv(P, 256) : 1024, 256, 0, s>>>(a.arfit, a.rank, a.sorted(), P, st->ctrl);
     SP_CHECK_LAUNCH();
     cma_penalty_state_kernel<T><<<1, 256, 0, s>>>(a);
@@ -313,7 +329,9 @@ static int cma_update(const sp_cma_state* st, int it, cudaStream_t s) {
         a.arx, a.vec() + 2 * N, a.arfit, P, N, st->ld, st->ctrl);
     SP_CHECK_LAUNCH();
   }
-  if (rank_launch<T>(a.arfit, P, a.rank, nullptr, s) != cudaSuccess) return SP_ERR_CUDA;
+  if (rank_launch<T>(a.arfit, P, a.rank, nullptr, s, &st->ctrl->base.status) != cudaSuccess) return SP_ERR_CUDA;
+  cma_gather_kernel<T><<<cdiv(P, 8) < sm_count() * 4 ? cdiv(P, 8) : sm_count() * 4, 256, 0, s>>>(a);
+  SP_CHECK_LAUNCH();
   cma_mean_partial_kernel<T><<<kMeanChunks, 256, 0, s>>>(a);
   SP_CHECK_LAUNCH();
   cma_paths_kernel<T><<<1, 256, 0, s>>>(a);

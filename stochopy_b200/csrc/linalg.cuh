@@ -100,6 +100,8 @@ struct GemmAcc<float> {
 
 // C[m][n] = epi(sum_k A(m,k) * B(n,k))        ("NT": both operands k-contiguous)
 // LoadA / LoadB: functors (row, k) -> T (0 outside bounds handled here); Epi: (m, n, acc).
+// The k-chunks are software pipelined: the global loads of chunk k+1 are issued (into registers) before
+// the tensor-core work on chunk k, so their latency hides behind the mma sequence.
 template <typename T, typename LoadA, typename LoadB, typename Epi>
 __device__ __forceinline__ void gemm_nt_tile(int M, int Nn, int K, int m0, int n0, LoadA la, LoadB lb, Epi epi) {
   __shared__ T As[kGemmK][kGemmLd];
@@ -107,16 +109,27 @@ __device__ __forceinline__ void gemm_nt_tile(int M, int Nn, int K, int m0, int n
   const int tid = threadIdx.x;
   GemmAcc<T> acc;
   acc.clear();
-  for (int k0 = 0; k0 < K; k0 += kGemmK) {
-    // 64 x 16 elements per operand, 4 per thread; k fastest so global reads are contiguous
+  T ra[4], rb[4];
+  // 64 x 16 elements per operand, 4 per thread; k fastest so global reads are contiguous
+  auto fetch = [&](int k0) {
 #pragma unroll
     for (int t = 0; t < 4; ++t) {
       const int e = tid + t * 256, r = e >> 4, kk = e & 15;
       const int m = m0 + r, n = n0 + r, k = k0 + kk;
-      As[kk][r] = (m < M && k < K) ? la(m, k) : T(0);
-      Bs[kk][r] = (n < Nn && k < K) ? lb(n, k) : T(0);
+      ra[t] = (m < M && k < K) ? la(m, k) : T(0);
+      rb[t] = (n < Nn && k < K) ? lb(n, k) : T(0);
+    }
+  };
+  fetch(0);
+  for (int k0 = 0; k0 < K; k0 += kGemmK) {
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const int e = tid + t * 256, r = e >> 4, kk = e & 15;
+      As[kk][r] = ra[t];
+      Bs[kk][r] = rb[t];
     }
     __syncthreads();
+    if (k0 + kGemmK < K) fetch(k0 + kGemmK);
     acc.chunk(As, Bs);
     __syncthreads();
   }
@@ -134,15 +147,26 @@ __device__ __forceinline__ void gemm_tn_tile(int R, int Cc, int i0, int i1, int 
   const int tid = threadIdx.x;
   GemmAcc<T> acc;
   acc.clear();
-  for (int ib = i0; ib < i1; ib += kGemmK) {
+  T ra[4], rb[4];
+  auto fetch = [&](int ib) {
 #pragma unroll
     for (int t = 0; t < 4; ++t) {
       const int e = tid + t * 256, kk = e >> 6, cc = e & 63;  // column fastest: contiguous row reads
       const int i = ib + kk;
-      As[kk][cc] = (i < i1 && r0 + cc < R) ? la(i, r0 + cc) : T(0);
-      Bs[kk][cc] = (i < i1 && c0 + cc < Cc) ? lb(i, c0 + cc) : T(0);
+      ra[t] = (i < i1 && r0 + cc < R) ? la(i, r0 + cc) : T(0);
+      rb[t] = (i < i1 && c0 + cc < Cc) ? lb(i, c0 + cc) : T(0);
+    }
+  };
+  fetch(i0);
+  for (int ib = i0; ib < i1; ib += kGemmK) {
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const int e = tid + t * 256, kk = e >> 6, cc = e & 63;
+      As[kk][cc] = ra[t];
+      Bs[kk][cc] = rb[t];
     }
     __syncthreads();
+    if (ib + kGemmK < i1) fetch(ib + kGemmK);
     acc.chunk(As, Bs);
     __syncthreads();
   }

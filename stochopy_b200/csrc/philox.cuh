@@ -102,15 +102,17 @@ __device__ __forceinline__ float fast_sqrt(float x) {
   return r;
 }
 __device__ __forceinline__ float unit_fraction(uint32_t w) { return __uint_as_float(0x3f800000u | (w & 0x007fffffu)); }
-__device__ __forceinline__ float radius_from(uint32_t w) {  // sqrt(-2 ln u), u = 2 - f
+__device__ __forceinline__ float radius_from(uint32_t w) {  // sqrt(-2 ln u), u = 2 - f; branch-free
   const float f = unit_fraction(w), x = f - 1.0f;
   const float series = x * (2.0f + x * (1.0f + x * (0.66666669f + 0.5f * x)));
   const float viaLog = -1.3862944f * __log2f(2.0f - f);
-  return fast_sqrt(x < 0.015625f ? series : viaLog);
+  float arg;
+  asm("slct.f32.f32 %0, %1, %2, %3;" : "=f"(arg) : "f"(viaLog), "f"(series), "f"(x - 0.015625f));  // x >= 2^-6 ? log : series
+  return fast_sqrt(arg);
 }
 __device__ __forceinline__ void normal_pair(uint32_t wr, uint32_t wa, float* z0, float* z1) {
   const float r = radius_from(wr);
-  const float a = 6.2831855f * (unit_fraction(wa) - 1.5f);  // [-pi, pi)
+  const float a = fmaf(unit_fraction(wa), 6.2831855f, -9.424778f);  // 2 pi (f - 1.5) in [-pi, pi)
   *z0 = r * __cosf(a);
   *z1 = r * __sinf(a);
 }

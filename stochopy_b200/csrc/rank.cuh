@@ -12,7 +12,8 @@
 // O(P log^2 c + P (P/c) log c) work instead of the P^2 of a counting rank: 32768 keys
 // take microseconds, which is what the CPSO restart (cpso/_cpso.py:420), the (mu, lambda)
 // weights (cmaes/_cmaes.py:272, vdcma/_vdcma.py:290) and NA's best cells (na/_na.py) need.
-// `gate` (optional): every kernel returns immediately unless *gate > 0.
+// `gate` (optional): every kernel returns immediately unless *gate > 0; `live` (optional): ... unless
+// *live == SP_RUNNING (the control block's status: generations enqueued behind a stop do nothing).
 #pragma once
 #include "common.cuh"
 
@@ -71,10 +72,13 @@ __device__ __forceinline__ RankItem64 rank_shfl(const RankItem64& v, int m) {
 template <typename T>
 __global__ void __launch_bounds__(kRankChunk / 2)
 rank_sort_kernel(const T* __restrict__ fit, int64_t P, int n, typename RankItem<T>::type* __restrict__ sorted,
-                 int32_t* __restrict__ rank, const int32_t* gate, int single) {
+                 int32_t* __restrict__ rank, const int32_t* gate, int single, const int32_t* live = nullptr) {
   using R = RankItem<T>;
   using I = typename R::type;
+  pdl_launch_dependents();  // no-ops unless launched with the programmatic-serialization attribute
+  pdl_wait();
   if (gate != nullptr && *gate <= 0) return;
+  if (live != nullptr && *reinterpret_cast<const volatile int32_t*>(live) != SP_RUNNING) return;
   __shared__ I s[kRankChunk];
   const int t = threadIdx.x;
   const int64_t base = (int64_t)blockIdx.x * n;
@@ -138,11 +142,14 @@ rank_sort_kernel(const T* __restrict__ fit, int64_t P, int n, typename RankItem<
 template <typename T>
 __global__ void __launch_bounds__(kRankChunk)
 rank_merge_kernel(const typename RankItem<T>::type* __restrict__ sorted, int64_t P, int C,
-                  int32_t* __restrict__ rank, const int32_t* gate) {
+                  int32_t* __restrict__ rank, const int32_t* gate, const int32_t* live = nullptr) {
   using R = RankItem<T>;
   using I = typename R::type;
   constexpr int n = kRankChunk;
+  pdl_launch_dependents();
+  pdl_wait();
   if (gate != nullptr && *gate <= 0) return;
+  if (live != nullptr && *reinterpret_cast<const volatile int32_t*>(live) != SP_RUNNING) return;
   __shared__ I s[2][n];
   const int ab = blockIdx.x, G = gridDim.y, t = threadIdx.x;
   const I me = sorted[(int64_t)ab * n + t];
@@ -189,15 +196,43 @@ inline cudaError_t rank_scratch(void** p, size_t bytes, cudaStream_t s) {
   return cudaMallocAsync(p, bytes, s);
 }
 
+// bytes of caller-provided scratch for rank_launch_ws (16-byte aligned)
+inline size_t rank_ws_bytes(int64_t P) { return (size_t)((P + kRankChunk - 1) / kRankChunk) * kRankChunk * 16; }
+
+// the same with caller-provided scratch and programmatic dependent launches: no pool traffic between
+// the kernels of a generation chain, and each kernel is scheduled while its predecessor drains
 template <typename T>
-inline cudaError_t rank_launch(const T* fit, int64_t P, int32_t* rank, const int32_t* gate, cudaStream_t s) {
+inline cudaError_t rank_launch_ws(const T* fit, int64_t P, int32_t* rank, void* ws, cudaStream_t s, const int32_t* live) {
+  using I = typename RankItem<T>::type;
+  const int32_t* gate = nullptr;
+  if (P <= kRankChunk) {
+    int n = 2;
+    while (n < P) n <<= 1;
+    int threads = n >> 1;
+    threads = threads < 32 ? 32 : threads;
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return launch_pdl(rank_sort_kernel<T>, dim3(1), dim3(threads), 0, s, true, fit, P, n, (I*)nullptr, rank, gate, 1, live);
+  }
+  const int n = kRankChunk;
+  const int C = (int)((P + n - 1) / n);
+  cudaError_t e = launch_pdl(rank_sort_kernel<T>, dim3(C), dim3(n / 2), 0, s, true, fit, P, n, (I*)ws, rank, gate, 0, live);
+  if (e != cudaSuccess) return e;
+  int G = (3 * sm_count() + C - 1) / C;  // about three CTAs per SM in all
+  G = G < 1 ? 1 : (G > C ? C : G);
+  g_launches.fetch_add(2, std::memory_order_relaxed);
+  return launch_pdl(rank_merge_kernel<T>, dim3((unsigned)C, (unsigned)G), dim3(n), 0, s, true, (const I*)ws, P, C, rank, gate, live);
+}
+
+template <typename T>
+inline cudaError_t rank_launch(const T* fit, int64_t P, int32_t* rank, const int32_t* gate, cudaStream_t s,
+                               const int32_t* live = nullptr) {
   using I = typename RankItem<T>::type;
   if (P <= kRankChunk) {
     int n = 2;
     while (n < P) n <<= 1;
     int threads = n >> 1;
     threads = threads < 32 ? 32 : threads;
-    rank_sort_kernel<T><<<1, threads, 0, s>>>(fit, P, n, nullptr, rank, gate, 1);
+    rank_sort_kernel<T><<<1, threads, 0, s>>>(fit, P, n, nullptr, rank, gate, 1, live);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return cudaGetLastError();
   }
@@ -206,10 +241,10 @@ inline cudaError_t rank_launch(const T* fit, int64_t P, int32_t* rank, const int
   void* ws = nullptr;
   cudaError_t e = rank_scratch(&ws, (size_t)C * n * sizeof(I), s);
   if (e != cudaSuccess) return e;
-  rank_sort_kernel<T><<<C, n / 2, 0, s>>>(fit, P, n, (I*)ws, rank, gate, 0);
+  rank_sort_kernel<T><<<C, n / 2, 0, s>>>(fit, P, n, (I*)ws, rank, gate, 0, live);
   int G = (3 * sm_count() + C - 1) / C;  // about three CTAs per SM in all
   G = G < 1 ? 1 : (G > C ? C : G);
-  rank_merge_kernel<T><<<dim3((unsigned)C, (unsigned)G), n, 0, s>>>((const I*)ws, P, C, rank, gate);
+  rank_merge_kernel<T><<<dim3((unsigned)C, (unsigned)G), n, 0, s>>>((const I*)ws, P, C, rank, gate, live);
   e = cudaGetLastError();
   g_launches.fetch_add(2, std::memory_order_relaxed);
   cudaError_t f = cudaFreeAsync(ws, s);

@@ -11,8 +11,10 @@ namespace sp {
 template <typename T, int CH, int LPR>
 __global__ void __launch_bounds__(kThreads)
 eval_kernel(int objective, const T* __restrict__ X, int64_t P, int N, int64_t ld, const T* __restrict__ scale,
-            const T* __restrict__ shift, T* __restrict__ f, int clip) {
+            const T* __restrict__ shift, T* __restrict__ f, int clip, const int32_t* live) {
   using TL = Tile<T, CH, LPR>;
+  // `live` (optional): the control block's status -- generations enqueued behind a stop do nothing
+  if (live != nullptr && *reinterpret_cast<const volatile int32_t*>(live) != SP_RUNNING) return;
   constexpr int VEC = Num<T>::VEC;
   const int lane = threadIdx.x & 31, l = lane % LPR, sub = lane / LPR;
   const int64_t warp = (int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
@@ -47,7 +49,7 @@ eval_kernel(int objective, const T* __restrict__ X, int64_t P, int N, int64_t ld
 
 template <typename T>
 inline int eval_launch(int objective, const void* X, int64_t P, int N, int64_t ld, const void* scale,
-                       const void* shift, void* f, int clip, cudaStream_t s) {
+                       const void* shift, void* f, int clip, cudaStream_t s, const int32_t* live = nullptr) {
   Shape sh;
   if (!pick_shape(N, Num<T>::VEC, &sh)) {
     set_error("sp_eval: ndim %d exceeds the compiled row shapes", N);
@@ -56,7 +58,7 @@ inline int eval_launch(int objective, const void* X, int64_t P, int N, int64_t l
   const int grid = grid_for_rows(P, sh.lpr, 8);
 #define SP_CALL(TT, C, L)                                                                                     \
   eval_kernel<TT, C, L><<<grid, kThreads, 0, s>>>(objective, (const TT*)X, P, N, ld, (const TT*)scale,        \
-                                                  (const TT*)shift, (TT*)f, clip)
+                                                  (const TT*)shift, (TT*)f, clip, live)
   SP_DISPATCH_SHAPE(T, sh, SP_CALL);
 #undef SP_CALL
   SP_CHECK_LAUNCH();

@@ -17,6 +17,7 @@
 namespace sp {
 
 constexpr int kVdChunks = 256;
+constexpr int kVdUpMax = 512;  // CTAs of vd_update_kernel: 3 N / 32 outputs each, N <= 2048 -> <= 192
 
 template <typename T>
 struct VdPtrs {
@@ -38,6 +39,15 @@ struct VdPtrs {
   __host__ __device__ T* fuse_a() const { return sums() + 4 * (size_t)N; }            // N + 4
   __host__ __device__ T* fuse_b() const { return fuse_a() + N + 4; }                  // N + 4
   __host__ __device__ T* hpart() const { return fuse_b() + N + 4; }                   // kVdChunks (vd_wsum's scalar partials)
+  // per-CTA scan results of vd_update_kernel's phase 1: (min f, max f, row of rank 0 or -1) as doubles,
+  // kVdUpMax CTAs; the slices before it hold an even number of scalars past kVdChunks * 4 * N + ... only
+  // when N and P are even, so the address is rounded up to 8 bytes
+  __host__ __device__ double* fpart() const {
+    return reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(hpart() + kVdChunks) + 7) & ~(uintptr_t)7);
+  }
+  __host__ __device__ unsigned char* rank_ws() const {
+    return reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(fpart() + 3 * kVdUpMax) + 15) & ~(uintptr_t)15);
+  }
 };
 
 // ctrl->aux: [0] |v|^2, [1] |v|
@@ -116,13 +126,15 @@ vd_inject_kernel(const VdPtrs<T> a) {
 // objective then sees clip(xmean + sigma y, -1, 1) xscale + xshift, cmaes/_constraints.py:30-32).
 template <typename T, int CH, int LPR, bool FULL, bool CLIP>
 __global__ void __launch_bounds__(kThreads, (CH * (int)sizeof(T) <= 32 ? 3 : 2))
-vd_sample_eval_kernel(const VdPtrs<T> a) {
+vd_sample_eval_kernel(const VdPtrs<T> a, const PhiloxKeys keys) {
   using TL = Tile<T, CH, LPR>;
   using V = typename Num<T>::vec_t;
   constexpr int VEC = Num<T>::VEC;
   constexpr int COLS = TL::COLS;
   __shared__ __align__(16) T s_vn[COLS], s_dv[COLS], s_fa[COLS], s_fb[COLS];
   const sp_es_ctrl* c = a.ctrl;
+  pdl_launch_dependents();
+  pdl_wait();  // the previous generation's update kernel wrote everything read below
   if (!es_running(c)) return;
   const int lane = threadIdx.x & 31, l = lane % LPR, sub = lane / LPR;
   const int64_t warp = (int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
@@ -184,7 +196,7 @@ vd_sample_eval_kernel(const VdPtrs<T> a) {
       const int j0 = TL::col(cc, l, 0);
       if (!a.host_z) {
         T z[VEC];
-        if (FULL || j0 < N) normal_block(philox4x32((uint32_t)(j0 / VEC), (uint32_t)row, (uint32_t)a.it, kEsZ, a.seed), z);
+        if (FULL || j0 < N) normal_block(philox4x32_keyed((uint32_t)(j0 / VEC), (uint32_t)row, (uint32_t)a.it, kEsZ, keys), z);
 #pragma unroll
         for (int e = 0; e < VEC; ++e) y.v[cc][e] = (FULL || j0 + e < N) ? z[e] : T(0);
       }
@@ -273,6 +285,8 @@ __global__ void __launch_bounds__(kWsThreads, 2)
 vd_wsum_kernel(const VdPtrs<T> a) {
   using V = typename Num<T>::vec_t;
   constexpr int VEC = Num<T>::VEC;
+  pdl_launch_dependents();
+  pdl_wait();
   if (!es_running(a.ctrl)) return;
   __shared__ int s_row[kWsTile];
   __shared__ T s_w[kWsTile], s_wyn[kWsTile];
@@ -293,8 +307,9 @@ vd_wsum_kernel(const VdPtrs<T> a) {
     __syncthreads();
     const int64_t i = t0 + tid;
     const int r = i < i1 ? a.rank[i] : a.mu;
+    const T yn = i < i1 ? a.yvn[i] : T(0);  // in flight together with the rank
     const bool sel = r < a.mu;
-    const T w = sel ? a.weights[r] : T(0), yn = sel ? a.yvn[i] : T(0);
+    const T w = sel ? a.weights[r] : T(0);
     const unsigned m = __ballot_sync(0xffffffffu, sel);
     T h = w * (T(0.5) * (yn * yn + T(1) + nv2t));  // 0 for the rows not selected
 #pragma unroll
@@ -368,11 +383,13 @@ vd_wsum_kernel(const VdPtrs<T> a) {
 // reduction of the chunk partials of vd_wsum.
 //   phase 1 (every CTA of the grid): sums[q][n] = sum over the chunks of part[chunk][q][n] in a fixed
 //     order -- a CTA owns kUpOut outputs, 8 thread groups take every 8th chunk with all their loads in
-//     flight at once, then the 8 group sums are added in order; the LAST CTA to finish goes on;
-//   phase 2 (that one CTA, 1024 threads, one column each for N <= 1024): the N-vectors live in
-//     registers and every dependent step is one combined block reduction; the scans over the
-//     population (row of rank 0, min / max fitness for the ladder) are unrolled so their loads overlap.
-constexpr int kUpThreads = 1024, kUpOut = kUpThreads / 8;
+//     flight at once, then the 8 group sums are added in order.  Every CTA also scans a slice of the
+//     population for the row of rank 0 and the fitness range the ladder needs.  The LAST CTA to finish
+//     goes on;
+//   phase 2 (that one CTA): the N-vectors live in registers (kVdNpt columns per thread; the scalar
+//     fp64 algebra between the reductions is replicated per warp, so few warps) and every dependent
+//     step is one combined block reduction.
+constexpr int kUpThreads = 256, kUpOut = kUpThreads / 8;
 template <typename T, int kVdNpt>
 __global__ void __launch_bounds__(kUpThreads)
 vd_update_kernel(const VdPtrs<T> a) {
@@ -380,6 +397,8 @@ vd_update_kernel(const VdPtrs<T> a) {
   __shared__ T s_p[8][kUpOut];
   __shared__ int s_best;
   __shared__ bool s_last;
+  pdl_launch_dependents();
+  pdl_wait();
   sp_es_ctrl* c = a.ctrl;
   if (!es_running(c)) return;
   const int N = a.N, tid = threadIdx.x, nt = blockDim.x;
@@ -388,21 +407,38 @@ vd_update_kernel(const VdPtrs<T> a) {
     const int e = blockIdx.x * kUpOut + o;
     T acc = 0;
     if (e < 3 * N) {
-      const T* p = a.part() + e;
+      const T* p = a.part() + e + (size_t)g * 3 * N;
+      const size_t step = (size_t)8 * 3 * N;
       T v[kVdChunks / 8];
 #pragma unroll
-      for (int k = 0; k < kVdChunks / 8; ++k) v[k] = (g + 8 * k < a.chunks) ? __ldcg(p + (size_t)(g + 8 * k) * 3 * N) : T(0);
+      for (int k = 0; k < kVdChunks / 8; ++k) v[k] = (g + 8 * k < a.chunks) ? __ldcg(p + k * step) : T(0);
 #pragma unroll
       for (int k = 0; k < kVdChunks / 8; ++k) acc += v[k];
     }
+    // this CTA's slice of the population: row of rank 0 (ties by index: the stable rank's first minimum)
+    // and min / max fitness
+    const int64_t per = (a.P + gridDim.x - 1) / gridDim.x;
+    const int64_t i0 = blockIdx.x * per, i1 = (i0 + per < a.P) ? i0 + per : a.P;
+    double ext[3] = {1.0 / 0.0, -1.0 / 0.0, -1.0};  // min f, max f, best row (or -1)
+    for (int64_t i = i0 + tid; i < i1; i += nt) {
+      const int rk = a.rank[i];
+      const double f = (double)a.arfit[i];
+      ext[0] = fmin(ext[0], f);
+      ext[1] = fmax(ext[1], f);
+      if (rk == 0) ext[2] = (double)i;
+    }
     s_p[g][o] = acc;
-    __syncthreads();
+    {
+      const int op[3] = {RED_MIN, RED_MAX, RED_MAX};
+      block_reduce<3>(ext, op, s_red);  // (barriers inside also publish s_p)
+    }
     if (g == 0 && e < 3 * N) {
       T tot = s_p[0][o];
 #pragma unroll
       for (int k = 1; k < 8; ++k) tot += s_p[k][o];
       a.sums()[e] = tot;
     }
+    if (tid < 3) a.fpart()[3 * blockIdx.x + tid] = ext[tid];
     __threadfence();
     __syncthreads();
     if (tid == 0) {
@@ -428,28 +464,14 @@ vd_update_kernel(const VdPtrs<T> a) {
     xm[k] = a.xmean[m], pc[k] = a.pc[m], vnT[k] = a.vn[m], dv[k] = a.dvec[m], vv[k] = a.vvec[m];
   }
   const int r0 = a.rank[0], r1 = a.P > 1 ? a.rank[1] : 0;
-  // row of rank 0 (ties by index: the stable rank's first minimum) and the fitness range of the ladder
+  // the per-CTA scan results of phase 1
   double fext[2] = {1.0 / 0.0, -1.0 / 0.0};
-  {
-    int best = -1;
-    constexpr int U = 4;
-    for (int64_t i0 = tid; i0 < a.P; i0 += (int64_t)U * nt) {
-      int rk[U];
-      T fv[U];
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int64_t i = i0 + (int64_t)u * nt;
-        rk[u] = i < a.P ? a.rank[i] : -1;
-        fv[u] = i < a.P ? a.arfit[i] : a.arfit[0];
-      }
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        if (rk[u] == 0) best = (int)(i0 + (int64_t)u * nt);
-        fext[0] = fmin(fext[0], (double)fv[u]);
-        fext[1] = fmax(fext[1], (double)fv[u]);
-      }
-    }
-    if (best >= 0) s_best = best;
+  for (int b = tid; b < (int)gridDim.x; b += nt) {
+    const double* fp = a.fpart() + 3 * b;
+    fext[0] = fmin(fext[0], __ldcg(fp));
+    fext[1] = fmax(fext[1], __ldcg(fp + 1));
+    const double row = __ldcg(fp + 2);
+    if (row >= 0.0) s_best = (int)row;
   }
   // sigma from the rank gap of the injected pair, _vdcma.py:299-307
   bool hsig = true;
@@ -684,16 +706,18 @@ static int vd_sample(const sp_vd_state* st, int it, int evaluate, cudaStream_t s
   // fixed-shape instantiations only for full-warp rows (the large-N case that matters)
   const bool full = sh.lpr == 32 && st->N == sh.ch * 32 * Num<T>::VEC && st->ld == st->N;
   const bool clip = st->constraint == SP_CONS_PENALIZE;
-#define SP_CALL(TT, C, L)                                                                         \
-  do {                                                                                            \
-    if (L == 32 && full) {                                                                        \
-      if (clip) vd_sample_eval_kernel<TT, C, (L == 32 ? 32 : 32), true, true><<<grid, kThreads, 0, s>>>(a);  \
-      else vd_sample_eval_kernel<TT, C, (L == 32 ? 32 : 32), true, false><<<grid, kThreads, 0, s>>>(a);      \
-    } else if (clip) {                                                                            \
-      vd_sample_eval_kernel<TT, C, L, false, true><<<grid, kThreads, 0, s>>>(a);                  \
-    } else {                                                                                      \
-      vd_sample_eval_kernel<TT, C, L, false, false><<<grid, kThreads, 0, s>>>(a);                 \
-    }                                                                                             \
+  const PhiloxKeys keys = philox_keys(st->seed);
+  const bool pdl = !st->host_z;  // with host draws the caller's copies sit between the generations anyway
+#define SP_CALL(TT, C, L)                                                                                         \
+  do {                                                                                                            \
+    if (L == 32 && full) {                                                                                        \
+      if (clip) launch_pdl(vd_sample_eval_kernel<TT, C, 32, true, true>, dim3(grid), dim3(kThreads), 0, s, pdl, a, keys);   \
+      else launch_pdl(vd_sample_eval_kernel<TT, C, 32, true, false>, dim3(grid), dim3(kThreads), 0, s, pdl, a, keys);       \
+    } else if (clip) {                                                                                            \
+      launch_pdl(vd_sample_eval_kernel<TT, C, L, false, true>, dim3(grid), dim3(kThreads), 0, s, pdl, a, keys);   \
+    } else {                                                                                                      \
+      launch_pdl(vd_sample_eval_kernel<TT, C, L, false, false>, dim3(grid), dim3(kThreads), 0, s, pdl, a, keys);  \
+    }                                                                                                             \
   } while (0)
   SP_DISPATCH_SHAPE(T, sh, SP_CALL);
 #undef SP_CALL
@@ -707,7 +731,7 @@ static int vd_update(const sp_vd_state* st, int it, cudaStream_t s) {
   const int64_t P = st->P;
   const int N = st->N;
   if (st->constraint == SP_CONS_PENALIZE) {
-    if (rank_launch<T>(a.arfit, P, a.rank, nullptr, s) != cudaSuccess) return SP_ERR_CUDA;
+    if (rank_launch<T>(a.arfit, P, a.rank, nullptr, s, &st->ctrl->base.status) != cudaSuccess) return SP_ERR_CUDA;
     scatter_sorted_kernel<T><<<cdiv(P, 256) < 1024 ? cdiv(P, 256) : 1024, 256, 0, s>>>(a.arfit, a.rank, a.sorted(), P, st->ctrl);
     SP_CHECK_LAUNCH();
     vd_penalty_state_kernel<T><<<1, 256, 0, s>>>(a);
@@ -716,14 +740,18 @@ static int vd_update(const sp_vd_state* st, int it, cudaStream_t s) {
         a.arx, a.coef(), a.arfit, P, N, st->ld, st->ctrl);
     SP_CHECK_LAUNCH();
   }
-  if (rank_launch<T>(a.arfit, P, a.rank, nullptr, s) != cudaSuccess) return SP_ERR_CUDA;
-  vd_wsum_kernel<T><<<dim3(cdiv(st->ld, 256 * Num<T>::VEC), a.chunks), kWsThreads, 0, s>>>(a);
+  if (rank_launch_ws<T>(a.arfit, P, a.rank, a.rank_ws(), s, &st->ctrl->base.status) != cudaSuccess) return SP_ERR_CUDA;
+  launch_pdl(vd_wsum_kernel<T>, dim3(cdiv(st->ld, 256 * Num<T>::VEC), a.chunks), dim3(kWsThreads), 0, s, true, a);
   SP_CHECK_LAUNCH();
   // chunk partials -> sums, then (last CTA) the update itself; also refreshes vn / diagC / fuse_a / fuse_b
   // (and dy) for the next generation
   const int ups = cdiv(3 * (int64_t)N, kUpOut);
-  if (N <= kUpThreads) vd_update_kernel<T, 1><<<ups, kUpThreads, 0, s>>>(a);
-  else vd_update_kernel<T, 2><<<ups, kUpThreads, 0, s>>>(a);
+  cudaError_t le;
+  if (N <= 256) le = launch_pdl(vd_update_kernel<T, 1>, dim3(ups), dim3(kUpThreads), 0, s, true, a);
+  else if (N <= 512) le = launch_pdl(vd_update_kernel<T, 2>, dim3(ups), dim3(kUpThreads), 0, s, true, a);
+  else if (N <= 1024) le = launch_pdl(vd_update_kernel<T, 4>, dim3(ups), dim3(kUpThreads), 0, s, true, a);
+  else le = launch_pdl(vd_update_kernel<T, 8>, dim3(ups), dim3(kUpThreads), 0, s, true, a);
+  (void)le;
   SP_CHECK_LAUNCH();
   return SP_OK;
 }
@@ -750,7 +778,7 @@ using namespace sp;
 
 extern "C" {
 
-int64_t sp_vd_work_scalars(int N, int64_t P) { return (int64_t)kVdChunks * 4 * N + 15LL * N + 8 + P + kVdChunks; }
+int64_t sp_vd_work_scalars(int N, int64_t P) { return (int64_t)kVdChunks * 4 * N + 15LL * N + 8 + P + kVdChunks + 2 + 2 * 3 * kVdUpMax + 4 * (P + 2 * kRankChunk); }
 
 int sp_vd_refresh(const sp_vd_state* st, void* stream) {
   int rc = vd_check(st, 1);

@@ -130,7 +130,7 @@ def test_cmaes_generation_steps_match_oracle(dtype, N, P, fun):
         Cs, B_o, D_o, inv_o = ocma.decompose(C)
         chk("C", s["C"], Cs, t_c)
         assert np.array_equal(s["C"], s["C"].T)  # symmetrised from the upper triangle (_cmaes.py:303)
-        chk("D", s["D"], D_o, 1e-9 if f64 else 2e-5)
+        chk("D", s["D"], D_o, 1e-9 if f64 else 1e-4)  # sqrt of fp32 Jacobi eigenvalues (~N eps)
         assert np.all(np.diff(s["D"]) >= 0)
         chk("BD2Bt", (s["B"] * s["D"] ** 2) @ s["B"].T, s["C"], t_i)
         chk("BtB", s["B"].T @ s["B"], np.eye(N), t_i)
