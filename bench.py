@@ -10,19 +10,34 @@ launch of the fused DE kernel over the whole population (65536 evaluations).
           the launching stream, L2 flushed (256 MiB write) before every generation
           so the population comes from HBM (the 2 x 32 MiB ping-pong state would
           otherwise live in the 126 MB L2); `value_l2_resident` is the same loop
-          without the flush, i.e. what an actual run sees.
-  e2e     the same metric through the public API: minimize(fun, bounds, x0=<host
-          array>, method="de", options=...) -- host->device copy of x0, K
+          without the flush, i.e. what an actual run sees; `value_kernel_only` subtracts
+          what an empty event pair costs on this stream (launch / record overhead that
+          `value` includes in every step).
+  e2e     the same metric through the public API: minimize(fun, bounds, x0=<host array in
+          page-locked memory>, method="de", options=...) -- host->device copy of x0, K
           generations with device-side termination, device->host result.
   roofline  the fused DE generation kernel against the measured HBM peak.
-  cpu_baseline  the oracle port of the reference algorithm on this box's host cores.
+  cpu_baseline  the UNMODIFIED reference (baseline/_ref, installed by baseline/fetch_ref.sh)
+          on this box's host cores: stochopy.optimize.minimize(method="de",
+          updating="deferred") on a population sample, plus the raw fun(x) loop.
+  configs (N = 1) the other BASELINE.json configurations through the public API (C2 DE
+          Rastrigin, C3 PSO / CPSO, C4 CMA-ES fp64, C5 VD-CMA): per-generation time by the
+          slope between a short and a long run.
 
 N > 1 (torchrun): one independent seed per GPU (weak scaling), no data-path
 collective; barrier + max-over-ranks timing; value = total evals / s.
+Additionally (extra keys; SURVEY.md 8e second row, BASELINE configs 3 and 5):
+  c3_sharded   ONE CPSO swarm (Styblinski-Tang ndim=64, popsize=32768, fp32) row-sharded over
+          the N ranks: per-generation time with the exchange fused into the kernels over
+          NVLink peer memory ("peer") and with one host-driven NCCL all-gather per generation
+          ("nccl", the baseline), bitwise comparison with the single-GPU run; the same at
+          popsize=262144 (strong scaling);
+  c5_seeds     VD-CMA Ackley ndim=1024, popsize=16384, fp32, 8 independent seeds per GPU.
+The extras run under a watchdog: whatever happens to them, the headline line is printed.
 
---impl reference: the reference's CPU algorithm (oracle port; the reference is pure
-Python and cannot run DE at P=65536 -- its donor index matrix is O(P^2)) on a bounded
-population sample, rank 0 only.
+--impl reference: the reference's own CPU implementation (see cpu_baseline; serial, loky and
+threading legs, population samples of 4096 and 8192 rows -- the reference's DE draws a
+(P-1) x P donor index matrix per generation, 34 GB at P=65536), rank 0 only.
 """
 import argparse
 import ctypes as C
@@ -43,6 +58,7 @@ UNIT = "evals/s"
 P, N = 65536, 128
 BOUND = 5.12
 ALG_BYTES_PER_EVAL = (2 + 2) * N * 4 + 3 * 4  # (k+2) rows + 3 scalars, k=2 donors = 2060
+OFF = dict(xtol=-1.0, ftol=-1.0e300)
 
 
 def peaks():
@@ -178,6 +194,135 @@ def build_state(eng, L, x0, seed, maxiter):
     return st, keep
 
 
+def slope_us(run, a, b, repeat=2):
+    """Per-generation time (us) of `run(maxiter)` by the slope between a short and a long run
+    (the fixed set-up cost cancels); returns (us per generation, fixed ms)."""
+    import torch
+
+    def timed(it):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        run(it)
+        torch.cuda.synchronize()
+        return time.perf_counter() - t0
+
+    run(min(a, 5))
+    ta = min(timed(a) for _ in range(repeat))
+    tb = min(timed(b) for _ in range(repeat))
+    per = (tb - ta) / (b - a)
+    return per * 1e6, (ta - a * per) * 1e3
+
+
+def other_configs(sb):
+    """BASELINE.json configs[1..4] on ONE GPU through the public API (device-side termination off)."""
+    out = {}
+    peak, _ = peaks()
+
+    def rec(name, p, run, a, b, alg_bytes=None, note=None):
+        us, fixed = slope_us(run, a, b)
+        d = {"us_per_generation": us, "evals_per_s": p / (us * 1e-6), "fixed_ms": fixed}
+        if alg_bytes is not None:
+            d["algorithmic_bytes_per_eval"] = alg_bytes
+            d["algorithmic_gb_s"] = alg_bytes * p / (us * 1e-6) / 1e9
+            d["roofline_frac"] = d["algorithmic_gb_s"] / peak
+        if note:
+            d["note"] = note
+        out[name] = d
+
+    b128, b64 = [[-BOUND, BOUND]] * 128, [[-BOUND, BOUND]] * 64
+
+    def mk(fun, bounds, method, **o):
+        return lambda it: sb.optimize.minimize(fun, bounds, method=method, options=dict(o, maxiter=it, seed=0, **OFF))
+
+    rec("c2_de_best1bin_rastrigin_n128_p65536_f32", 65536,
+        mk(sb.factory.rastrigin, b128, "de", popsize=65536, dtype="float32", strategy="best1bin", updating="deferred"),
+        50, 450, alg_bytes=2060, note="the 2 x 32 MiB state stays in the 126 MB L2 in a real run")
+    rec("c3_pso_styblinski_n64_p32768_f32", 32768,
+        mk(sb.factory.styblinski_tang, b64, "pso", popsize=32768, dtype="float32", updating="deferred"), 50, 450,
+        alg_bytes=1292)
+    rec("c3_cpso_styblinski_n64_p32768_f32", 32768,
+        mk(sb.factory.styblinski_tang, b64, "cpso", popsize=32768, dtype="float32", updating="deferred",
+           competitivity=1.0), 50, 450, alg_bytes=1292)
+    rec("c4_cmaes_rosenbrock_n256_p4096_f64", 4096,
+        mk(sb.factory.rosenbrock, [[-BOUND, BOUND]] * 256, "cmaes", popsize=4096), 10, 40,
+        note="fp64; 0.99 GFLOP per generation incl. eigh (SURVEY.md 8d); latency bound")
+    rec("c5_vdcma_ackley_n1024_p16384_f32", 16384,
+        mk(sb.factory.ackley, [[-BOUND, BOUND]] * 1024, "vdcma", popsize=16384, dtype="float32"), 20, 120,
+        alg_bytes=6152)
+    return out
+
+
+def sharded_swarm(sb, dist, world, popsize, gens=(100, 400), nccl=True):
+    """ONE CPSO swarm row-sharded over the ranks (parallel.cpso_sharded).  Per-generation time =
+    slope between two run lengths (the IPC mailbox set-up is a fixed cost), max over ranks."""
+    import torch
+
+    from stochopy_b200 import parallel
+
+    b64 = [[-BOUND, BOUND]] * 64
+    base = dict(popsize=popsize, seed=0, dtype="float32", competitivity=1.0, **OFF)
+    dev = torch.device("cuda", torch.cuda.current_device())
+
+    def timed(exchange, it):
+        dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        r = parallel.cpso_sharded(sb.factory.styblinski_tang, b64, maxiter=it, exchange=exchange, **base)
+        torch.cuda.synchronize()
+        t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), r
+
+    out = {"popsize": popsize, "ndim": 64, "rows_per_gpu": popsize // world}
+    res = None
+    for exchange in (("peer", "nccl") if nccl else ("peer",)):
+        timed(exchange, 8)
+        ta, _ = timed(exchange, gens[0])
+        tb, r = timed(exchange, gens[1])
+        per = (tb - ta) / (gens[1] - gens[0])
+        out[f"us_per_gen_{exchange}"] = per * 1e6
+        out[f"fixed_ms_{exchange}"] = (ta - gens[0] * per) * 1e3
+        if exchange == "peer":
+            res = r
+            out["evals_per_s"] = popsize / per
+            out["evals_per_s_incl_setup"] = popsize * (gens[1] - 1) / tb
+    # the same swarm on ONE GPU (every rank runs it on its own GPU: same work, no interference)
+    def run1(it):
+        return sb.optimize.minimize(sb.factory.styblinski_tang, b64, method="cpso",
+                                    options=dict(base, maxiter=it, updating="deferred"))
+
+    us1, _ = slope_us(run1, gens[0], gens[1], repeat=1)
+    r1 = run1(gens[1])
+    out["us_per_gen_1gpu"] = us1
+    out["strong_scaling_efficiency"] = us1 / (world * out["us_per_gen_peer"])
+    same = bool(np.array_equal(r1.x, res.x) and r1.fun == res.fun and r1.nit == res.nit and r1.status == res.status)
+    t = torch.tensor([1 if same else 0], dtype=torch.int32, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    out["bitwise_equal_to_1gpu"] = bool(t.item())
+    return out
+
+
+def vdcma_seeds(sb, dist, world, per_gpu=8, gens=40):
+    """BASELINE configs[4]: independent VD-CMA seeds, `per_gpu` per GPU, no collective in the loop."""
+    import torch
+
+    from stochopy_b200 import parallel
+
+    b = [[-BOUND, BOUND]] * 1024
+    o = dict(popsize=16384, dtype="float32", **OFF)
+    parallel.minimize_seeds(sb.factory.ackley, b, list(range(world)), method="vdcma", options=dict(o, maxiter=3))
+    dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    seeds = list(range(per_gpu * world))
+    r = parallel.minimize_seeds(sb.factory.ackley, b, seeds, method="vdcma", options=dict(o, maxiter=gens))
+    torch.cuda.synchronize()
+    dist.barrier()
+    dt = time.perf_counter() - t0
+    return {"seeds": len(seeds), "generations": gens, "popsize": 16384, "ndim": 1024, "seconds": dt,
+            "evals_per_s": len(seeds) * gens * 16384 / dt, "best_fun": float(r["fun"])}
+
+
 def our_arm(args):
     import torch
     import torch.distributed as dist
@@ -193,11 +338,13 @@ def our_arm(args):
     from stochopy_b200 import _lib as L
     from stochopy_b200.optimize._common import Engine
 
+    nvtx = torch.cuda.nvtx
     eng = Engine("float32")
     K, W = args.steps, args.warmup
     seed = 1000 + rank  # one independent seed per GPU
     rs = np.random.RandomState(seed)
-    x0 = rs.uniform(-BOUND, BOUND, (P, N)).astype(np.float32)
+    x0_pin = torch.from_numpy(rs.uniform(-BOUND, BOUND, (P, N)).astype(np.float32)).pin_memory()
+    x0 = x0_pin.numpy()  # host buffer in page-locked memory: what minimize() is handed in the e2e leg
     st, keep = build_state(eng, L, x0, seed, 2 * (K + W) + 10)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=eng.device)
 
@@ -206,24 +353,28 @@ def our_arm(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def max_over_ranks(ms):
+    def max_over_ranks(v):
         if world == 1:
-            return ms
-        t = torch.tensor([ms], dtype=torch.float64, device=eng.device)
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device=eng.device)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
     it = 2
+    nvtx.range_push("warmup")
     for _ in range(max(W, 3)):  # warm-up
         flush.fill_(1)
         L.call("sp_de_generation", C.byref(st), it, eng.stream)
         it += 1
+    nvtx.range_pop()
 
     # (1) value: HBM-cold generations, one event pair per generation
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    ev0 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
     barrier()
     launches0 = L.launch_count()
     with ClockSampler(local) as clocks:
+        nvtx.range_push("timed: HBM-cold generations")
         wall0 = time.perf_counter()
         for k in range(K):
             flush.fill_(k & 1)
@@ -234,35 +385,45 @@ def our_arm(args):
             ev[k][1].record()
             it += 1
         barrier()
+        nvtx.range_pop()
         wall_cold = time.perf_counter() - wall0
         launches = L.launch_count() - launches0
         cold_ms = max_over_ranks(sum(a.elapsed_time(b) for a, b in ev))
+        # what an event pair with nothing between it costs on this stream (inside every step of `value`)
+        for a, b in ev0:
+            flush[: 1 << 20].fill_(0)
+            a.record()
+            b.record()
+        torch.cuda.synchronize()
+        empty_ms = sum(a.elapsed_time(b) for a, b in ev0)
 
         # (2) the same loop as a real run sees it: no flush, state stays in L2
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
+        nvtx.range_push("timed: L2-resident run")
         s.record()
         L.call("sp_de_run", C.byref(st), it, K, eng.stream)
         e.record()
         barrier()
+        nvtx.range_pop()
         it += K
         warm_ms = max_over_ranks(s.elapsed_time(e))
 
-        # (3) e2e through the public API with host buffers
-        x0_64 = x0.astype(np.float64)
+        # (3) e2e through the public API with host buffers (x0 in page-locked memory)
         opts = dict(maxiter=K + 1, popsize=P, mutation=0.5, recombination=0.9, strategy="best1bin", seed=seed,
-                    xtol=-1.0, ftol=-1.0e300, updating="deferred", dtype="float32")
+                    updating="deferred", dtype="float32", **OFF)
         sb.optimize.minimize(sb.factory.rosenbrock, [[-BOUND, BOUND]] * N, x0=x0, method="de",
                              options=dict(opts, maxiter=max(W, 3) + 1))  # warm-up call
-        barrier()
-        t0 = time.perf_counter()
-        res = sb.optimize.minimize(sb.factory.rosenbrock, [[-BOUND, BOUND]] * N, x0=x0, method="de", options=opts)
-        torch.cuda.synchronize()
-        e2e_s = time.perf_counter() - t0
-        if world > 1:
-            t = torch.tensor([e2e_s], dtype=torch.float64, device=eng.device)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            e2e_s = float(t.item())
+        e2e_s = 1e30
+        for _ in range(3):
+            barrier()
+            nvtx.range_push("timed: e2e minimize()")
+            t0 = time.perf_counter()
+            res = sb.optimize.minimize(sb.factory.rosenbrock, [[-BOUND, BOUND]] * N, x0=x0, method="de", options=opts)
+            torch.cuda.synchronize()
+            e2e_s = min(e2e_s, time.perf_counter() - t0)
+            nvtx.range_pop()
+        e2e_s = max_over_ranks(e2e_s)
     assert res.nit == K + 1 and res.status == -1, (res.nit, res.status)
     c = eng.read_ctrl(keep[6])
     assert c.status == L.SP_RUNNING and c.nit == it - 1, (c.status, c.nit, it)
@@ -274,11 +435,13 @@ def our_arm(args):
         dist.all_reduce(t, op=dist.ReduceOp.MIN)
         best_fun = float(t.item())
 
+    line = None
     if rank == 0:
         peak, peak_src = peaks()
         per_launch_s = cold_ms * 1e-3 / K
         achieved = ALG_BYTES_PER_EVAL * P / per_launch_s / 1e9
         value = world * P * K / (cold_ms * 1e-3)
+        kern_ms = max(cold_ms - empty_ms, 1e-6)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": max(W, 3),
             "ms_per_step": cold_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -292,22 +455,70 @@ def our_arm(args):
                        "best_fun_over_seeds": best_fun},
             "value_l2_resident": world * P * K / (warm_ms * 1e-3),
             "ms_per_step_l2_resident": warm_ms / K,
+            "value_kernel_only": world * P * K / (kern_ms * 1e-3),
+            "ms_per_step_kernel_only": kern_ms / K,
+            "event_pair_overhead_us": empty_ms / K * 1e3,
             "wall_s_timed_loop": wall_cold,
             "e2e": {"value": world * P * K / e2e_s, "unit": UNIT, "h2d_bytes_per_step": x0.nbytes / K,
-                    "d2h_bytes_per_step": (N * 4 + 64 * (K // 64 + 2)) / K, "seconds": e2e_s,
-                    "call": "stochopy_b200.optimize.minimize(rosenbrock, bounds, x0=<host fp32 array>, method='de')"},
+                    "d2h_bytes_per_step": (N * 4 + 64 * (K // 64 + 2)) / K, "seconds": e2e_s, "best_of": 3,
+                    "call": "stochopy_b200.optimize.minimize(rosenbrock, bounds, x0=<host fp32 array, page-locked>, "
+                            "method='de')"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic_from_profile(), "kernel": "de_pool_kernel<float,CH=1,best1bin,FULL,PLAIN>",
                          "algorithmic_bytes_per_launch": ALG_BYTES_PER_EVAL * P, "peak_source": peak_src,
-                         "launch_us": per_launch_s * 1e6},
+                         "launch_us": per_launch_s * 1e6,
+                         "frac_kernel_only": ALG_BYTES_PER_EVAL * P / (kern_ms * 1e-3 / K) / 1e9 / peak},
             "clocks": clocks.summary(),
         }
-        if world == 1 and not args.no_cpu:
-            line["cpu_baseline"] = cpu_baseline_block(cpu_legs(12, 1, full=False))
-        print(json.dumps(line), flush=True)
+
+    # ---- extras, bounded by a watchdog: the headline line is printed whatever happens to them -----
+    done = threading.Event()
+
+    def emit(extra_error=None):
+        if rank == 0 and not done.is_set():
+            done.set()
+            if extra_error:
+                line["extras_error"] = extra_error
+            print(json.dumps(line), flush=True)
+
+    def watchdog():
+        emit("extras did not finish within the time limit")
+        os._exit(0)
+
+    if not args.no_extras:
+        timer = threading.Timer(args.extras_timeout, watchdog)
+        timer.daemon = True
+        timer.start()
+        try:
+            if world == 1:
+                nvtx.range_push("configs C2-C5")
+                cfgs = other_configs(sb)
+                nvtx.range_pop()
+                if rank == 0:
+                    line["configs"] = cfgs
+            else:
+                nvtx.range_push("c3 sharded swarm")
+                c3 = sharded_swarm(sb, dist, world, 32768)
+                c3_large = sharded_swarm(sb, dist, world, 262144, gens=(50, 200), nccl=False)
+                nvtx.range_pop()
+                nvtx.range_push("c5 vdcma seeds")
+                c5 = vdcma_seeds(sb, dist, world)
+                nvtx.range_pop()
+                if rank == 0:
+                    line["c3_sharded"], line["c3_sharded_p262144"], line["c5_seeds"] = c3, c3_large, c5
+        except Exception as ex:  # noqa: BLE001 -- the headline must survive a failing extra
+            if rank == 0:
+                line["extras_error"] = repr(ex)[:300]
+        timer.cancel()
+    if rank == 0 and world == 1 and not args.no_cpu:
+        line["cpu_baseline"] = cpu_baseline_block(cpu_legs(12, 1, full=False))
+    emit()
     if world > 1:
-        dist.destroy_process_group()
+        try:
+            dist.destroy_process_group()
+        except Exception:  # noqa: BLE001
+            pass
     return 0
 
 
@@ -318,6 +529,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-extras", action="store_true", help="headline only (no C2-C5 / sharded-swarm keys)")
+    ap.add_argument("--extras-timeout", type=float, default=240.0)
     args = ap.parse_args()
     if args.impl == "reference":
         return reference_arm(args)

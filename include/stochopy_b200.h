@@ -33,6 +33,9 @@ extern "C" {
 
 /* ctrl.status while the optimiser has not terminated */
 #define SP_RUNNING (-1000)
+/* ctrl.status when a kernel found its own state inconsistent (e.g. a ranking without rank 0): the
+ * front-ends raise instead of returning a result */
+#define SP_STATUS_INTERNAL (-902)
 
 typedef enum { SP_F32 = 0, SP_F64 = 1 } sp_dtype;
 

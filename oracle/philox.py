@@ -32,15 +32,22 @@ VD_V0 = 11
 NA_WALK = 12
 
 
-def philox4x32(c0, c1, c2, c3, seed):
-    """Vectorised Philox4x32-10.  Counter words broadcast; returns 4 uint64 arrays (<2^32)."""
+# rounds per purpose: 10, except the ES normal draws (csrc/philox.cuh kEsZRounds)
+ROUNDS_BY_PURPOSE = {8: 7}
+
+
+def philox4x32(c0, c1, c2, c3, seed, rounds=None):
+    """Vectorised Philox4x32-R (R = 10, or ROUNDS_BY_PURPOSE[c3] when c3 is a scalar purpose tag).
+    Counter words broadcast; returns 4 uint64 arrays (<2^32)."""
+    if rounds is None:
+        rounds = ROUNDS_BY_PURPOSE.get(int(c3), 10) if np.ndim(c3) == 0 else 10
     c0, c1, c2, c3 = np.broadcast_arrays(
         *(np.asarray(c, dtype=np.uint64) & MASK32 for c in (c0, c1, c2, c3))
     )
     c0, c1, c2, c3 = (c.copy() for c in (c0, c1, c2, c3))
     k0 = int(seed) & 0xFFFFFFFF
     k1 = (int(seed) >> 32) & 0xFFFFFFFF
-    for _ in range(10):
+    for _ in range(rounds):
         p0 = M0 * c0
         p1 = M1 * c2
         hi0, lo0 = p0 >> np.uint64(32), p0 & MASK32

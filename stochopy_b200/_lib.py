@@ -13,6 +13,7 @@ LIB_PATH = os.path.join(_HERE, "libstochopy_b200.so")
 SP_RUNNING = -1000
 SP_STATUS_PEER_TIMEOUT = -900
 SP_STATUS_RESTART_PENDING = -901
+SP_STATUS_INTERNAL = -902
 PEER_HANDLE_BYTES = 64
 SP_F32, SP_F64 = 0, 1
 OBJECTIVES = {

@@ -22,7 +22,7 @@ __global__ void normal_fill_kernel(T* __restrict__ Z, int64_t P, int N, int64_t 
     const int64_t row = t / nb;
     const int b = (int)(t - row * nb);
     T z[VEC];
-    normal_block(philox4x32((uint32_t)b, (uint32_t)row, (uint32_t)it, purpose, seed), z);
+    normal_block(philox4x32_for(purpose, (uint32_t)b, (uint32_t)row, (uint32_t)it, seed), z);
 #pragma unroll
     for (int e = 0; e < VEC; ++e)
       if (b * VEC + e < N) Z[row * ld + b * VEC + e] = z[e];

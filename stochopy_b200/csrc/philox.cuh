@@ -27,10 +27,11 @@ enum Purpose : uint32_t {
   kNaWalk = 12,
 };
 
+template <int ROUNDS = 10>
 __device__ __forceinline__ uint4 philox4x32(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint64_t seed) {
   uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
 #pragma unroll
-  for (int r = 0; r < 10; ++r) {
+  for (int r = 0; r < ROUNDS; ++r) {
     uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
     uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
     uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
@@ -43,6 +44,9 @@ __device__ __forceinline__ uint4 philox4x32(uint32_t c0, uint32_t c1, uint32_t c
   }
   return make_uint4(c0, c1, c2, c3);
 }
+
+// the stream a purpose tag selects (run-time tag: uniform branch)
+__device__ __forceinline__ uint4 philox4x32_for(uint32_t purpose, uint32_t c0, uint32_t c1, uint32_t c2, uint64_t seed);
 
 // Philox4x32-10 with the ten round keys taken from kernel parameters (constant bank
 // operands of the LOP3s) instead of being re-derived from the seed for every call.
@@ -60,9 +64,14 @@ inline PhiloxKeys philox_keys(uint64_t seed) {
   }
   return r;
 }
+// ROUNDS: 10 everywhere except the N(0,1) draws of the evolution strategies (purpose kEsZ), which take the
+// 7-round variant -- the fewest rounds for which Philox4x32 passes BigCrush (Salmon et al., SC'11, table 2);
+// mirrored by oracle/philox.py (ROUNDS_BY_PURPOSE).
+constexpr int kEsZRounds = 7;
+template <int ROUNDS = 10>
 __device__ __forceinline__ uint4 philox4x32_keyed(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, const PhiloxKeys& K) {
 #pragma unroll
-  for (int r = 0; r < 10; ++r) {
+  for (int r = 0; r < ROUNDS; ++r) {
     const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
     const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
     const uint32_t n0 = hi1 ^ c1 ^ K.k[2 * r], n2 = hi0 ^ c3 ^ K.k[2 * r + 1];
@@ -72,6 +81,10 @@ __device__ __forceinline__ uint4 philox4x32_keyed(uint32_t c0, uint32_t c1, uint
     c3 = lo0;
   }
   return make_uint4(c0, c1, c2, c3);
+}
+
+__device__ __forceinline__ uint4 philox4x32_for(uint32_t purpose, uint32_t c0, uint32_t c1, uint32_t c2, uint64_t seed) {
+  return purpose == kEsZ ? philox4x32<kEsZRounds>(c0, c1, c2, purpose, seed) : philox4x32<10>(c0, c1, c2, purpose, seed);
 }
 
 // U[0,1) for one vector of a row: fp32 -> 4 x 24-bit, fp64 -> 2 x 53-bit
@@ -101,14 +114,21 @@ __device__ __forceinline__ float fast_sqrt(float x) {
   asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
   return r;
 }
-__device__ __forceinline__ float unit_fraction(uint32_t w) { return __uint_as_float(0x3f800000u | (w & 0x007fffffu)); }
-__device__ __forceinline__ float radius_from(uint32_t w) {  // sqrt(-2 ln u), u = 2 - f; branch-free
+__device__ __forceinline__ float unit_fraction(uint32_t w) {  // (w & 0x7fffff) | 0x3f800000 as ONE lop3 (both masks in registers)
+  uint32_t r;
+  asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(r) : "r"(w), "r"(0x007fffffu), "r"(0x3f800000u));
+  return __uint_as_float(r);
+}
+__device__ __forceinline__ float fast_log2(float x) {  // x is never subnormal here: no range fix-up around the MUFU
+  float r;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float radius_from(uint32_t w) {  // sqrt(-2 ln u), u = 2 - f
   const float f = unit_fraction(w), x = f - 1.0f;
   const float series = x * (2.0f + x * (1.0f + x * (0.66666669f + 0.5f * x)));
-  const float viaLog = -1.3862944f * __log2f(2.0f - f);
-  float arg;
-  asm("slct.f32.f32 %0, %1, %2, %3;" : "=f"(arg) : "f"(viaLog), "f"(series), "f"(x - 0.015625f));  // x >= 2^-6 ? log : series
-  return fast_sqrt(arg);
+  const float viaLog = -1.3862944f * fast_log2(2.0f - f);
+  return fast_sqrt(x >= 0.015625f ? viaLog : series);
 }
 __device__ __forceinline__ void normal_pair(uint32_t wr, uint32_t wa, float* z0, float* z1) {
   const float r = radius_from(wr);

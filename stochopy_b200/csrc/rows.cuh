@@ -76,7 +76,7 @@ __global__ void random_fill_kernel(T* __restrict__ out, int64_t P, int N, int64_
     const int64_t row = t / nb;
     const int b = (int)(t - row * nb);
     T z[VEC];
-    const uint4 o = philox4x32((uint32_t)b, (uint32_t)row, (uint32_t)it, purpose, seed);
+    const uint4 o = philox4x32_for(purpose, (uint32_t)b, (uint32_t)row, (uint32_t)it, seed);
     if (normal) normal_block(o, z);
     else uniform_block(o, z);
 #pragma unroll

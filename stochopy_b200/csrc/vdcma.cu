@@ -11,6 +11,7 @@
 //                    constants and the injection dy of the next generation
 //   (vd_inject / vd_refresh stand alone only for host-provided draws and the first generation)
 #include <cstdlib>
+#include <type_traits>
 
 #include "es_common.cuh"
 
@@ -124,13 +125,18 @@ vd_inject_kernel(const VdPtrs<T> a) {
 // does, and the front-end for the result); otherwise arx = xmean + sigma y is stored too.
 // FULL: ndim == CH * LPR * VEC == ld (no padding, no bounds predicates); CLIP: Penalize is on (the
 // objective then sees clip(xmean + sigma y, -1, 1) xscale + xshift, cmaes/_constraints.py:30-32).
-template <typename T, int CH, int LPR, bool FULL, bool CLIP>
-__global__ void __launch_bounds__(kThreads, (CH * (int)sizeof(T) <= 32 ? 3 : 2))
+// FAST (only with !CLIP): the device-resident loop's configuration fixed at compile time -- in-kernel draws,
+// lean, objective evaluated, plain (1) or evict-first (2) stores of y -- so the row body has no run-time
+// switches between its chunks; 0: those are read from the state.  The two injected rows take their own
+// copy of the row body (a row-level branch), which keeps the common one straight-line.
+template <typename T, int CH, int LPR, bool FULL, bool CLIP, int FAST>
+__global__ void __launch_bounds__(kThreads, (FAST != 0 && CH * (int)sizeof(T) <= 32 ? 3 : 2))
 vd_sample_eval_kernel(const VdPtrs<T> a, const PhiloxKeys keys) {
   using TL = Tile<T, CH, LPR>;
   using V = typename Num<T>::vec_t;
   constexpr int VEC = Num<T>::VEC;
   constexpr int COLS = TL::COLS;
+  static_assert(!(CLIP && FAST != 0), "the fast variants never clip");
   __shared__ __align__(16) T s_vn[COLS], s_dv[COLS], s_fa[COLS], s_fb[COLS];
   const sp_es_ctrl* c = a.ctrl;
   pdl_launch_dependents();
@@ -151,7 +157,10 @@ vd_sample_eval_kernel(const VdPtrs<T> a, const PhiloxKeys keys) {
   const T sigma = (T)c->sigma;
   const T fac = (T)(sqrt(1.0 + c->aux[0]) - 1.0);
   const bool inject = c->inject != 0;
-  const bool store_x = !a.lean;
+  const bool host_z = FAST ? false : a.host_z != 0;
+  const bool store_x = FAST ? false : !a.lean;
+  const bool stream = FAST == 2 ? true : (FAST == 1 ? false : a.stream_stores != 0);
+  const bool evaluate = FAST ? true : a.evaluate != 0;
   if (blockIdx.x == 0 && threadIdx.x == 0) const_cast<sp_es_ctrl*>(c)->sigma_gen = c->sigma;
   __syncthreads();
   auto svec = [&](const T* p, int cc, T (&o)[VEC]) {  // shared memory: always in bounds (COLS wide)
@@ -179,24 +188,23 @@ vd_sample_eval_kernel(const VdPtrs<T> a, const PhiloxKeys keys) {
       T* q = reinterpret_cast<T*>(&t);
 #pragma unroll
       for (int e = 0; e < VEC; ++e) q[e] = val[e];
-      if (a.stream_stores) __stcs(reinterpret_cast<V*>(rowp + j0), t);
+      if (stream) __stcs(reinterpret_cast<V*>(rowp + j0), t);
       else *reinterpret_cast<V*>(rowp + j0) = t;
     }
   };
-
-  for (int64_t g = warp; g < groups; g += nwarps) {
-    int64_t row = g * TL::RPW + sub;
-    const bool live = row < a.P;
-    if (!live) row = a.P - 1;
+  // one row (group of RPW rows per warp); INJ: rows 0 / 1 of an injecting generation carry +-dy
+  auto row_body = [&](int64_t row, bool live, auto inj_tag) {
+    constexpr bool INJ = decltype(inj_tag)::value;
     TL y;
-    if (a.host_z) y.load(a.ary + row * a.ld, l, ld);
+    if (host_z) y.load(a.ary + row * a.ld, l, ld);
     T zv = 0;
 #pragma unroll
     for (int cc = 0; cc < CH; ++cc) {
       const int j0 = TL::col(cc, l, 0);
-      if (!a.host_z) {
+      if (!host_z) {
         T z[VEC];
-        if (FULL || j0 < N) normal_block(philox4x32_keyed((uint32_t)(j0 / VEC), (uint32_t)row, (uint32_t)a.it, kEsZ, keys), z);
+        if (FULL || j0 < N)
+          normal_block(philox4x32_keyed<kEsZRounds>((uint32_t)(j0 / VEC), (uint32_t)row, (uint32_t)a.it, kEsZ, keys), z);
 #pragma unroll
         for (int e = 0; e < VEC; ++e) y.v[cc][e] = (FULL || j0 + e < N) ? z[e] : T(0);
       }
@@ -207,7 +215,6 @@ vd_sample_eval_kernel(const VdPtrs<T> a, const PhiloxKeys keys) {
     }
     zv = group_sum<LPR>(zv);
     const T k = fac * zv;
-    const bool inj_row = inject && row < 2;
     T yv = 0;
     T* __restrict__ yrow = a.ary + row * a.ld;
     T* __restrict__ xrow = a.arx + row * a.ld;
@@ -217,7 +224,7 @@ vd_sample_eval_kernel(const VdPtrs<T> a, const PhiloxKeys keys) {
       T vn[VEC], dv[VEC], yy[VEC], tt[VEC];
       svec(s_vn, cc, vn);
       svec(s_dv, cc, dv);
-      if (inj_row) {  // rows 0 / 1 carry +-dy (_vdcma.py:247-248); t = y / D
+      if (INJ) {  // _vdcma.py:247-248; t = y / D
         T dy[VEC];
         gvec(a.dy, cc, dy);
 #pragma unroll
@@ -262,9 +269,23 @@ vd_sample_eval_kernel(const VdPtrs<T> a, const PhiloxKeys keys) {
     }
     yv = group_sum<LPR>(yv);
     if (live && l == 0) a.yvn[row] = yv;
-    if (!a.evaluate) continue;
+    if (!evaluate) return;
     const T f = evaluate_tile<T, CH, LPR>(a.objective, y, l, N);
     if (live && l == 0) a.arfit[row] = f;
+  };
+
+  for (int64_t g = warp; g < groups; g += nwarps) {
+    int64_t row = g * TL::RPW + sub;
+    const bool live = row < a.P;
+    if (!live) row = a.P - 1;
+    // rows 0 and 1 share a warp only when RPW > 1; then the whole group takes the injecting copy, whose
+    // per-row test keeps the other rows on the sampling formula
+    if (inject && g == 0) {
+      if (row < 2) row_body(row, live, std::true_type{});
+      else row_body(row, live, std::false_type{});
+    } else {
+      row_body(row, live, std::false_type{});
+    }
   }
 }
 
@@ -379,6 +400,29 @@ vd_wsum_kernel(const VdPtrs<T> a) {
     }
 }
 
+// Block reduction with ONE barrier: warp butterflies, one shared slot per (value, warp), then every thread
+// folds the NW warp results itself, in warp order (deterministic).  Two slot sets alternate (`ph`), so a
+// thread may start the next reduction while others still read this one's slots.
+template <int K, int NW>
+__device__ __forceinline__ void reduce1(double (&v)[K], const int (&op)[K], double (*buf)[kRedMax][NW], int& ph) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < K; ++k) v[k] = red_warp(v[k], op[k]);
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < K; ++k) buf[ph][k][warp] = v[k];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    double x = buf[ph][k][0];
+#pragma unroll
+    for (int w = 1; w < NW; ++w) x = red_apply(x, buf[ph][k][w], op[k]);
+    v[k] = x;
+  }
+  ph ^= 1;
+}
+
 // mean, step size, paths, natural gradient, termination (_vdcma.py:290-396), fused with the
 // reduction of the chunk partials of vd_wsum.
 //   phase 1 (every CTA of the grid): sums[q][n] = sum over the chunks of part[chunk][q][n] in a fixed
@@ -395,7 +439,6 @@ __global__ void __launch_bounds__(kUpThreads)
 vd_update_kernel(const VdPtrs<T> a) {
   __shared__ double s_red[kRedDoubles];
   __shared__ T s_p[8][kUpOut];
-  __shared__ int s_best;
   __shared__ bool s_last;
   pdl_launch_dependents();
   pdl_wait();
@@ -450,10 +493,15 @@ vd_update_kernel(const VdPtrs<T> a) {
     if (!s_last) return;
     __threadfence();
   }
+  // ---- phase 2 -----------------------------------------------------------------------------------
+  // Six dependent block reductions, one barrier each (reduce1), instead of a dozen three-barrier ones:
+  //   L1 max vn^2, (pc/D).vn, H and everything the termination ladder needs   L2 vn.q   L3 ria, via
+  //   L4 s.vn^2   L5 |ngv|^2, min D/|ngd|   L6 |v'|^2 and the three sums of the next injection
+  __shared__ double s_r1[2][kRedMax][kUpThreads / 32];
+  int ph = 0;
   const double nv2 = c->aux[0], nv = c->aux[1];
-  // ---- everything this generation reads, issued up front ------------------------------------------
   bool ok[kVdNpt];
-  T xm[kVdNpt], pc[kVdNpt], vnT[kVdNpt], dv[kVdNpt], vv[kVdNpt], Sy[kVdNpt], Sa[kVdNpt], Sb[kVdNpt];
+  T xm[kVdNpt], pc[kVdNpt], vnT[kVdNpt], dv[kVdNpt], vv[kVdNpt], Sy[kVdNpt], Sa[kVdNpt], Sb[kVdNpt], dC[kVdNpt];
 #pragma unroll
   for (int k = 0; k < kVdNpt; ++k) {
     const int n = tid + k * nt;
@@ -461,17 +509,31 @@ vd_update_kernel(const VdPtrs<T> a) {
     const int m = ok[k] ? n : 0;
     const T* p = a.sums();
     Sy[k] = __ldcg(p + m), Sa[k] = __ldcg(p + N + m), Sb[k] = __ldcg(p + 2 * N + m);
-    xm[k] = a.xmean[m], pc[k] = a.pc[m], vnT[k] = a.vn[m], dv[k] = a.dvec[m], vv[k] = a.vvec[m];
+    xm[k] = a.xmean[m], pc[k] = a.pc[m], vnT[k] = a.vn[m], dv[k] = a.dvec[m], vv[k] = a.vvec[m], dC[k] = a.diagC[m];
   }
   const int r0 = a.rank[0], r1 = a.P > 1 ? a.rank[1] : 0;
-  // the per-CTA scan results of phase 1
-  double fext[2] = {1.0 / 0.0, -1.0 / 0.0};
-  for (int b = tid; b < (int)gridDim.x; b += nt) {
+  const double inf = 1.0 / 0.0;
+  // [0] max vn^2  [1] (pc/D).vn  [2] H  [3] |xold - xmean|^2  [4] max sd  [5] any 0.2 sigma sd < 1e-10
+  // [6] any sigma sd > 1e3 sigma0  [7] all sigma |pc| < 1e-11 sigma0  [8..11] min / max of the zero-padded
+  // best-fitness history (all of it, and the window it-ilim..it) WITHOUT this generation's entry
+  // [12] min f  [13] max f  [14] row of rank 0
+  double L1[15] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 1.0, inf, -inf, inf, -inf, inf, -inf, -1.0};
+  if (tid < a.chunks) L1[2] = (double)__ldcg(a.hpart() + tid);
+  for (int b = tid; b < (int)gridDim.x; b += nt) {  // the per-CTA scan results of phase 1
     const double* fp = a.fpart() + 3 * b;
-    fext[0] = fmin(fext[0], __ldcg(fp));
-    fext[1] = fmax(fext[1], __ldcg(fp + 1));
-    const double row = __ldcg(fp + 2);
-    if (row >= 0.0) s_best = (int)row;
+    L1[12] = fmin(L1[12], __ldcg(fp));
+    L1[13] = fmax(L1[13], __ldcg(fp + 1));
+    L1[14] = fmax(L1[14], __ldcg(fp + 2));
+  }
+  for (int i = tid; i < a.maxiter; i += nt) {  // _cmaes.py:412-414 (window incl. one not-yet-written zero), :424-427
+    if (i == a.it - 1) continue;
+    const double h = (double)a.besthist[i];
+    L1[8] = fmin(L1[8], h);
+    L1[9] = fmax(L1[9], h);
+    if (i >= a.it - a.ilim && i <= a.it) {
+      L1[10] = fmin(L1[10], h);
+      L1[11] = fmax(L1[11], h);
+    }
   }
   // sigma from the rank gap of the injected pair, _vdcma.py:299-307
   bool hsig = true;
@@ -486,8 +548,6 @@ vd_update_kernel(const VdPtrs<T> a) {
   // mean, _vdcma.py:291; evolution path, :310-315
   const T kpc = (T)sqrt(a.cc * (2.0 - a.cc) * a.mueff);
   T dx[kVdNpt];
-  double red2[3] = {0.0, 0.0, 0.0};  // max vn^2, (pc / D) . vn, H = sum of vd_wsum's scalar partials
-  if (tid < a.chunks) red2[2] = (double)__ldcg(a.hpart() + tid);
 #pragma unroll
   for (int k = 0; k < kVdNpt; ++k) {
     dx[k] = mul_rn((T)c->sigma_gen, Sy[k]);  // = w . x[top mu] - (sum w) xmean (_vdcma.py:291), without the cancellation
@@ -496,20 +556,46 @@ vd_update_kernel(const VdPtrs<T> a) {
     pc[k] = v;
     if (ok[k]) {
       const int n = tid + k * nt;
+      const T xnew = add_rn(xm[k], dx[k]);
       a.dx[n] = dx[k];
       a.xold[n] = xm[k];
-      a.xmean[n] = add_rn(xm[k], dx[k]);
+      a.xmean[n] = xnew;
       a.pc[n] = v;
       const double vn = (double)vnT[k];
-      red2[0] = fmax(red2[0], vn * vn);
-      red2[1] += (double)div_rn(v, dv[k]) * vn;
+      L1[0] = fmax(L1[0], vn * vn);
+      L1[1] += (double)div_rn(v, dv[k]) * vn;
+      const double d = (double)xm[k] - (double)xnew, sd = sqrt((double)dC[k]);
+      L1[3] += d * d;
+      L1[4] = fmax(L1[4], sd);
+      if (0.2 * sigma * sd < 1.0e-10) L1[5] = 1.0;
+      if (sigma * sd > 1.0e3 * a.insigma) L1[6] = 1.0;
+      if (!(sigma * fabs((double)v) < 1.0e-11 * a.insigma)) L1[7] = 0.0;
+      xm[k] = xnew;
     }
   }
   {
-    const int op[3] = {RED_MAX, RED_SUM, RED_SUM};
-    block_reduce<3>(red2, op, s_red);
+    const int op[15] = {RED_MAX, RED_SUM, RED_SUM, RED_SUM, RED_MAX, RED_MAX, RED_MAX, RED_MIN, RED_MIN, RED_MAX,
+                        RED_MIN, RED_MAX, RED_MIN, RED_MAX, RED_MAX};
+    reduce1<15, kUpThreads / 32>(L1, op, s_r1, ph);
   }
-  const double vmax = red2[0], yv1 = red2[1], hmu = red2[2];
+  const double vmax = L1[0], yv1 = L1[1], hmu = L1[2];
+  const double best = L1[12];  // the row of rank 0 carries the minimum
+  const int best_row = (int)L1[14];  // -1 would mean the ranking holds no rank 0: reported as SP_STATUS_INTERNAL below
+  // termination ladder (_cmaes.py:360-434 without B, D: _vdcma.py:380-396); diagC still describes the
+  // population just evaluated
+  int status = SP_RUNNING;
+  {
+    const double hmin = fmin(L1[8], best), hmax = fmax(L1[9], best), wmin = fmin(L1[10], best), wmax = fmax(L1[11], best);
+    if (a.it >= a.maxiter) status = -1;
+    else if (sqrt(L1[3]) <= a.xtol && best < a.ftol) status = 0;
+    else if (best <= a.ftol) status = 1;
+    else if (L1[5] > 0.5) status = -3;
+    else if (a.it >= a.ilim && wmax - wmin < 1.0e-10) status = -5;
+    else if (L1[6] > 0.5) status = -6;
+    else if (a.it > 2 && fmax(L1[13], hmax) - fmin(L1[12], hmin) < 1.0e-12) status = -7;
+    else if (L1[7] > 0.5 && sigma * L1[4] < 1.0e-11 * a.insigma) status = -8;
+    if (best_row < 0) status = SP_STATUS_INTERNAL;
+  }
   // alpha and friends, _vdcma.py:318-329
   const double gamma = 1.0 / sqrt(1.0 + nv2);
   double alpha = sqrt(nv2 * nv2 + (1.0 + nv2) / vmax * (2.0 - gamma)) / (2.0 + nv2), beta = 0.0;
@@ -519,7 +605,7 @@ vd_update_kernel(const VdPtrs<T> a) {
   // rank-one vectors from pc / dvec, then p = cmu p_mu (+ c1 p_1), q likewise
   const double k1 = nv2 / (1.0 + nv2);
   T pv[kVdNpt], qv[kVdNpt];
-  double vq = 0.0;
+  double vq[1] = {0.0};
 #pragma unroll
   for (int k = 0; k < kVdNpt; ++k) {
     const double vn = (double)vnT[k];
@@ -536,17 +622,21 @@ vd_update_kernel(const VdPtrs<T> a) {
     }
     pv[k] = (T)p;
     qv[k] = (T)q;
-    if (ok[k]) vq += vn * q;
+    if (ok[k]) vq[0] += vn * q;
   }
   double up = 1.0;
+  T vv2[kVdNpt], dv2[kVdNpt];
+#pragma unroll
+  for (int k = 0; k < kVdNpt; ++k) vv2[k] = vv[k], dv2[k] = dv[k];
   if (a.cmu + a.c1 > 0.0) {  // natural gradient, _vdcma.py:444-458
-    vq = block_sum(vq, s_red);
+    const int sum1[1] = {RED_SUM};
+    reduce1<1, kUpThreads / 32>(vq, sum1, s_r1, ph);
     T sv[kVdNpt];
     double red3[2] = {0.0, 0.0};  // ria, via
 #pragma unroll
     for (int k = 0; k < kVdNpt; ++k) {
       const double vn = (double)vnT[k], vnn = vn * vn, avec = 2.0 - (bsca + 2.0 * alpha * alpha) * vnn;
-      const double r = (double)pv[k] - alpha / (1.0 + nv2) * ((2.0 + nv2) * (double)qv[k] * vn - nv2 * vq * vnn);
+      const double r = (double)pv[k] - alpha / (1.0 + nv2) * ((2.0 + nv2) * (double)qv[k] * vn - nv2 * vq[0] * vnn);
       sv[k] = (T)r;
       if (ok[k]) {
         red3[0] += r * (vnn / avec);
@@ -555,24 +645,24 @@ vd_update_kernel(const VdPtrs<T> a) {
     }
     {
       const int op[2] = {RED_SUM, RED_SUM};
-      block_reduce<2>(red3, op, s_red);
+      reduce1<2, kUpThreads / 32>(red3, op, s_r1, ph);
     }
     const double ria = red3[0], via = red3[1];
-    double svnn = 0.0;
+    double svnn[1] = {0.0};
 #pragma unroll
     for (int k = 0; k < kVdNpt; ++k) {
       const double vn = (double)vnT[k], vnn = vn * vn, avec = 2.0 - (bsca + 2.0 * alpha * alpha) * vnn;
       const double sn = (double)sv[k] / avec - bsca * ria / (1.0 + bsca * via) * (vnn / avec);
       sv[k] = (T)sn;
-      if (ok[k]) svnn += sn * vnn;
+      if (ok[k]) svnn[0] += sn * vnn;
     }
-    svnn = block_sum(svnn, s_red);
+    reduce1<1, kUpThreads / 32>(svnn, sum1, s_r1, ph);
     T ngv[kVdNpt], ngd[kVdNpt];
-    double red4[2] = {0.0, 1.0 / 0.0};  // |ngv|^2, min D / |ngd|
+    double red4[2] = {0.0, inf};  // |ngv|^2, min D / |ngd|
 #pragma unroll
     for (int k = 0; k < kVdNpt; ++k) {
       const double vn = (double)vnT[k], sn = (double)sv[k];
-      const double gv = (double)qv[k] / nv - alpha / nv * ((2.0 + nv2) * (vn * sn) - svnn * vn);
+      const double gv = (double)qv[k] / nv - alpha / nv * ((2.0 + nv2) * (vn * sn) - svnn[0] * vn);
       const double gd = (double)dv[k] * sn;
       ngv[k] = (T)gv;
       ngd[k] = (T)gd;
@@ -583,22 +673,59 @@ vd_update_kernel(const VdPtrs<T> a) {
     }
     {
       const int op[2] = {RED_SUM, RED_MIN};
-      block_reduce<2>(red4, op, s_red);
+      reduce1<2, kUpThreads / 32>(red4, op, s_r1, ph);
     }
     up = fmin(1.0, 0.7 * nv / sqrt(red4[0]));  // at most 70 % change, _vdcma.py:361-363
     up = fmin(up, 0.7 * red4[1]);
 #pragma unroll
-    for (int k = 0; k < kVdNpt; ++k)
+    for (int k = 0; k < kVdNpt; ++k) {
+      vv2[k] = add_rn(vv[k], mul_rn((T)up, ngv[k]));
+      dv2[k] = add_rn(dv[k], mul_rn((T)up, ngd[k]));
       if (ok[k]) {
         const int n = tid + k * nt;
-        a.vvec[n] = add_rn(vv[k], mul_rn((T)up, ngv[k]));
-        a.dvec[n] = add_rn(dv[k], mul_rn((T)up, ngd[k]));
+        a.vvec[n] = vv2[k];
+        a.dvec[n] = dv2[k];
       }
+    }
   }
-  __syncthreads();  // s_best, and the vectors written above, are visible to the whole CTA
+  // next generation: |v|^2, vn, diagC, the fused sampling constants and (in-kernel draws, still running)
+  // the injected direction dy = |g| / |dx|_C dx of _vdcma.py:243-246 with a fresh g ~ N(0, I)
+  const bool inject_next = !a.host_z && status == SP_RUNNING;
+  double L6[4] = {0.0, 0.0, 0.0, 0.0};  // |v'|^2, |g|^2, |dx/D'|^2, (dx/D').v'
+#pragma unroll
+  for (int k = 0; k < kVdNpt; ++k) {
+    if (!ok[k]) continue;
+    const int n = tid + k * nt;
+    L6[0] += (double)vv2[k] * (double)vv2[k];
+    if (inject_next) {
+      T z[Num<T>::VEC];
+      normal_block(philox4x32((uint32_t)(n / Num<T>::VEC), 0u, (uint32_t)(a.it + 1), kVdInject, a.seed), z);
+      const T g = z[n % Num<T>::VEC];
+      const double ddx = (double)div_rn(dx[k], dv2[k]);
+      L6[1] += (double)g * (double)g;
+      L6[2] += ddx * ddx;
+      L6[3] += ddx * (double)vv2[k];
+    }
+  }
+  {
+    const int op[4] = {RED_SUM, RED_SUM, RED_SUM, RED_SUM};
+    reduce1<4, kUpThreads / 32>(L6, op, s_r1, ph);
+  }
+  const double nv2n = L6[0], nvn = sqrt(nv2n);
+  const T kinj = inject_next ? (T)(sqrt(L6[1]) / sqrt(L6[2] - L6[3] * L6[3] / (1.0 + nv2n))) : T(0);
+#pragma unroll
+  for (int k = 0; k < kVdNpt; ++k) {
+    if (!ok[k]) continue;
+    const int n = tid + k * nt;
+    const T v = vv2[k], d = dv2[k], sc = a.xscale[n];
+    a.vn[n] = div_rn(v, (T)nvn);
+    a.diagC[n] = mul_rn(mul_rn(d, add_rn(T(1), mul_rn(v, v))), d);  // _vdcma.py:251-256
+    a.fuse_a()[n] = ((T)sigma * d) * sc;
+    a.fuse_b()[n] = xm[k] * sc + a.xshift[n];
+    if (inject_next) a.dy[n] = mul_rn(kinj, dx[k]);
+  }
   if (tid == 0) {
-    const double best = (double)a.arfit[s_best];
-    c->base.gbest_row = s_best;
+    c->base.gbest_row = best_row;
     c->base.gfit = best;
     a.besthist[a.it - 1] = (T)best;
     c->hsig = hsig ? 1 : 0;
@@ -606,17 +733,12 @@ vd_update_kernel(const VdPtrs<T> a) {
     c->sigma = sigma;
     if (injected) c->vd_ps = ps_new;
     c->inject = 1;
+    c->aux[0] = nv2n;
+    c->aux[1] = nvn;
     c->aux[2] = up;
+    c->base.nit = a.it;
+    c->base.status = status;
   }
-  __syncthreads();
-  // diagC still describes the population just evaluated (_vdcma.py:380-396: no B, D)
-  converge_ladder<T>(c, a.it, N, a.maxiter, a.ilim, a.P, a.xmean, a.xold, a.besthist, a.arfit, a.pc, a.diagC, 1,
-                     (const T*)nullptr, (const T*)nullptr, a.xtol, a.ftol, a.insigma, s_red, fext);
-  // next generation's |v|^2, vn, diagC and (in-kernel draws) its injected direction dy
-  __syncthreads();
-  vd_refresh_body<T>(a, s_red);
-  __syncthreads();
-  if (!a.host_z && es_running(c)) vd_inject_body<T>(a, a.it + 1, c->aux[0], s_red);
 }
 
 template <typename T>
@@ -674,7 +796,8 @@ static VdPtrs<T> vd_ptrs(const sp_vd_state* st, int it, int evaluate) {
   // y and x of a population larger than the L2 are stored evict-first (st.global.cs); SP_VD_PLAIN_STORES=1
   // keeps normal stores (profiling switch)
   static const bool plain_stores = getenv("SP_VD_PLAIN_STORES") != nullptr;
-  a.stream_stores = !plain_stores && 2 * (size_t)st->P * st->ld * sizeof(T) > ((size_t)96 << 20) ? 1 : 0;
+  // (lean: only y is stored, and vd_wsum re-reads half of it right away -- keep it in the L2 when it fits)
+  a.stream_stores = !plain_stores && (st->lean ? 1 : 2) * (size_t)st->P * st->ld * sizeof(T) > ((size_t)96 << 20) ? 1 : 0;
   a.chunks = vd_chunks(st->P);
   a.P = st->P;
   a.ld = st->ld;
@@ -702,25 +825,37 @@ static int vd_sample(const sp_vd_state* st, int it, int evaluate, cudaStream_t s
     vd_inject_kernel<T><<<1, 256, 0, s>>>(a);
     SP_CHECK_LAUNCH();
   }
-  const int grid = grid_for_rows(st->P, sh.lpr, sh.ch * (int)sizeof(T) <= 32 ? 3 : 2);
+  int grid = grid_for_rows(st->P, sh.lpr, sh.ch * (int)sizeof(T) <= 32 ? 3 : 2);
   // fixed-shape instantiations only for full-warp rows (the large-N case that matters)
   const bool full = sh.lpr == 32 && st->N == sh.ch * 32 * Num<T>::VEC && st->ld == st->N;
   const bool clip = st->constraint == SP_CONS_PENALIZE;
   const PhiloxKeys keys = philox_keys(st->seed);
   const bool pdl = !st->host_z;  // with host draws the caller's copies sit between the generations anyway
-#define SP_CALL(TT, C, L)                                                                                         \
-  do {                                                                                                            \
-    if (L == 32 && full) {                                                                                        \
-      if (clip) launch_pdl(vd_sample_eval_kernel<TT, C, 32, true, true>, dim3(grid), dim3(kThreads), 0, s, pdl, a, keys);   \
-      else launch_pdl(vd_sample_eval_kernel<TT, C, 32, true, false>, dim3(grid), dim3(kThreads), 0, s, pdl, a, keys);       \
-    } else if (clip) {                                                                                            \
-      launch_pdl(vd_sample_eval_kernel<TT, C, L, false, true>, dim3(grid), dim3(kThreads), 0, s, pdl, a, keys);   \
-    } else {                                                                                                      \
-      launch_pdl(vd_sample_eval_kernel<TT, C, L, false, false>, dim3(grid), dim3(kThreads), 0, s, pdl, a, keys);  \
-    }                                                                                                             \
+  // the device-resident loop (in-kernel draws, lean, objective on the device, no Penalize) on full-warp rows
+  // runs the compile-time configured variants
+  const int fast = (st->lean && !st->host_z && evaluate && !clip && sh.lpr == 32) ? (a.stream_stores ? 2 : 1) : 0;
+  if (!fast) grid = grid_for_rows(st->P, sh.lpr, 2);  // the run-time configured variant keeps 128 registers
+#define SP_GO(TT, C, L, F, CL, FA) launch_pdl(vd_sample_eval_kernel<TT, C, L, F, CL, FA>, dim3(grid), dim3(kThreads), 0, s, pdl, a, keys)
+#define SP_CALL(TT, C, L)                                                  \
+  do {                                                                     \
+    if (L == 32 && fast == 1) {                                            \
+      if (full) SP_GO(TT, C, 32, true, false, 1);                          \
+      else SP_GO(TT, C, 32, false, false, 1);                              \
+    } else if (L == 32 && fast == 2) {                                     \
+      if (full) SP_GO(TT, C, 32, true, false, 2);                          \
+      else SP_GO(TT, C, 32, false, false, 2);                              \
+    } else if (L == 32 && full) {                                          \
+      if (clip) SP_GO(TT, C, 32, true, true, 0);                           \
+      else SP_GO(TT, C, 32, true, false, 0);                               \
+    } else if (clip) {                                                     \
+      SP_GO(TT, C, L, false, true, 0);                                     \
+    } else {                                                               \
+      SP_GO(TT, C, L, false, false, 0);                                    \
+    }                                                                      \
   } while (0)
   SP_DISPATCH_SHAPE(T, sh, SP_CALL);
 #undef SP_CALL
+#undef SP_GO
   SP_CHECK_LAUNCH();
   return SP_OK;
 }

@@ -17,7 +17,7 @@ import numpy as np
 import torch
 
 from .. import _lib as L
-from ._common import HistoryStreamer, Engine, NumpyStream, device_objective, fresh_seed, messages, validate_common
+from ._common import HistoryStreamer, Engine, NumpyStream, device_objective, fresh_seed, messages, validate_common, device_scope
 from ._helpers import OptimizeResult, register
 
 __all__ = ["minimize"]
@@ -59,6 +59,7 @@ class EsHistory:
             res.update({"xall": self.xall[:it], "funall": self.funall[:it]})
 
 
+@device_scope
 def minimize(
     fun,
     bounds,
@@ -225,6 +226,8 @@ def minimize(
                 callback(Xh, res)
 
     it = c.base.nit
+    if c.base.status == L.SP_STATUS_INTERNAL:
+        raise L.EngineError("inconsistent device state (ranking without a rank 0)")
     if streamer is not None:
         streamer.finish(hist, it, transform=lambda X: unstd(valid_rows(X)))
     best = arx[c.base.gbest_row, :N].to("cpu").numpy().astype(np.float64)

@@ -8,6 +8,7 @@ that calls the user's Python callable row by row (the exact reference contract).
 PyTorch is used for device buffers and streams only.
 """
 import ctypes as C
+import functools
 import os
 
 import numpy as np
@@ -54,6 +55,28 @@ def device_objective(fun, args):
     return None
 
 
+def device_scope(fn):
+    """Run a front-end with its ``device=`` option as the current CUDA device.  The C library
+    launches on the current device (it only ever calls cudaGetDevice), so a run on "cuda:1" while
+    device 0 is current must switch for its whole duration; the previous device is restored on
+    return.  Without the option (or without CUDA: the engine then raises) nothing happens."""
+
+    @functools.wraps(fn)
+    def wrapper(*args, **kw):
+        dev = kw.get("device")
+        if dev is None or not torch.cuda.is_available():
+            return fn(*args, **kw)
+        d = torch.device("cuda", dev) if isinstance(dev, int) else torch.device(dev)
+        if d.type != "cuda":
+            raise ValueError()
+        idx = torch.cuda.current_device() if d.index is None else d.index
+        kw["device"] = torch.device("cuda", idx)
+        with torch.cuda.device(idx):
+            return fn(*args, **kw)
+
+    return wrapper
+
+
 def fresh_seed(seed):
     if seed is None:
         return int.from_bytes(os.urandom(8), "little")
@@ -69,7 +92,13 @@ class Engine:
         if not torch.cuda.is_available():
             raise L.EngineError("stochopy_b200 needs a CUDA device (no CPU fallback)")
         self.np_dt, self.t_dt, self.sp_dt = resolve_dtype(dtype)
-        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        dev = torch.device("cuda") if device is None else (torch.device("cuda", device) if isinstance(device, int)
+                                                           else torch.device(device))
+        if dev.type != "cuda":
+            raise ValueError()
+        # always an explicit index ("cuda" = the current device); the C library launches on the current
+        # device, so the front-ends run under `device_scope` which makes this device current
+        self.device = torch.device("cuda", torch.cuda.current_device() if dev.index is None else dev.index)
         self.vec = 16 // self.np_dt.itemsize
         key = (self.device.type, self.device.index)
         if key not in _PINNED:
@@ -90,16 +119,28 @@ class Engine:
         """Zero-filled (p, ld) row buffer."""
         return self.zeros(p, self.ld(n))
 
+    def rows_scratch(self, p, n):
+        """(p, ld) row buffer that is about to be overwritten: only the padding columns (if any)
+        have to be zero, so an unpadded buffer is left uninitialised."""
+        return self.empty(p, n) if self.ld(n) == n else self.zeros(p, self.ld(n))
+
     def upload_rows(self, host, out=None):
         """Host (p, n) array -> padded device rows (copy; the caller's array is never
-        aliased).  fp32/fp64 sources travel as they are and are cast on the device."""
+        aliased).  fp32/fp64 sources travel as they are and are cast on the device.  A source in
+        page-locked memory (e.g. the numpy view of a pinned torch tensor) is copied asynchronously by
+        DMA straight into the row buffer; the caller keeps it alive until the run returns."""
         host = np.asarray(host)
         if host.dtype not in (np.float32, np.float64):
             host = host.astype(np.float64)
         host = np.ascontiguousarray(host)
         p, n = host.shape
-        out = self.rows(p, n) if out is None else out
-        out[:, :n].copy_(torch.from_numpy(host).to(self.device))
+        out = self.rows_scratch(p, n) if out is None else out
+        src = torch.from_numpy(host)
+        pinned = src.is_pinned()
+        if out.shape[1] == n:  # unpadded rows: one copy (and the dtype cast, if any, on the device side of it)
+            out.copy_(src, non_blocking=pinned)
+        else:
+            out[:, :n].copy_(src.to(self.device, non_blocking=pinned))
         return out
 
     def upload_vec(self, host, pad_to=None, dtype=None):

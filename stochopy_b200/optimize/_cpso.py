@@ -6,12 +6,13 @@ keyword signature, defaults and validation (:12-179); the generation loop
 ``updating`` is validated but the device path is always synchronous.
 """
 import ctypes as C
+import warnings
 
 import numpy as np
 import torch
 
 from .. import _lib as L
-from ._common import Engine, History, HistoryStreamer, NumpyStream, device_objective, fresh_seed, messages, validate_common
+from ._common import Engine, History, HistoryStreamer, NumpyStream, device_objective, fresh_seed, messages, validate_common, device_scope
 from ._helpers import OptimizeResult, register
 
 __all__ = ["minimize"]
@@ -19,6 +20,7 @@ __all__ = ["minimize"]
 _CONSTRAINTS = {None: L.CONS_NONE, "Shrink": L.CONS_SHRINK}  # cpso/_constraints.py:69-72
 
 
+@device_scope
 def minimize(
     fun,
     bounds,
@@ -64,6 +66,12 @@ def minimize(
         raise ValueError()
     if updating not in {"immediate", "deferred"}:
         raise ValueError()
+    if updating == "immediate":
+        # the reference's default is sequential by construction (_common.py:163-194: every individual sees
+        # the best found so far, '<=' acceptance); on the device the population moves synchronously, as the
+        # reference itself does for workers > 1 / backend="mpi" -- say so instead of switching silently
+        warnings.warn("updating='immediate' runs as updating='deferred' on the CUDA backend "
+                      "(synchronous generations); pass updating='deferred' to silence this", UserWarning, stacklevel=3)
     if callback is not None and not hasattr(callback, "__call__"):
         raise ValueError()
     if rng not in {"philox", "numpy"}:

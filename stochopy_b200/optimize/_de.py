@@ -7,12 +7,13 @@ accepted and validated but the device path is always synchronous ("deferred"),
 exactly as the reference forces for workers > 1 or backend == "mpi" (:142-145).
 """
 import ctypes as C
+import warnings
 
 import numpy as np
 import torch
 
 from .. import _lib as L
-from ._common import Engine, History, HistoryStreamer, NumpyStream, device_objective, fresh_seed, messages, validate_common
+from ._common import Engine, History, HistoryStreamer, NumpyStream, device_objective, fresh_seed, messages, validate_common, device_scope
 from ._helpers import OptimizeResult, register
 
 __all__ = ["minimize"]
@@ -20,6 +21,7 @@ __all__ = ["minimize"]
 _CONSTRAINTS = {None: L.CONS_NONE, "Random": L.CONS_RANDOM}  # de/_constraints.py:31-34
 
 
+@device_scope
 def minimize(
     fun,
     bounds,
@@ -61,6 +63,12 @@ def minimize(
         raise ValueError()
     if updating not in {"immediate", "deferred"}:
         raise ValueError()
+    if updating == "immediate":
+        # the reference's default is sequential by construction (_common.py:163-194: every individual sees
+        # the best found so far, '<=' acceptance); on the device the population moves synchronously, as the
+        # reference itself does for workers > 1 / backend="mpi" -- say so instead of switching silently
+        warnings.warn("updating='immediate' runs as updating='deferred' on the CUDA backend "
+                      "(synchronous generations); pass updating='deferred' to silence this", UserWarning, stacklevel=3)
     strat = L.DE_STRATEGIES[strategy]  # KeyError like _strategy_map[strategy], _de.py:140
     if callback is not None and not hasattr(callback, "__call__"):
         raise ValueError()
@@ -78,7 +86,7 @@ def minimize(
     stream = NumpyStream(seed) if rng == "numpy" else None
 
     ld = eng.ld(N)
-    X = [eng.rows(P, N), eng.rows(P, N)]
+    X = [eng.rows_scratch(P, N), eng.rows_scratch(P, N)]
     pbestfit, pfit = eng.empty(P), eng.empty(P)
     gbest = eng.zeros(ld)
     d_lower, d_upper = eng.upload_vec(lower, ld), eng.upload_vec(upper, ld)
@@ -126,11 +134,14 @@ def minimize(
             callback(Xh, res)
         return c, xbest
 
-    c, xbest = snapshot(1, 0)
-
     it = 1
     last = max(int(maxiter), 2)
     fast = obj is not None and stream is None and not observe
+    if fast:  # nobody looks at generation 1: no host round trip before the first chunk (status cannot be set yet)
+        c = L.Ctrl()
+        c.status, c.nit = L.SP_RUNNING, 1
+    else:
+        c, xbest = snapshot(1, 0)
     streamer = HistoryStreamer.maybe(eng, hist, callback, P, N) if obj is not None and stream is None else None
     keep = None
     while c.status == L.SP_RUNNING:

@@ -46,5 +46,12 @@ def minimize(fun, bounds, x0=None, args=(), method="de", options=None, callback=
     ('philox': counter-based draws in the kernels; 'numpy': the reference's
     MT19937 draw order from the host, for fixed-seed trajectory parity).
     An unknown method raises KeyError, like the reference."""
-    options = options if options else {}
-    return _optimizer_map[method](fun=fun, bounds=bounds, x0=x0, args=args, callback=callback, **options)
+    options = dict(options) if options else {}
+    fn = _optimizer_map[method]
+    if options.get("backend") == "mpi" and options.get("seed") is None:
+        # the reference's mpi backend broadcasts rank 0's population every generation; here all ranks run
+        # the same optimiser, so they must share one random stream: rank 0's seed
+        from ..parallel import shared_seed
+
+        options["seed"] = shared_seed(None)
+    return fn(fun=fun, bounds=bounds, x0=x0, args=args, callback=callback, **options)

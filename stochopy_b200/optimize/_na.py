@@ -10,12 +10,13 @@ import numpy as np
 import torch
 
 from .. import _lib as L
-from ._common import Engine, History, NumpyStream, device_objective, fresh_seed, messages, validate_common
+from ._common import Engine, History, NumpyStream, device_objective, fresh_seed, messages, validate_common, device_scope
 from ._helpers import OptimizeResult, register
 
 __all__ = ["minimize"]
 
 
+@device_scope
 def minimize(
     fun,
     bounds,

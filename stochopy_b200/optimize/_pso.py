@@ -2,9 +2,12 @@
 from ._cpso import minimize as cpso
 from ._helpers import register
 
+from ._common import device_scope
+
 __all__ = ["minimize"]
 
 
+@device_scope
 def minimize(
     fun,
     bounds,

@@ -14,7 +14,7 @@ import torch
 
 from .. import _lib as L
 from ._cmaes import EsHistory, selection_weights
-from ._common import HistoryStreamer, Engine, NumpyStream, device_objective, fresh_seed, messages, validate_common
+from ._common import HistoryStreamer, Engine, NumpyStream, device_objective, fresh_seed, messages, validate_common, device_scope
 from ._helpers import OptimizeResult, register
 
 __all__ = ["minimize"]
@@ -22,6 +22,7 @@ __all__ = ["minimize"]
 _CONSTRAINTS = {None: L.CONS_NONE, "Penalize": L.CONS_PENALIZE}  # reuses cmaes' Penalize, _vdcma.py:5-6
 
 
+@device_scope
 def minimize(
     fun,
     bounds,
@@ -184,6 +185,8 @@ def minimize(
                 callback(Xh, res)
 
     it = c.base.nit
+    if c.base.status == L.SP_STATUS_INTERNAL:
+        raise L.EngineError("inconsistent device state (ranking without a rank 0)")
     if streamer is not None:
         streamer.finish(hist, it, transform=lambda X: unstd(valid_rows(X)))
     if lean:  # x = xmean_old + sigma * y in the working precision, as the exact kernel stores it (_vdcma.py:249)

@@ -23,7 +23,8 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
-__all__ = ["shard_range", "shard_seeds", "reduce_best", "minimize_seeds", "cpso_sharded", "PeerMailboxes", "evaluate_split"]
+__all__ = ["shard_range", "shard_seeds", "reduce_best", "minimize_seeds", "cpso_sharded", "PeerMailboxes", "evaluate_split",
+           "shared_seed"]
 
 
 def _all_gather_flat(out, part, group):
@@ -87,27 +88,47 @@ class PeerMailboxes:
         self.own, self._opened = None, []
 
 
+def _group_root(group):
+    """Global rank of the group's rank 0 (the broadcast source)."""
+    return dist.get_global_rank(group, 0) if group is not None else 0
+
+
 def evaluate_split(fun, args, rows, group=None):
-    """The reference's ``backend="mpi"`` evaluation (``_common.py:58-72``: every rank holds
-    the population, evaluates the rows ``rank::size`` and an Allreduce(SUM) completes the
-    fitness vector) over ``torch.distributed`` -- for objectives that are expensive *on the
-    host* (SURVEY.md 8f-4).  All ranks run the same optimiser with the same seed, so the
-    population is already identical everywhere and nothing is broadcast; only the
-    per-generation fitness vector (P doubles) is reduced.  Without an initialised process
+    """The reference's ``backend="mpi"`` evaluation (``_common.py:58-72``) over
+    ``torch.distributed`` -- for objectives that are expensive *on the host* (SURVEY.md 8f-4):
+    rank 0's population is broadcast (the reference's ``Bcast(x, root=0)``), every rank
+    evaluates the rows ``rank::size`` and an Allreduce(SUM) completes the fitness vector, so
+    all ranks get the fitness of rank 0's rows whatever their own random streams did.  (The
+    front-ends additionally share rank 0's seed when none was given -- ``shared_seed`` -- so
+    the ranks hold the same population in the first place.)  Without an initialised process
     group this is the serial loop."""
-    rows = np.asarray(rows)
+    rows = np.ascontiguousarray(rows, dtype=np.float64)
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     if world == 1:
         return np.array([fun(r, *args) for r in rows], dtype=np.float64)
     rank = dist.get_rank(group)
+    on_gpu = dist.get_backend(group) == "nccl"
+    dev = torch.device("cuda", torch.cuda.current_device()) if on_gpu else torch.device("cpu")
+    x = torch.from_numpy(rows).to(dev)
+    dist.broadcast(x, src=_group_root(group), group=group)
+    rows = x.cpu().numpy()
     f = np.zeros(len(rows), dtype=np.float64)
     f[rank::world] = [fun(r, *args) for r in rows[rank::world]]
-    on_gpu = dist.get_backend(group) == "nccl"
-    t = torch.from_numpy(f)
-    if on_gpu:
-        t = t.to(torch.device("cuda", torch.cuda.current_device()))
+    t = torch.from_numpy(f).to(dev)
     dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
     return t.cpu().numpy()
+
+
+def shared_seed(seed, group=None):
+    """``backend="mpi"`` with ``seed=None``: every rank would draw its own random seed and hold a
+    different population.  Rank 0 draws one and broadcasts it."""
+    if seed is not None or not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return seed
+    on_gpu = dist.get_backend(group) == "nccl"
+    dev = torch.device("cuda", torch.cuda.current_device()) if on_gpu else torch.device("cpu")
+    t = torch.from_numpy(np.random.SeedSequence().generate_state(1, dtype=np.uint32).astype(np.int64)).to(dev)
+    dist.broadcast(t, src=_group_root(group), group=group)
+    return int(t.cpu().item())
 
 
 def shard_range(total, rank, world):

@@ -160,3 +160,41 @@ def test_sharded_swarm_equals_single_process(opts, exchange):
     assert np.array_equal(solo.x, one.x) and solo.fun == one.fun and (solo.nit, solo.status) == (one.nit, one.status)
     for rank, (x, fun, nit, status) in _spawn(_sharded, 2, o):  # two ranks, odd split 51 + 50
         assert np.array_equal(np.array(x), one.x) and fun == one.fun and (nit, status) == (one.nit, one.status)
+
+
+# ---- the mpi-backend analogue must evaluate rank 0's population on every rank -------------
+def _split_rows(rank, world):
+    rs = np.random.RandomState(100 + rank)  # every rank holds DIFFERENT rows, like unseeded optimisers would
+    rows = rs.uniform(-1, 1, (11, 3))
+    f = parallel.evaluate_split(lambda x: float(np.sum(x * x)), (), rows)
+    seed = parallel.shared_seed(None)
+    return f.tolist(), seed, parallel.shared_seed(7)
+
+
+def test_evaluate_split_broadcasts_rank0_rows_and_shares_a_seed():
+    """reference _common.py:58-72: Bcast(x, root=0), strided evaluation, Allreduce -- all ranks end up with
+    the fitness of rank 0's rows; with seed=None the ranks agree on rank 0's seed."""
+    out = _spawn(_split_rows, 2)
+    want = np.sum(np.random.RandomState(100).uniform(-1, 1, (11, 3)) ** 2, axis=1)
+    for _, (f, seed, given) in out:
+        assert np.allclose(f, want, rtol=1e-15)
+        assert given == 7
+    assert out[0][1][1] == out[1][1][1] and out[0][1][1] is not None
+
+
+# ---- real multi-GPU run (driver-visible): sharded swarm == single GPU bitwise, seeds agree ---------------
+@pytest.mark.gpu
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_multi_gpu_sharded_swarm_equals_single_gpu(world):
+    """tests/multi_gpu_check.py under torchrun on `world` real GPUs (NCCL + NVLink peer mailboxes); skipped
+    when the box has fewer devices."""
+    import subprocess
+    import sys
+
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs, box has {torch.cuda.device_count()}")
+    here = os.path.dirname(os.path.abspath(__file__))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+           "--master-addr", "127.0.0.1", "--master-port", str(_free_port()), os.path.join(here, "multi_gpu_check.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "multi_gpu_check ok" in r.stdout, (r.stdout[-2000:], r.stderr[-4000:])
