@@ -7,9 +7,11 @@ termination disabled (xtol=-1, ftol=-1e300).  One *step* = one generation = one
 launch of the fused DE kernel over the whole population (65536 evaluations).
 
   value   device-resident throughput: K generations, each timed with CUDA events on
-          the launching stream, L2 flushed (256 MiB write) before every generation
-          so the population comes from HBM (the 2 x 32 MiB ping-pong state would
-          otherwise live in the 126 MB L2); `value_l2_resident` is the same loop
+          the launching stream, L2 flushed before every generation (256 MiB write, then a
+          256 MiB read: the L2 is full of clean foreign lines) so the population comes
+          from HBM (the 2 x 32 MiB ping-pong state would otherwise live in the 126 MB
+          L2); `value_dirty_flush`: write-only flush as in round 1 (the kernel then also
+          pays the write-back of the flush buffer); `value_l2_resident` is the same loop
           without the flush, i.e. what an actual run sees; `value_kernel_only` subtracts
           what an empty event pair costs on this stream (launch / record overhead that
           `value` includes in every step).
@@ -345,8 +347,15 @@ def our_arm(args):
     rs = np.random.RandomState(seed)
     x0_pin = torch.from_numpy(rs.uniform(-BOUND, BOUND, (P, N)).astype(np.float32)).pin_memory()
     x0 = x0_pin.numpy()  # host buffer in page-locked memory: what minimize() is handed in the e2e leg
-    st, keep = build_state(eng, L, x0, seed, 2 * (K + W) + 10)
+    st, keep = build_state(eng, L, x0, seed, 3 * (K + W) + 20)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=eng.device)
+    flush_src = torch.zeros(64 << 20, dtype=torch.float32, device=eng.device)  # 256 MiB, only ever read (fp32: sum() reads it in place)
+
+    def flush_l2(k):
+        """256 MiB write (evicts everything), then a 256 MiB read: the L2 is left full of CLEAN foreign lines,
+        so the timed kernel is not charged the write-back of ~126 MB of the flush buffer's dirty lines."""
+        flush.fill_(k & 1)
+        return flush_src.sum()
 
     def barrier():
         if world > 1:
@@ -363,7 +372,7 @@ def our_arm(args):
     it = 2
     nvtx.range_push("warmup")
     for _ in range(max(W, 3)):  # warm-up
-        flush.fill_(1)
+        flush_l2(1)
         L.call("sp_de_generation", C.byref(st), it, eng.stream)
         it += 1
     nvtx.range_pop()
@@ -377,7 +386,7 @@ def our_arm(args):
         nvtx.range_push("timed: HBM-cold generations")
         wall0 = time.perf_counter()
         for k in range(K):
-            flush.fill_(k & 1)
+            flush_l2(k)
             ev[k][0].record()
             # chained like sp_de_run does it: generation k resolves the argmin / gbest / status of
             # generation k-1 in its prologue and leaves its own to k+1; the last one resolves itself
@@ -389,6 +398,17 @@ def our_arm(args):
         wall_cold = time.perf_counter() - wall0
         launches = L.launch_count() - launches0
         cold_ms = max_over_ranks(sum(a.elapsed_time(b) for a, b in ev))
+        # round 1's flush for comparison: write only -- the L2 is then full of the flush buffer's DIRTY lines and
+        # every line the kernel brings in forces one of them out to HBM first
+        evd = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+        for k in range(K):
+            flush.fill_(k & 1)
+            evd[k][0].record()
+            L.call("sp_de_generation_chained", C.byref(st), it, (1 if k > 0 else 0) | (2 if k < K - 1 else 0), eng.stream)
+            evd[k][1].record()
+            it += 1
+        barrier()
+        dirty_ms = max_over_ranks(sum(a.elapsed_time(b) for a, b in evd))
         # what an event pair with nothing between it costs on this stream (inside every step of `value`)
         for a, b in ev0:
             flush[: 1 << 20].fill_(0)
@@ -448,11 +468,16 @@ def our_arm(args):
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"DE best1bin, Rosenbrock ndim={N}, popsize={P} per GPU, fp32, bounds +-{BOUND}, "
                                    "one independent seed per GPU, in-kernel Philox draws",
-                       "popsize": P, "ndim": N, "l2": "flushed (256 MiB write) before every timed generation",
+                       "popsize": P, "ndim": N,
+                       "l2": "flushed before every timed generation: 256 MiB write, then a 256 MiB read so that the lines "
+                             "the kernel evicts are clean (value_dirty_flush: write only, as in round 1 -- the kernel then "
+                             "also pays the write-back of the flush buffer's dirty lines)",
                        "timing": "CUDA events around each generation launch, summed; max over ranks; generations chained "
                                  "as in sp_de_run (each launch resolves the previous generation's argmin/gbest/status "
                                  "in its prologue, the last one its own)",
                        "best_fun_over_seeds": best_fun},
+            "value_dirty_flush": world * P * K / (dirty_ms * 1e-3),
+            "ms_per_step_dirty_flush": dirty_ms / K,
             "value_l2_resident": world * P * K / (warm_ms * 1e-3),
             "ms_per_step_l2_resident": warm_ms / K,
             "value_kernel_only": world * P * K / (kern_ms * 1e-3),

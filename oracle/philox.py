@@ -3,6 +3,7 @@
 The CUDA kernels draw from Philox4x32-10 (Salmon et al., SC'11) with
   key     = (seed & 0xffffffff, seed >> 32)
   counter = (block, row, generation, purpose)
+(the DE crossover decisions: 16-bit pieces of Philox2x32-10, see de_cross_uniform)
 so that a draw depends only on *what it is for*, never on the launch shape or
 on how many GPUs share the work.  This file reproduces those draws bit for bit
 (integers, uniforms) or to libm accuracy (Box-Muller normals) so the oracle's
@@ -115,6 +116,37 @@ def normal(rows, ncols, gen, purpose, seed, dtype):
     out[:, :, 0] = r * np.cos(np.pi * (2.0 * u2))
     out[:, :, 1] = r * np.sin(np.pi * (2.0 * u2))
     return out.reshape(len(rows), nb * 2)[:, :ncols]
+
+
+M2 = np.uint64(0xD256D193)
+
+
+def philox2x32(c0, c1, key, rounds=10):
+    """Vectorised Philox2x32-R (Salmon et al., SC'11): counter (c0, c1), 32-bit key bumped by W0 per round."""
+    c0, c1 = np.broadcast_arrays(*(np.asarray(c, dtype=np.uint64) & MASK32 for c in (c0, c1)))
+    c0, c1 = c0.copy(), c1.copy()
+    k = int(key) & 0xFFFFFFFF
+    for _ in range(rounds):
+        p = M2 * c0
+        c0, c1 = (p >> np.uint64(32)) ^ np.uint64(k) ^ c1, p & MASK32
+        k = (k + W0) & 0xFFFFFFFF
+    return c0, c1
+
+
+def de_cross_uniform(P, N, gen, seed, dtype):
+    """The DE crossover uniforms of the device (csrc/philox.cuh "DE crossover stream"): 16-bit pieces.
+    Stream id (key, o0, o1) = words 0..2 of Philox4x32-10(counter (0, 0, gen, DE_CROSS), seed); per row and
+    group of 4 columns (x, y) = Philox2x32-10(counter (row + o0, group ^ o1), key); column j takes piece j & 3 of
+    (x >> 16, x & 0xffff, y >> 16, y & 0xffff); u = piece * 2^-16 (exact in fp32 and fp64)."""
+    sk = philox4x32(0, 0, gen, DE_CROSS, seed, rounds=10)
+    key, o0, o1 = (int(np.asarray(w).reshape(-1)[0]) for w in sk[:3])
+    ng = _blocks(N, 4)
+    rows = (np.arange(P, dtype=np.uint64)[:, None] + np.uint64(o0)) & MASK32
+    groups = np.arange(ng, dtype=np.uint64)[None, :] ^ np.uint64(o1)
+    x, y = philox2x32(rows, groups, key)
+    lo = np.uint64(0xFFFF)
+    pieces = np.stack((x >> np.uint64(16), x & lo, y >> np.uint64(16), y & lo), axis=-1).reshape(P, ng * 4)[:, :N]
+    return (pieces.astype(np.float64) * 2.0**-16).astype(dtype)
 
 
 def _mulhi(word, n):

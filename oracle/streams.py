@@ -90,7 +90,7 @@ class PhiloxStream:
         return jitter, perms
 
     def de(self, it, P, N, k, lower, upper, repair):
-        r1 = px.uniform(np.arange(P), N, it, px.DE_CROSS, self.seed, self.dtype)
+        r1 = px.de_cross_uniform(P, N, it, self.seed, self.dtype)
         irand, donors = px.de_indices(P, N, k, it, self.seed)
         rep = None
         if repair:

@@ -216,7 +216,34 @@ def check(rc):
         raise EngineError(f"libstochopy_b200 error {rc}: {msg}")
 
 
+# NVTX: one range per optimiser run (optimize/_helpers.py) always; with SP_NVTX=1 also one range per C-ABI
+# call (a chunk of generations / a chain stage), named after the entry point -- off by default because the
+# per-generation host paths would pay ~2 us per call for it.
+_NVTX_CALLS = os.environ.get("SP_NVTX", "") not in ("", "0")
+
+
+def nvtx_range(name):
+    """Context manager: an NVTX range (visible in Nsight Systems / ncu --nvtx) around a block of host code."""
+    import contextlib
+
+    import torch
+
+    @contextlib.contextmanager
+    def _range():
+        torch.cuda.nvtx.range_push(name)
+        try:
+            yield
+        finally:
+            torch.cuda.nvtx.range_pop()
+
+    return _range()
+
+
 def call(name, *args):
+    if _NVTX_CALLS:
+        with nvtx_range(name):
+            check(getattr(load(), name)(*args))
+        return
     check(getattr(load(), name)(*args))
 
 

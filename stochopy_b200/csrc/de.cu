@@ -21,7 +21,7 @@ static const bool g_force_direct = getenv("SP_DE_DIRECT") != nullptr;
 
 template <typename T, int CH, int LPR, bool PHILOX>
 __global__ void __launch_bounds__(kThreads)
-de_generation_kernel(const DeArgs<T> a) {
+de_generation_kernel(const DeArgs<T> a, const CrossKeys keys) {
   using TL = Tile<T, CH, LPR>;
   constexpr int VEC = Num<T>::VEC;
   if (!running(a.ctrl)) return;
@@ -103,17 +103,20 @@ de_generation_kernel(const DeArgs<T> a) {
     for (int c = 0; c < CH; ++c) {
       const int j0 = TL::col(c, l, 0);
       if (j0 < a.N) {
-        T r[VEC];
-        if (PHILOX) {
-          uniform_block(philox4x32((uint32_t)(j0 / VEC), (uint32_t)row, (uint32_t)a.it, kDeCross, a.seed), r);
+        bool tk[VEC];
+        if (PHILOX) {  // 16-bit pieces of one Philox2x32-10 call per 4 columns (philox.cuh: DE crossover stream)
+          bool t4[4];
+          de_cross_take((uint32_t)row, (uint32_t)(j0 >> 2), keys, t4);
+#pragma unroll
+          for (int e = 0; e < VEC; ++e) tk[e] = VEC == 4 ? t4[e] : ((j0 & 2) ? t4[2 + (e & 1)] : t4[e & 1]);
         } else {
 #pragma unroll
-          for (int e = 0; e < VEC; ++e) r[e] = (j0 + e < a.N) ? a.r1[row * a.ld + j0 + e] : T(2);
+          for (int e = 0; e < VEC; ++e) tk[e] = (j0 + e < a.N) ? (a.r1[row * a.ld + j0 + e] <= a.CR) : false;
         }
 #pragma unroll
         for (int e = 0; e < VEC; ++e) {
           const int j = j0 + e;
-          const bool take = (j == irand) || (r[e] <= a.CR);
+          const bool take = (j == irand) || tk[e];
           u.v[c][e] = (take && j < a.N) ? u.v[c][e] : xi.v[c][e];
         }
         if (a.constraint == SP_CONS_RANDOM) {
@@ -211,7 +214,6 @@ static int de_launch(const sp_de_state* st, int it, int propose_only, int chain,
     return SP_ERR_ARG;
   }
   if (pool) {
-    a.cr_cut = crossover_cut<T>(st->CR);
     a.chain = propose_only ? 0 : chain;
     cudaError_t e = de_tma_dispatch(a, sh.ch, s);
     if (e != cudaSuccess) {
@@ -222,10 +224,11 @@ static int de_launch(const sp_de_state* st, int it, int propose_only, int chain,
     return SP_OK;
   }
   const int grid = grid_for_rows(st->P, sh.lpr, sh.ch >= 4 ? 2 : 4);
+  const CrossKeys ck = de_cross_keys(a.seed, a.it, (double)a.CR);
 #define SP_CALL(TT, C, L)                                                        \
   do {                                                                           \
-    if (philox) de_generation_kernel<TT, C, L, true><<<grid, kThreads, 0, s>>>(a); \
-    else de_generation_kernel<TT, C, L, false><<<grid, kThreads, 0, s>>>(a);     \
+    if (philox) de_generation_kernel<TT, C, L, true><<<grid, kThreads, 0, s>>>(a, ck); \
+    else de_generation_kernel<TT, C, L, false><<<grid, kThreads, 0, s>>>(a, ck);     \
   } while (0)
   SP_DISPATCH_SHAPE(T, sh, SP_CALL);
 #undef SP_CALL

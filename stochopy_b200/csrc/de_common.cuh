@@ -25,8 +25,7 @@ struct DeArgs {
   const int64_t* donors;
   const int64_t* irand;
   const T* repair;
-  int chain;        // SP_CHAIN_IN / SP_CHAIN_OUT (pool kernel only)
-  uint64_t cr_cut;  // integer form of `r <= CR` for the Philox words (crossover_cut)
+  int chain;  // SP_CHAIN_IN / SP_CHAIN_OUT (pool kernel only)
 };
 
 __host__ __device__ constexpr int de_donor_count(int strategy) {
@@ -67,23 +66,6 @@ __device__ __forceinline__ void draw_donors(uint32_t row, uint32_t P, int k, int
   }
 }
 
-
-// `u <= CR` on the raw Philox words, bit-identical to comparing the converted
-// uniform: fp32 u = (w >> 8) * 2^-24  ->  w <= cut32;  fp64 u = m53 * 2^-53 -> m53 <= cut53.
-template <typename T>
-inline uint64_t crossover_cut(double CR);
-template <>
-inline uint64_t crossover_cut<float>(double CR) {
-  const double t = (double)(float)CR * 16777216.0;
-  if (t < 0.0) return 0;  // unreachable (CR is validated to [0,1]); word 0 still passes like u = 0 <= CR
-  const uint64_t thr = (uint64_t)t;
-  return thr >= (1ull << 24) ? 0xFFFFFFFFull : ((thr << 8) | 0xFFull);
-}
-template <>
-inline uint64_t crossover_cut<double>(double CR) {
-  const double t = CR * 9007199254740992.0;
-  return t < 0.0 ? 0 : (uint64_t)t;
-}
 
 // pool kernel (de_tma.cuh), one translation unit per (dtype, strategy)
 bool de_tma_fits(int ch, int64_t P, int K, int64_t ld, size_t elem);

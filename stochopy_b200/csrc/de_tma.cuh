@@ -29,8 +29,6 @@ struct Strat {
 };
 
 
-__device__ __forceinline__ bool cross_take(uint32_t w, uint64_t cut) { return w <= (uint32_t)cut; }
-__device__ __forceinline__ bool cross_take(unsigned long long m53, uint64_t cut) { return m53 <= cut; }
 
 // own row + K donor rows of one individual, in registers
 template <typename T, int CH, int K>
@@ -65,26 +63,32 @@ __device__ __forceinline__ void mutant(const RowSet<T, CH, Strat<STRAT>::K>& r, 
 
 constexpr int kPoolStages = 3;
 
+// Per-row record of the slice tables, at a FIXED shared-memory offset so every access in the row loop is
+// `[row * stride + immediate]`: word 0 = forced crossover column, words 1..K = donor rows, then (aligned to
+// sizeof(T)) the personal best fitness and the candidate fitness of this generation.
+template <typename T, int K>
+struct PoolRec {
+  static constexpr int kT = (int)(sizeof(T) / 4);
+  static constexpr int kBest = ((1 + K + kT - 1) / kT) * kT;
+  static constexpr int kFnew = kBest + kT;
+  static constexpr int kWords = ((kFnew + kT + 3) / 4) * 4;
+  static constexpr int kBytes = kWords * 4;
+};
+constexpr uint32_t kPoolRecBase = 16;  // [0,16): claim counter
+
 // shared-memory carve-up (bytes), identical on host and device
 struct PoolLayout {
-  uint32_t bars, queue, ir, don, best, fnew, ring, total;
+  uint32_t bars, queue, ring, total;
 };
-__host__ __device__ inline PoolLayout pool_layout(int warps, int nb, int K, int64_t ld, size_t elem, bool with_ring = true) {
+__host__ __device__ inline PoolLayout pool_layout(int warps, int nb, int rec_bytes, int K, int64_t ld, size_t elem,
+                                                  bool with_ring = true) {
   PoolLayout L;
   auto up16 = [](uint32_t v) { return (v + 15u) & ~15u; };
-  uint32_t o = 16;  // [0,16): claim counter
+  uint32_t o = up16(kPoolRecBase + (uint32_t)nb * (uint32_t)rec_bytes);
   L.bars = o;
-  o = up16(o + (uint32_t)warps * kPoolStages * 8);
+  if (with_ring) o = up16(o + (uint32_t)warps * kPoolStages * 8);
   L.queue = o;
-  o = up16(o + (uint32_t)warps * kPoolStages * 4);
-  L.ir = o;
-  o = up16(o + (uint32_t)nb * 4);
-  L.don = o;
-  o = up16(o + (uint32_t)nb * 4 * (uint32_t)K);
-  L.best = o;
-  o = up16(o + (uint32_t)nb * (uint32_t)elem);
-  L.fnew = o;
-  o = up16(o + (uint32_t)nb * (uint32_t)elem);
+  if (with_ring) o = up16(o + (uint32_t)warps * kPoolStages * 4);
   o = (o + 127u) & ~127u;
   L.ring = o;
   if (with_ring) o += (uint32_t)warps * kPoolStages * (uint32_t)K * (uint32_t)ld * (uint32_t)elem;
@@ -98,30 +102,28 @@ __host__ __device__ inline PoolLayout pool_layout(int warps, int nb, int K, int6
 // ring costs ~45 warp instructions per row (mbarrier wait, elected-lane issue, uniform-register
 // traffic, queue) against ~10 for two address computations and loads, and with 32 warps per SM
 // one row of lookahead (~2000 cycles) already covers the L2 / HBM latency.
-template <typename T, int CH, int STRAT, bool FULL, bool PLAIN, bool RING>
+// OBJ >= 0: the objective is a compile-time constant (no jump table in the row loop); -1: a.objective.
+template <typename T, int CH, int STRAT, bool FULL, bool PLAIN, bool RING, int OBJ>
 __global__ void __launch_bounds__(1024 / CH, 1)
-de_pool_kernel(const DeArgs<T> a, int nb, const PhiloxKeys keys) {
+de_pool_kernel(const DeArgs<T> a, int nb, const CrossKeys keys) {
   using TL = Tile<T, CH, 32>;
   using V = typename Num<T>::vec_t;
   constexpr int VEC = Num<T>::VEC;
   constexpr int K = Strat<STRAT>::K;
   constexpr int S = kPoolStages;
   using RS = RowSet<T, CH, K>;
+  using Rec = PoolRec<T, K>;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5, warps = blockDim.x >> 5;
   const int ld = FULL ? TL::COLS : (int)a.ld;
   const int N = FULL ? TL::COLS : a.N;
-  const PoolLayout L = pool_layout(warps, nb, K, ld, sizeof(T), RING);
   int* s_next = reinterpret_cast<int*>(smem_raw);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + L.bars) + wib * S;
-  int* queue = reinterpret_cast<int*>(smem_raw + L.queue) + wib * S;
-  int* tab_ir = reinterpret_cast<int*>(smem_raw + L.ir);
-  uint32_t* tab_d = reinterpret_cast<uint32_t*>(smem_raw + L.don);  // [K][nb]
-  T* s_best = reinterpret_cast<T*>(smem_raw + L.best);
-  T* s_fnew = reinterpret_cast<T*>(smem_raw + L.fnew);
+  unsigned char* recs = smem_raw + kPoolRecBase;  // compile-time offset: accesses are [row * kBytes + imm]
+  auto rec_u32 = [&](int r, int w) -> uint32_t& { return *reinterpret_cast<uint32_t*>(recs + r * Rec::kBytes + 4 * w); };
+  auto rec_best = [&](int r) -> T& { return *reinterpret_cast<T*>(recs + r * Rec::kBytes + 4 * Rec::kBest); };
+  auto rec_fnew = [&](int r) -> T& { return *reinterpret_cast<T*>(recs + r * Rec::kBytes + 4 * Rec::kFnew); };
   const uint32_t row_bytes = (uint32_t)(ld * sizeof(T));
   const uint32_t stage_elems = (uint32_t)K * (uint32_t)ld;  // a stage = the K donor rows
-  T* ring = reinterpret_cast<T*>(smem_raw + L.ring) + (size_t)wib * S * stage_elems;
 
   // slice of this CTA
   const int64_t q = a.P / gridDim.x, rem = a.P % gridDim.x;
@@ -132,18 +134,13 @@ de_pool_kernel(const DeArgs<T> a, int nb, const PhiloxKeys keys) {
   // (an explicit cp.async.bulk.prefetch.L2 of the CTA's slice was measured slower when the L2 is
   // full of dirty lines: 38.3 vs 36.1 us per generation -- demand fetches are left alone)
   if (tid == 0) *s_next = 0;
-  if (RING && lane == 0) {
-#pragma unroll
-    for (int s = 0; s < S; ++s) mbar_init(&bars[s], 1);
-    mbar_fence_init();
-  }
   for (int t = tid; t < rows; t += blockDim.x) {
     uint32_t dd[5];
     int ir;
     draw_donors((uint32_t)(b0 + t), (uint32_t)a.P, K, a.it, a.seed, a.N, dd, &ir);
-    tab_ir[t] = ir;
+    rec_u32(t, 0) = (uint32_t)ir;
 #pragma unroll
-    for (int k = 0; k < K; ++k) tab_d[k * nb + t] = dd[k];
+    for (int k = 0; k < K; ++k) rec_u32(t, 1 + k) = dd[k];
   }
   // Programmatic dependent launch: everything above depends only on (seed, generation), so
   // it overlaps the tail of the previous generation's kernel; from here on we read what that
@@ -157,10 +154,9 @@ de_pool_kernel(const DeArgs<T> a, int nb, const PhiloxKeys keys) {
     if (lane == 0) s_top = b;
   }
   pdl_launch_dependents();  // the next generation may start its own prologue as SMs free up
-  for (int t = tid; t < rows; t += blockDim.x) s_best[t] = a.pbestfit[b0 + t];
+  for (int t = tid; t < rows; t += blockDim.x) rec_best(t) = a.pbestfit[b0 + t];
   TL gb;
   if (Strat<STRAT>::kBest && !chain_in) gb.load(a.gbest, lane, ld);
-  const uint64_t cut = a.cr_cut;
   const T F = a.F;
   const uint32_t it = (uint32_t)a.it;
   __syncthreads();
@@ -175,54 +171,36 @@ de_pool_kernel(const DeArgs<T> a, int nb, const PhiloxKeys keys) {
 
   // ---- phase 1: claim / fetch / process ----------------------------------------------------
   const uint32_t s_next_addr = smem_u32(s_next);
-  auto claim = [&]() {  // one elected lane claims (elect.sync: ptxas then emits no warp-aggregation preamble)
+  auto claim = [&](uint32_t n) {  // one elected lane claims n rows (elect.sync: no warp-aggregation preamble)
     int r = 0;
     uint32_t leader = 0;
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
         "elect.sync %1|p, 0xffffffff;\n"
-        "@p atom.shared.add.u32 %0, [%2], 1;\n"
+        "@p atom.shared.add.u32 %0, [%2], %3;\n"
         "}\n"
         : "+r"(r), "+r"(leader)
-        : "r"(s_next_addr)
+        : "r"(s_next_addr), "r"(n)
         : "memory");
     return __shfl_sync(0xffffffffu, r, leader);
   };
-  auto issue = [&](int st, int r) {  // one elected lane fills stage `st` with the donors of row r
-    if (lane == 0) {
-      T* dst = ring + (size_t)st * stage_elems;
-      mbar_expect_tx(&bars[st], (uint32_t)K * row_bytes);
-#pragma unroll
-      for (int k = 0; k < K; ++k)
-        tma_load_row(dst + (size_t)k * ld, a.Xold + (int64_t)tab_d[k * nb + r] * ld, row_bytes, &bars[st]);
-      queue[st] = r;
-    }
-  };
   // crossover, repair, objective, selection and store of one individual (u: mutant, xi: own row)
   auto finish = [&](TL& u, const TL& xi, int r) {
-    const int irand = tab_ir[r];
+    const int irand = (int)rec_u32(r, 0);
     const uint32_t row = (uint32_t)(b0 + r);
     // binomial crossover (_de.py:339-344) and Random repair (de/_constraints.py:22-26)
 #pragma unroll
     for (int c = 0; c < CH; ++c) {
       const int j0 = TL::col(c, lane, 0);
       if (FULL || j0 < N) {
-        const uint4 o = philox4x32_keyed((uint32_t)(j0 / VEC), row, it, kDeCross, keys);
-        bool take[VEC];
-        if (VEC == 4) {
-          take[0] = cross_take(o.x, cut);
-          take[1] = cross_take(o.y, cut);
-          take[2 % VEC] = cross_take(o.z, cut);
-          take[3 % VEC] = cross_take(o.w, cut);
-        } else {
-          take[0] = cross_take(((unsigned long long)o.x << 21) | (o.y >> 11), cut);
-          take[1] = cross_take(((unsigned long long)o.z << 21) | (o.w >> 11), cut);
-        }
+        bool t4[4];
+        de_cross_take(row, (uint32_t)(j0 >> 2), keys, t4);
+        const int d = irand - j0;  // the forced column, relative to this vector
 #pragma unroll
         for (int e = 0; e < VEC; ++e) {
-          const int jj = j0 + e;
-          const bool t = (take[e] || jj == irand) && (FULL || jj < N);
+          const bool tk = VEC == 4 ? t4[e] : ((j0 & 2) ? t4[2 + (e & 1)] : t4[e & 1]);
+          const bool t = (tk || d == e) && (FULL || j0 + e < N);
           u.v[c][e] = t ? u.v[c][e] : xi.v[c][e];
         }
         if (!PLAIN && a.constraint == SP_CONS_RANDOM) {
@@ -254,21 +232,39 @@ de_pool_kernel(const DeArgs<T> a, int nb, const PhiloxKeys keys) {
       u.store(out_row, lane, ld);
       return;
     }
-    const T f = evaluate_tile<T, CH, 32>(a.objective, u, lane, N);
-    const T old = s_best[r];
-    const bool win = f < old;  // strict, _common.py:127
+    const T f = evaluate_tile<T, CH, 32>(OBJ >= 0 ? OBJ : a.objective, u, lane, N);
+    const bool win = f < rec_best(r);  // strict, _common.py:127
     if (win) u.store(out_row, lane, ld);  // two predicated 16-byte stores instead of a select per scalar
     else xi.store(out_row, lane, ld);
-    if (lane == 0) {
-      s_fnew[r] = f;
-      if (win) s_best[r] = f;
-    }
+    // every lane holds the same f: same-address, same-value stores need no lane-0 branch
+    rec_fnew(r) = f;
+    if (win) rec_best(r) = f;
   };
 
   if (RING) {
-  #pragma unroll
+    const PoolLayout L = pool_layout(warps, nb, Rec::kBytes, K, ld, sizeof(T), true);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + L.bars) + wib * S;
+    int* queue = reinterpret_cast<int*>(smem_raw + L.queue) + wib * S;
+    T* ring = reinterpret_cast<T*>(smem_raw + L.ring) + (size_t)wib * S * stage_elems;
+    if (lane == 0) {
+#pragma unroll
+      for (int s = 0; s < S; ++s) mbar_init(&bars[s], 1);
+      mbar_fence_init();
+    }
+    __syncwarp();
+    auto issue = [&](int st, int r) {  // one elected lane fills stage `st` with the donors of row r
+      if (lane == 0) {
+        T* dst = ring + (size_t)st * stage_elems;
+        mbar_expect_tx(&bars[st], (uint32_t)K * row_bytes);
+#pragma unroll
+        for (int k = 0; k < K; ++k)
+          tma_load_row(dst + (size_t)k * ld, a.Xold + (int64_t)rec_u32(r, 1 + k) * ld, row_bytes, &bars[st]);
+        queue[st] = r;
+      }
+    };
+#pragma unroll
     for (int st = 0; st < S; ++st) {
-      const int r = claim();
+      const int r = claim(1);
       if (r < rows) issue(st, r);
       else if (lane == 0) queue[st] = r;
     }
@@ -291,16 +287,16 @@ de_pool_kernel(const DeArgs<T> a, int nb, const PhiloxKeys keys) {
       mbar_wait(&bars[st], (n / S) & 1u);
       const T* sx = ring + (size_t)st * stage_elems;
       auto lds = [&](TL& t, int slot) {
-  #pragma unroll
+#pragma unroll
         for (int c = 0; c < CH; ++c) {
           const int j0 = TL::col(c, lane, 0);
           if (FULL || j0 < ld) {
             V v = *reinterpret_cast<const V*>(sx + (size_t)slot * ld + j0);
             const T* p = reinterpret_cast<const T*>(&v);
-  #pragma unroll
+#pragma unroll
             for (int e = 0; e < VEC; ++e) t.v[c][e] = p[e];
           } else {
-  #pragma unroll
+#pragma unroll
             for (int e = 0; e < VEC; ++e) t.v[c][e] = T(0);
           }
         }
@@ -308,13 +304,13 @@ de_pool_kernel(const DeArgs<T> a, int nb, const PhiloxKeys keys) {
       TL u;
       {
         RS cur;
-  #pragma unroll
+#pragma unroll
         for (int k = 0; k < K; ++k) lds(cur.d[k], k);
         mutant<T, CH, STRAT>(cur, gb, F, u);
       }
       __syncwarp();  // every lane holds its part of the stage: hand it back and refill it
       {
-        const int r2 = claim();
+        const int r2 = claim(1);
         if (r2 < rows) issue(st, r2);
         else if (lane == 0) queue[st] = r2;
       }
@@ -322,30 +318,39 @@ de_pool_kernel(const DeArgs<T> a, int nb, const PhiloxKeys keys) {
       finish(u, xi, r);
     }
   } else {
-    // rows travel through registers: while row A is processed, row B (own + K donor rows) is in flight
-    // (measured: a compile-time objective -- no jump table in evaluate_tile -- makes ptxas spill at the
-    // 64-register cap and is slower, 34.6 vs 28.1 us HBM-cold; the run-time switch stays)
+    // rows travel through registers: while row A is processed, row B (own + K donor rows) is in flight.
+    // Rows are claimed in PAIRS (2c, 2c+1): one shared atomic per two rows.
     // (measured: claiming two rows ahead and requesting the third row's lines with prefetch.global.L2
     // is slower, HBM-cold 30.1 vs 28.4 us per generation -- one row of lookahead is left alone)
     RS A, B;
     auto fetch = [&](RS& t, int r) {
       t.x.load(a.Xold + (b0 + r) * ld, lane, ld);
+      if (K <= 3) {
+        const uint4 rec = *reinterpret_cast<const uint4*>(recs + r * Rec::kBytes);  // (irand, d0, d1, d2)
+        const uint32_t dn[3] = {rec.y, rec.z, rec.w};
 #pragma unroll
-      for (int k = 0; k < K; ++k) t.d[k].load(a.Xold + (int64_t)tab_d[k * nb + r] * ld, lane, ld);
+        for (int k = 0; k < K; ++k) t.d[k].load(a.Xold + (int64_t)dn[k % 3] * ld, lane, ld);
+      } else {
+#pragma unroll
+        for (int k = 0; k < K; ++k) t.d[k].load(a.Xold + (int64_t)rec_u32(r, 1 + k) * ld, lane, ld);
+      }
     };
-    int ra = claim();
-    if (ra < rows) fetch(A, ra);
+    // (fetches are unconditional on a clamped row: a predicated fetch makes ptxas load into temporaries and
+    // copy 12 registers per row; the price is one wasted row load per warp at the end of the slice)
+    const int last = rows - 1;
+    int ra = claim(2);
+    fetch(A, ra < last ? ra : last);
     while (ra < rows) {
-      int rb = claim();
-      if (rb < rows) fetch(B, rb);
+      const int rb = ra + 1;
+      fetch(B, rb < last ? rb : last);
       {
         TL u;
         mutant<T, CH, STRAT>(A, gb, F, u);
         finish(u, A.x, ra);
       }
       if (rb >= rows) break;
-      ra = claim();
-      if (ra < rows) fetch(A, ra);
+      ra = claim(2);
+      fetch(A, ra < last ? ra : last);
       {
         TL u;
         mutant<T, CH, STRAT>(B, gb, F, u);
@@ -359,9 +364,9 @@ de_pool_kernel(const DeArgs<T> a, int nb, const PhiloxKeys keys) {
   __syncthreads();
   Best mine{1.0 / 0.0, 0x7fffffffffffffffLL};
   for (int t = tid; t < rows; t += blockDim.x) {
-    const T b = s_best[t];
+    const T b = rec_best(t);
     a.pbestfit[b0 + t] = b;
-    a.pfit[b0 + t] = s_fnew[t];
+    a.pfit[b0 + t] = rec_fnew(t);
     if (better((double)b, b0 + t, mine.f, mine.row)) mine = Best{(double)b, b0 + t};
   }
   if (a.chain & SP_CHAIN_OUT) {  // leave the CTA minimum for the next launch's prologue
@@ -381,7 +386,7 @@ struct PoolShape {
   size_t smem;
 };
 template <int CH>
-inline bool pool_shape(int64_t P, int K, int64_t ld, size_t elem, PoolShape* ps, bool with_ring = true) {
+inline bool pool_shape(int64_t P, int rec_bytes, int K, int64_t ld, size_t elem, PoolShape* ps, bool with_ring = true) {
   const int sms = sm_count();
   int64_t grid = P < sms ? P : sms;
   const int nb = (int)((P + grid - 1) / grid);
@@ -389,7 +394,7 @@ inline bool pool_shape(int64_t P, int K, int64_t ld, size_t elem, PoolShape* ps,
   int wmax = 32 / CH;
   if (env_w != nullptr && atoi(env_w) >= 1 && atoi(env_w) < wmax) wmax = atoi(env_w);
   for (int warps = wmax; warps >= 1; warps = warps > 1 && (warps & (warps - 1)) ? warps - 1 : warps >> 1) {
-    const PoolLayout L = pool_layout(warps, nb, K, ld, elem, with_ring);
+    const PoolLayout L = pool_layout(warps, nb, rec_bytes, K, ld, elem, with_ring);
     if (L.total <= 220 * 1024) {
       *ps = {(int)grid, warps * 32, nb, L.total};
       return true;
@@ -397,12 +402,18 @@ inline bool pool_shape(int64_t P, int K, int64_t ld, size_t elem, PoolShape* ps,
   }
   return false;
 }
+inline int pool_rec_bytes(int K, size_t elem) {  // PoolRec<T, K>::kBytes without the types
+  const int kt = (int)(elem / 4);
+  const int best = ((1 + K + kt - 1) / kt) * kt;
+  return ((best + 2 * kt + 3) / 4) * 16;
+}
 
-template <typename T, int CH, int STRAT, bool FULL, bool PLAIN, bool RING>
+template <typename T, int CH, int STRAT, bool FULL, bool PLAIN, bool RING, int OBJ>
 static cudaError_t de_pool_launch_v(const DeArgs<T>& a, cudaStream_t s) {
-  auto kern = de_pool_kernel<T, CH, STRAT, FULL, PLAIN, RING>;
+  auto kern = de_pool_kernel<T, CH, STRAT, FULL, PLAIN, RING, OBJ>;
+  constexpr int K = Strat<STRAT>::K;
   PoolShape ps;
-  if (!pool_shape<CH>(a.P, Strat<STRAT>::K, a.ld, sizeof(T), &ps, RING)) return cudaErrorInvalidConfiguration;
+  if (!pool_shape<CH>(a.P, PoolRec<T, K>::kBytes, K, a.ld, sizeof(T), &ps, RING)) return cudaErrorInvalidConfiguration;
   static thread_local size_t configured[64];
   int dev = 0;
   cudaGetDevice(&dev);
@@ -422,18 +433,29 @@ static cudaError_t de_pool_launch_v(const DeArgs<T>& a, cudaStream_t s) {
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, kern, a, ps.nb, philox_keys(a.seed));
+  return cudaLaunchKernelEx(&cfg, kern, a, ps.nb, de_cross_keys(a.seed, a.it, (double)a.CR));
 }
 
 // register-pipelined variant where two row sets fit the register budget, TMA ring otherwise
-// (SP_DE_RING=1 forces the ring: profiling switch)
+// (SP_DE_RING=1 forces the ring: profiling switch).  The register-pipelined FULL + PLAIN kernel is also
+// instantiated with the objective as a compile-time constant for the two objectives of the BASELINE
+// configurations (SP_DE_GENERIC_OBJ=1 forces the run-time switch: profiling / parity switch).
 template <typename T, int CH, int STRAT, bool FULL, bool PLAIN>
 static cudaError_t de_pool_launch(const DeArgs<T>& a, cudaStream_t s) {
   if constexpr (CH == 1 && Strat<STRAT>::K <= 3) {
     static const bool force_ring = getenv("SP_DE_RING") != nullptr;
-    if (!force_ring) return de_pool_launch_v<T, CH, STRAT, FULL, PLAIN, false>(a, s);
+    if (!force_ring) {
+      if constexpr (FULL && PLAIN) {
+        static const bool generic = getenv("SP_DE_GENERIC_OBJ") != nullptr;
+        if (!generic && a.objective == SP_OBJ_ROSENBROCK)
+          return de_pool_launch_v<T, CH, STRAT, FULL, PLAIN, false, SP_OBJ_ROSENBROCK>(a, s);
+        if (!generic && a.objective == SP_OBJ_RASTRIGIN)
+          return de_pool_launch_v<T, CH, STRAT, FULL, PLAIN, false, SP_OBJ_RASTRIGIN>(a, s);
+      }
+      return de_pool_launch_v<T, CH, STRAT, FULL, PLAIN, false, -1>(a, s);
+    }
   }
-  return de_pool_launch_v<T, CH, STRAT, FULL, PLAIN, true>(a, s);
+  return de_pool_launch_v<T, CH, STRAT, FULL, PLAIN, true, -1>(a, s);
 }
 
 template <typename T, int CH, int STRAT>
@@ -458,12 +480,13 @@ static cudaError_t de_tma_by_ch(const DeArgs<T>& a, int ch, cudaStream_t s) {
 // does the pool kernel have a launch shape for this problem? (host-side test used by the dispatcher)
 inline bool de_pool_fits(int ch, int64_t P, int K, int64_t ld, size_t elem) {
   PoolShape ps;
+  const int rb = pool_rec_bytes(K, elem);
   switch (ch) {
-    case 1: return pool_shape<1>(P, K, ld, elem, &ps);
-    case 2: return pool_shape<2>(P, K, ld, elem, &ps);
-    case 4: return pool_shape<4>(P, K, ld, elem, &ps);
-    case 8: return pool_shape<8>(P, K, ld, elem, &ps);
-    default: return pool_shape<16>(P, K, ld, elem, &ps);
+    case 1: return pool_shape<1>(P, rb, K, ld, elem, &ps);
+    case 2: return pool_shape<2>(P, rb, K, ld, elem, &ps);
+    case 4: return pool_shape<4>(P, rb, K, ld, elem, &ps);
+    case 8: return pool_shape<8>(P, rb, K, ld, elem, &ps);
+    default: return pool_shape<16>(P, rb, K, ld, elem, &ps);
   }
 }
 

@@ -83,6 +83,65 @@ __device__ __forceinline__ uint4 philox4x32_keyed(uint32_t c0, uint32_t c1, uint
   return make_uint4(c0, c1, c2, c3);
 }
 
+// ---- DE crossover stream: Philox2x32-10 on 16-bit pieces ------------------------------------------
+// The binomial crossover needs one Bernoulli(CR) decision per coordinate -- a 16-bit uniform
+// (CR resolved to 2^-16 = 1.5e-5) is plenty, and four of them come out of ONE Philox2x32-10 call
+// (20 instructions per 4 coordinates instead of ~44 for Philox4x32-10 on 32-bit words).
+//   stream id   (key, o0, o1) = words x, y, z of Philox4x32-10(counter = (0, 0, generation, kDeCross), key = seed),
+//               derived on the host once per generation (de_cross_keys)
+//   call        (x, y) = Philox2x32-10(counter = (row + o0, group ^ o1), key),  group = column / 4
+//   column j    piece (j & 3) of (x >> 16, x & 0xffff, y >> 16, y & 0xffff);  u = piece * 2^-16;  take iff u <= CR
+// mirrored bit for bit by oracle/philox.py::de_cross_uniform.
+struct CrossKeys {
+  uint32_t k[10];  // round keys key + r * 0x9E3779B9
+  uint32_t o0, o1;
+  uint32_t cut_hi;  // piece <= floor(CR * 65536)  <=>  (piece << 16 | low bits) <= cut_hi
+  uint32_t pad;
+};
+inline void philox4x32_host(uint32_t (&c)[4], uint64_t seed) {
+  uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+  for (int r = 0; r < 10; ++r) {
+    const uint64_t p0 = (uint64_t)0xD2511F53u * c[0], p1 = (uint64_t)0xCD9E8D57u * c[2];
+    const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c[1] ^ k0, n2 = (uint32_t)(p0 >> 32) ^ c[3] ^ k1;
+    c[0] = n0;
+    c[1] = (uint32_t)p1;
+    c[2] = n2;
+    c[3] = (uint32_t)p0;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+}
+inline CrossKeys de_cross_keys(uint64_t seed, int it, double CR_as_T) {
+  uint32_t c[4] = {0u, 0u, (uint32_t)it, (uint32_t)kDeCross};
+  philox4x32_host(c, seed);
+  CrossKeys r;
+  for (int i = 0; i < 10; ++i) r.k[i] = c[0] + (uint32_t)i * 0x9E3779B9u;
+  r.o0 = c[1];
+  r.o1 = c[2];
+  const double t = CR_as_T * 65536.0;
+  const uint32_t cut = t < 0.0 ? 0u : (t >= 65536.0 ? 65536u : (uint32_t)t);
+  r.cut_hi = cut >= 65536u ? 0xFFFFFFFFu : ((cut << 16) | 0xFFFFu);
+  r.pad = 0;
+  return r;
+}
+__device__ __forceinline__ uint2 philox2x32_keyed(uint32_t c0, uint32_t c1, const CrossKeys& K) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi = __umulhi(0xD256D193u, c0), lo = 0xD256D193u * c0;
+    c0 = hi ^ K.k[r] ^ c1;
+    c1 = lo;
+  }
+  return make_uint2(c0, c1);
+}
+// the four crossover decisions of column group `group` of `row`
+__device__ __forceinline__ void de_cross_take(uint32_t row, uint32_t group, const CrossKeys& K, bool (&take)[4]) {
+  const uint2 w = philox2x32_keyed(row + K.o0, group ^ K.o1, K);
+  take[0] = w.x <= K.cut_hi;
+  take[1] = (w.x << 16) <= K.cut_hi;
+  take[2] = w.y <= K.cut_hi;
+  take[3] = (w.y << 16) <= K.cut_hi;
+}
+
 __device__ __forceinline__ uint4 philox4x32_for(uint32_t purpose, uint32_t c0, uint32_t c1, uint32_t c2, uint64_t seed) {
   return purpose == kEsZ ? philox4x32<kEsZRounds>(c0, c1, c2, purpose, seed) : philox4x32<10>(c0, c1, c2, purpose, seed);
 }

@@ -229,8 +229,14 @@ vd_sample_eval_kernel(const VdPtrs<T> a, const PhiloxKeys keys) {
         gvec(a.dy, cc, dy);
 #pragma unroll
         for (int e = 0; e < VEC; ++e) {
-          yy[e] = row == 0 ? dy[e] : -dy[e];
-          tt[e] = (FULL || j0 + e < N) ? div_rn(yy[e], dv[e]) : T(0);
+          if (row < 2) {
+            yy[e] = row == 0 ? dy[e] : -dy[e];
+            tt[e] = (FULL || j0 + e < N) ? div_rn(yy[e], dv[e]) : T(0);
+          } else {  // RPW > 1: the other rows of the group keep the sampling formula (per-lane select, no divergence
+                    // around the warp shuffles of the row reductions)
+            tt[e] = k * vn[e] + y.v[cc][e];
+            yy[e] = dv[e] * tt[e];
+          }
         }
       } else {
 #pragma unroll
@@ -280,9 +286,8 @@ vd_sample_eval_kernel(const VdPtrs<T> a, const PhiloxKeys keys) {
     if (!live) row = a.P - 1;
     // rows 0 and 1 share a warp only when RPW > 1; then the whole group takes the injecting copy, whose
     // per-row test keeps the other rows on the sampling formula
-    if (inject && g == 0) {
-      if (row < 2) row_body(row, live, std::true_type{});
-      else row_body(row, live, std::false_type{});
+    if (inject && g * TL::RPW < 2) {  // the group holds row 0 and / or row 1 (RPW == 1: two groups); warp-uniform
+      row_body(row, live, std::true_type{});
     } else {
       row_body(row, live, std::false_type{});
     }

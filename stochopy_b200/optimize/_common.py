@@ -281,60 +281,78 @@ class HistoryStreamer:
     rows and their fitness are snapshotted device-to-device into a small ring on the
     launching stream, and a side stream moves the ring slots to pinned host memory while
     the next generations run.  An event per slot keeps a slot from being overwritten
-    before its copy has left the device.  Nothing here synchronises with the host until
-    ``finish``."""
+    before its copy has left the device.  The pinned host side is a ring too (a window of
+    `win` generations, at most PIN_LIMIT bytes): when it wraps, the host waits for the copy
+    event of the generation it is about to overwrite -- `win` generations in the past, so
+    the device queue stays full -- and moves that part of the window into the History
+    arrays.  Nothing here synchronises with the host per generation."""
 
     SLOTS = 4
-    PIN_LIMIT = 2 << 30  # bytes of pinned history we are willing to allocate
+    PIN_LIMIT = 256 << 20  # bytes of pinned window
 
     @classmethod
     def maybe(cls, eng, hist, callback, P, N):
         if not hist.enabled or callback is not None or hist.nout <= 0:
             return None
-        if hist.xall.shape[0] * hist.nout * (N + 1) * eng.np_dt.itemsize > cls.PIN_LIMIT:
-            return None
         return cls(eng, hist, N)
 
     def __init__(self, eng, hist, N):
-        self.eng, self.N, self.nout = eng, N, hist.nout
+        self.eng, self.N, self.nout, self.hist = eng, N, hist.nout, hist
         self.main = torch.cuda.current_stream(eng.device)
         self.side = torch.cuda.Stream(device=eng.device)
         maxiter = hist.xall.shape[0]
+        per_gen = self.nout * (N + 1) * eng.np_dt.itemsize
+        self.win = int(max(self.SLOTS, min(maxiter, self.PIN_LIMIT // max(1, per_gen))))
         self.slotX = [eng.empty(self.nout, N) for _ in range(self.SLOTS)]
         self.slotF = [eng.empty(self.nout) for _ in range(self.SLOTS)]
-        self.hX = torch.empty((maxiter, self.nout, N), dtype=eng.t_dt, pin_memory=True)
-        self.hF = torch.empty((maxiter, self.nout), dtype=eng.t_dt, pin_memory=True)
+        self.hX = torch.empty((self.win, self.nout, N), dtype=eng.t_dt, pin_memory=True)
+        self.hF = torch.empty((self.win, self.nout), dtype=eng.t_dt, pin_memory=True)
         self.free = [None] * self.SLOTS
+        self.done = {}  # generation -> event of its D2H copy (generations still in the window)
         self.first = None
+        self.last = None
+
+    def _drain(self, upto):
+        """Move generations <= upto from the pinned window into the History arrays."""
+        for it in sorted(g for g in self.done if g <= upto):
+            self.done.pop(it).synchronize()
+            h = (it - 1) % self.win
+            self.hist.xall[it - 1] = self.hX[h].numpy()
+            self.hist.funall[it - 1] = self.hF[h].numpy()
 
     def push(self, it, X, fit):
         """Enqueue the snapshot of generation `it` (X: device rows, fit: device vector)."""
         k = it % self.SLOTS
+        if it - self.win in self.done:  # the window wraps onto a generation that has not been moved out yet
+            self._drain(it - self.win + max(0, self.win // 2 - 1))  # half a window at a time
         if self.free[k] is not None:
             self.main.wait_event(self.free[k])
         self.slotX[k].copy_(X[: self.nout, : self.N])
         self.slotF[k].copy_(fit[: self.nout])
         ready = torch.cuda.Event()
         ready.record(self.main)
+        h = (it - 1) % self.win
         with torch.cuda.stream(self.side):
             self.side.wait_event(ready)
-            self.hX[it - 1].copy_(self.slotX[k], non_blocking=True)
-            self.hF[it - 1].copy_(self.slotF[k], non_blocking=True)
+            self.hX[h].copy_(self.slotX[k], non_blocking=True)
+            self.hF[h].copy_(self.slotF[k], non_blocking=True)
             done = torch.cuda.Event()
             done.record(self.side)
         self.free[k] = done
+        self.done[it] = done
         if self.first is None:
             self.first = it
+        self.last = it
 
     def finish(self, hist, nit, transform=None):
         """Wait for the copies and hand generations first..nit to the History arrays
         (`transform`: host map applied to the float64 rows, e.g. un-standardisation)."""
         self.side.synchronize()
-        if self.first is not None and nit >= self.first:
+        if self.last is not None:
+            self._drain(self.last)
+        if transform is not None and self.first is not None and nit >= self.first:
             a, b = self.first - 1, nit
-            X = self.hX[a:b].numpy().astype(np.float64)
-            hist.xall[a:b] = X if transform is None else transform(X)
-            hist.funall[a:b] = self.hF[a:b].numpy()
+            hist.xall[a:b] = transform(hist.xall[a:b].copy())
 
 
 def validate_common(fun, bounds, callback):

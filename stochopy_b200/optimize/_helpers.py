@@ -54,4 +54,7 @@ def minimize(fun, bounds, x0=None, args=(), method="de", options=None, callback=
         from ..parallel import shared_seed
 
         options["seed"] = shared_seed(None)
-    return fn(fun=fun, bounds=bounds, x0=x0, args=args, callback=callback, **options)
+    from .._lib import nvtx_range
+
+    with nvtx_range(f"stochopy_b200.minimize[{method}]"):
+        return fn(fun=fun, bounds=bounds, x0=x0, args=args, callback=callback, **options)

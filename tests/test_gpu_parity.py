@@ -512,7 +512,7 @@ def test_return_all_streaming_equals_synchronous_history(method, opts, dtype):
     import stochopy_b200 as sb
 
     b = [[-5.12, 5.12]] * 6
-    for ftol in (-1.0, 5.0e-2):
+    for ftol in (-1.0, 0.5):
         o = dict(opts, maxiter=90, popsize=40, seed=17, dtype=dtype, updating="deferred", return_all=True,
                  verbosity=0.5, ftol=ftol)
         a = sb.optimize.minimize(sb.factory.sphere, b, method=method, options=dict(o))
@@ -575,3 +575,20 @@ def test_return_all_streaming_es_methods(method, opts, dtype):
         assert a.xall.shape == d.xall.shape == (a.nit, 8, 7)
         assert np.array_equal(a.xall, d.xall) and np.array_equal(a.funall, d.funall)
         assert np.array_equal(a.x, d.x) and a.fun == d.fun
+
+
+@pytest.mark.parametrize("method,opts", [("de", dict(strategy="best1bin", updating="deferred")), ("vdcma", {})])
+def test_return_all_streaming_window_wraps(method, opts, monkeypatch):
+    """The pinned host side of HistoryStreamer is a ring: with a window of a few generations (PIN_LIMIT
+    forced tiny) the history still equals the synchronous one -- no fallback to per-generation syncs."""
+    import stochopy_b200 as sb
+    from stochopy_b200.optimize import _common
+
+    monkeypatch.setattr(_common.HistoryStreamer, "PIN_LIMIT", 1)  # window = SLOTS generations
+    b = [[-3.0, 5.0]] * 7
+    for ftol in (-1.0, 1.0e-3):
+        o = dict(opts, maxiter=70, popsize=16, seed=5, return_all=True, verbosity=0.5, ftol=ftol)
+        a = sb.optimize.minimize(sb.factory.sphere, b, method=method, options=dict(o))
+        d = sb.optimize.minimize(sb.factory.sphere, b, method=method, options=dict(o), callback=lambda X, s: None)
+        assert (a.nit, a.status) == (d.nit, d.status)
+        assert np.array_equal(a.xall, d.xall) and np.array_equal(a.funall, d.funall)
