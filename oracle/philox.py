@@ -149,6 +149,18 @@ def de_cross_uniform(P, N, gen, seed, dtype):
     return (pieces.astype(np.float64) * 2.0**-16).astype(dtype)
 
 
+def pso_uniforms(rows, N, gen, seed, dtype):
+    """PSO velocity coefficients of the device (csrc/philox.cuh pso_r12): one Philox4x32-10 call per row and
+    group of 4 columns, counter (group, row, gen, PSO_R1); column 4g+p: r1 = (w_p >> 16) 2^-16, r2 = (w_p & 0xffff) 2^-16."""
+    rows = np.asarray(rows, dtype=np.uint64)[:, None]
+    ng = _blocks(N, 4)
+    o = philox4x32(np.arange(ng)[None, :], rows, gen, PSO_R1, seed, rounds=10)
+    w = np.stack(o, axis=-1).reshape(len(rows), ng * 4)[:, :N]
+    r1 = ((w >> np.uint64(16)).astype(np.float64) * 2.0**-16).astype(dtype)
+    r2 = ((w & np.uint64(0xFFFF)).astype(np.float64) * 2.0**-16).astype(dtype)
+    return r1, r2
+
+
 def _mulhi(word, n):
     return (word * np.uint64(n)) >> np.uint64(32)
 

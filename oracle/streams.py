@@ -101,11 +101,7 @@ class PhiloxStream:
         return r1, donors, irand, rep
 
     def pso(self, it, P, N):
-        rows = np.arange(P)
-        return (
-            px.uniform(rows, N, it, px.PSO_R1, self.seed, self.dtype),
-            px.uniform(rows, N, it, px.PSO_R2, self.seed, self.dtype),
-        )
+        return px.pso_uniforms(np.arange(P), N, it, self.seed, self.dtype)
 
     def pso_restart(self, it, rows, N, lower, upper):
         u = px.uniform(np.asarray(rows), N, it, px.PSO_RESTART, self.seed, self.dtype)

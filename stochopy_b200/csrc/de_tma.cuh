@@ -236,7 +236,9 @@ de_pool_kernel(const DeArgs<T> a, int nb, const CrossKeys keys) {
     const bool win = f < rec_best(r);  // strict, _common.py:127
     if (win) u.store(out_row, lane, ld);  // two predicated 16-byte stores instead of a select per scalar
     else xi.store(out_row, lane, ld);
-    // every lane holds the same f: same-address, same-value stores need no lane-0 branch
+    // every lane holds the same f: same-address, same-value stores need no lane-0 branch; the warp barrier
+    // orders them after every lane's read of the record (racecheck: intra-warp write-after-read)
+    __syncwarp();
     rec_fnew(r) = f;
     if (win) rec_best(r) = f;
   };

@@ -17,8 +17,8 @@ enum Purpose : uint32_t {
   kDeCross = 2,
   kDeIndex = 3,
   kDeRepair = 4,
-  kPsoR1 = 5,
-  kPsoR2 = 6,
+  kPsoR1 = 5,  // r1 AND r2 (16-bit pieces of one call, pso_r12)
+  kPsoR2 = 6,  // retired
   kPsoRestart = 7,
   kEsZ = 8,
   kVdInject = 9,
@@ -140,6 +140,35 @@ __device__ __forceinline__ void de_cross_take(uint32_t row, uint32_t group, cons
   take[1] = (w.x << 16) <= K.cut_hi;
   take[2] = w.y <= K.cut_hi;
   take[3] = (w.y << 16) <= K.cut_hi;
+}
+
+// ---- PSO velocity coefficients: r1 and r2 of four columns from ONE Philox4x32-10 call -------------
+//   (w0..w3) = Philox4x32-10(counter = (column / 4, row, generation, kPsoR1), key = seed)
+//   column j = 4 g + p:  r1 = (w_p >> 16) * 2^-16,  r2 = (w_p & 0xffff) * 2^-16   (16-bit uniforms, exact in fp32)
+// instead of two calls and eight 24-bit conversions; mirrored by oracle/philox.py::pso_uniforms.
+// fp32 conversion without an integer->float instruction: the piece becomes the low mantissa bits of 2^23
+// (one PRMT), and f * 2^-16 - 128 is exact (one FFMA).
+__device__ __forceinline__ float piece_hi_f32(uint32_t w) {
+  return fmaf(__uint_as_float(__byte_perm(w, 0x4B000000u, 0x7632)), 1.52587890625e-05f, -128.0f);
+}
+__device__ __forceinline__ float piece_lo_f32(uint32_t w) {
+  return fmaf(__uint_as_float(__byte_perm(w, 0x4B000000u, 0x7610)), 1.52587890625e-05f, -128.0f);
+}
+// j0: first column of this lane's vector (multiple of VEC)
+__device__ __forceinline__ void pso_r12(uint4 w, int j0, float (&r1)[4], float (&r2)[4]) {
+  const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    r1[e] = piece_hi_f32(ww[e]);
+    r2[e] = piece_lo_f32(ww[e]);
+  }
+}
+__device__ __forceinline__ void pso_r12(uint4 w, int j0, double (&r1)[2], double (&r2)[2]) {
+  const uint32_t a = (j0 & 2) ? w.z : w.x, b = (j0 & 2) ? w.w : w.y;
+  r1[0] = (double)(a >> 16) * 1.52587890625e-05;
+  r2[0] = (double)(a & 0xffffu) * 1.52587890625e-05;
+  r1[1] = (double)(b >> 16) * 1.52587890625e-05;
+  r2[1] = (double)(b & 0xffffu) * 1.52587890625e-05;
 }
 
 __device__ __forceinline__ uint4 philox4x32_for(uint32_t purpose, uint32_t c0, uint32_t c1, uint32_t c2, uint64_t seed) {

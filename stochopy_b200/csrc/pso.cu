@@ -5,6 +5,7 @@
 //
 // Per particle (row-local, in place): read X, V, pbest; write X, V and, on
 // improvement only, pbest.  Algorithmic HBM bytes per particle: 5 * N * s + 3 * s.
+#include <cstdlib>
 #include <type_traits>
 
 #include "peer.cuh"
@@ -71,7 +72,10 @@ __device__ __forceinline__ void peer_best_exchange(const PsoArgs<T>& a, Best top
 
 // CHAIN: compiled with the chained-generation prologue / epilogue (fp32 whole-swarm PSO); the
 // plain instantiation keeps the register footprint of the unchained kernel.
-template <typename T, int CH, int LPR, bool PHILOX, bool CHAIN>
+// PLAIN (host-checked): no constraint, not propose-only, ndim == CH * LPR * VEC == ld and popsize a multiple
+// of the rows per warp -- no bounds predicates, no dead-row tests, compile-time row stride.
+// OBJ >= 0: the objective is a compile-time constant (no jump table in the row loop); -1: a.objective.
+template <typename T, int CH, int LPR, bool PHILOX, bool CHAIN, int OBJ = -1, bool PLAIN = false>
 __global__ void __launch_bounds__(kThreads)
 pso_generation_kernel(const PsoArgs<T> a, const PhiloxKeys keys) {
   using TL = Tile<T, CH, LPR>;
@@ -83,16 +87,18 @@ pso_generation_kernel(const PsoArgs<T> a, const PhiloxKeys keys) {
   const int64_t warp = (int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
   const int64_t nwarps = (int64_t)gridDim.x * (kThreads / 32);
   const int64_t groups = (a.P + TL::RPW - 1) / TL::RPW;
-  const int ld = (int)a.ld;
+  const int ld = PLAIN ? TL::COLS : (int)a.ld;
+  const int64_t ldr = PLAIN ? (int64_t)TL::COLS : a.ld;  // row stride
+  const int N = PLAIN ? TL::COLS : a.N;
 
   // software pipeline: the next row group's X, V, pbest are in flight while this one computes
   TL nx, nv, npb;
   auto fetch = [&](int64_t g) {
     int64_t r = g * TL::RPW + sub;
-    if (r >= a.P) r = a.P - 1;
-    nx.load(a.X + r * a.ld, l, ld);
-    nv.load(a.V + r * a.ld, l, ld);
-    npb.load(a.pbest + r * a.ld, l, ld);
+    if (!PLAIN && r >= a.P) r = a.P - 1;
+    nx.load(a.X + r * ldr, l, ld);
+    nv.load(a.V + r * ldr, l, ld);
+    npb.load(a.pbest + r * ldr, l, ld);
   };
   bool have_first = false;
   TL gb;
@@ -118,13 +124,15 @@ pso_generation_kernel(const PsoArgs<T> a, const PhiloxKeys keys) {
   }
 
   Best mine{1.0 / 0.0, 0x7fffffffffffffffLL};
+  T mine_f = Num<T>::inf();  // PLAIN: the lane's minimum in T (rows ascend, strict < keeps the first = np.argmin's tie rule)
+  int64_t mine_row = 0x7fffffffffffffffLL;
   // measured on B200 (C3, fp32 N=64): prefetching one group ahead costs 26 registers and a resident
   // CTA per SM and is slower (21.3 vs 17.0 us per generation) -- the state is L2 resident; keep it off
   constexpr bool kPrefetch = false;
   if (kPrefetch && warp < groups) fetch(warp);
   for (int64_t g = warp; g < groups; g += nwarps) {
     int64_t row = g * TL::RPW + sub;
-    const bool live = row < a.P;
+    const bool live = PLAIN || row < a.P;
     if (!live) row = a.P - 1;
 
     if (!kPrefetch && !(CHAIN && have_first)) fetch(g);
@@ -138,9 +146,8 @@ pso_generation_kernel(const PsoArgs<T> a, const PhiloxKeys keys) {
       for (int c = 0; c < CH; ++c) {
         const int j0 = TL::col(c, l, 0);
         T r1[VEC], r2[VEC];
-        if (PHILOX) {
-          uniform_block(philox4x32_keyed((uint32_t)(j0 / VEC), (uint32_t)(a.row0 + row), (uint32_t)a.it, kPsoR1, keys), r1);
-          uniform_block(philox4x32_keyed((uint32_t)(j0 / VEC), (uint32_t)(a.row0 + row), (uint32_t)a.it, kPsoR2, keys), r2);
+        if (PHILOX) {  // r1 and r2 of four columns from one call (philox.cuh pso_r12)
+          pso_r12(philox4x32_keyed((uint32_t)(j0 >> 2), (uint32_t)(a.row0 + row), (uint32_t)a.it, kPsoR1, keys), j0, r1, r2);
         } else {
 #pragma unroll
           for (int e = 0; e < VEC; ++e) {
@@ -155,12 +162,12 @@ pso_generation_kernel(const PsoArgs<T> a, const PhiloxKeys keys) {
           T t = mul_rn(a.w, v.v[c][e]);
           t = add_rn(t, mul_rn(mul_rn(a.c1, r1[e]), sub_rn(pb.v[c][e], xe)));
           t = add_rn(t, mul_rn(mul_rn(a.c2, r2[e]), sub_rn(gb.v[c][e], xe)));
-          v.v[c][e] = (j0 + e < a.N) ? t : T(0);
+          v.v[c][e] = (PLAIN || j0 + e < a.N) ? t : T(0);
         }
       }
     }
 
-    if (a.constraint == SP_CONS_SHRINK) {  // cpso/_constraints.py:22-55
+    if (!PLAIN && a.constraint == SP_CONS_SHRINK) {  // cpso/_constraints.py:22-55
       T beta = Num<T>::inf();
 #pragma unroll
       for (int c = 0; c < CH; ++c)
@@ -188,25 +195,33 @@ pso_generation_kernel(const PsoArgs<T> a, const PhiloxKeys keys) {
       for (int e = 0; e < VEC; ++e) x.v[c][e] = add_rn(x.v[c][e], v.v[c][e]);
 
     if (live) {
-      x.store(a.X + row * a.ld, l, ld);
-      v.store(a.V + row * a.ld, l, ld);
+      x.store(a.X + row * ldr, l, ld);
+      v.store(a.V + row * ldr, l, ld);
     }
-    if (a.propose_only) continue;  // SP_OBJ_HOST: caller evaluates X, then sp_select_sync(copy_when=1)
+    if (!PLAIN && a.propose_only) continue;  // SP_OBJ_HOST: caller evaluates X, then sp_select_sync(copy_when=1)
 
-    const T f = evaluate_tile<T, CH, LPR>(a.objective, x, l, a.N);
+    const T f = evaluate_tile<T, CH, LPR>(OBJ >= 0 ? OBJ : a.objective, x, l, N);
     T best = a.pbestfit[row];
     const bool win = f < best;
     if (win) best = f;
     if (live) {
-      if (win) x.store(a.pbest + row * a.ld, l, ld);
+      if (win) x.store(a.pbest + row * ldr, l, ld);
       if (l == 0) {
-        a.pbestfit[row] = best;
+        if (!PLAIN || win) a.pbestfit[row] = best;
         a.pfit[row] = f;
-        if (better((double)best, row, mine.f, mine.row)) mine = Best{(double)best, row};
+        if (PLAIN) {
+          if (best < mine_f) {
+            mine_f = best;
+            mine_row = row;
+          }
+        } else if (better((double)best, row, mine.f, mine.row)) {
+          mine = Best{(double)best, row};
+        }
       }
     }
   }
-  if (a.propose_only) return;
+  if (!PLAIN && a.propose_only) return;
+  if (PLAIN) mine = Best{(double)mine_f, mine_row};
   if (CHAIN && (a.chain & SP_CHAIN_OUT)) {  // leave the CTA's minimum and its row for the next launch's prologue
     __shared__ Best s_red[32];
     __shared__ long long s_row;
@@ -482,6 +497,38 @@ static void launch_chained(const PsoArgs<float>& a, int grid, cudaStream_t s, bo
 template <int C, int L>
 static void launch_chained(const PsoArgs<double>&, int, cudaStream_t, bool, const PhiloxKeys&) {}
 
+// PLAIN instantiations with a compile-time objective: the shapes and objectives of the BASELINE configurations
+// (C3: Styblinski-Tang ndim 64; also Rastrigin / Rosenbrock, ndim 64 / 128 in fp32 and 64 in fp64).
+// SP_PSO_GENERIC=1 keeps the generic kernel (profiling / parity switch).  Returns false if not applicable.
+template <typename T, int C, int L, int OBJ>
+static void launch_plain(const PsoArgs<T>& a, int grid, cudaStream_t s, bool pdl, const PhiloxKeys& keys) {
+  if constexpr (std::is_same<T, float>::value) {
+    if (a.chain != 0) {
+      launch_pdl(pso_generation_kernel<T, C, L, true, true, OBJ, true>, dim3(grid), dim3(kThreads), 0, s, pdl, a, keys);
+      return;
+    }
+  }
+  launch_pdl(pso_generation_kernel<T, C, L, true, false, OBJ, true>, dim3(grid), dim3(kThreads), 0, s, pdl, a, keys);
+}
+template <typename T, int C, int L>
+static bool pso_launch_plain(const PsoArgs<T>& a, int grid, cudaStream_t s, bool pdl, const PhiloxKeys& keys) {
+  constexpr bool shape_ok = C == 1 && (L == 32 || (L == 16 && std::is_same<T, float>::value));
+  if constexpr (shape_ok) {
+    static const bool generic = getenv("SP_PSO_GENERIC") != nullptr;
+    using TL = Tile<T, C, L>;
+    if (generic || a.constraint != SP_CONS_NONE || a.propose_only || a.N != TL::COLS || a.ld != a.N ||
+        a.P % TL::RPW != 0 || a.r1 != nullptr)
+      return false;
+    switch (a.objective) {
+      case SP_OBJ_STYBLINSKI_TANG: launch_plain<T, C, L, SP_OBJ_STYBLINSKI_TANG>(a, grid, s, pdl, keys); return true;
+      case SP_OBJ_RASTRIGIN: launch_plain<T, C, L, SP_OBJ_RASTRIGIN>(a, grid, s, pdl, keys); return true;
+      case SP_OBJ_ROSENBROCK: launch_plain<T, C, L, SP_OBJ_ROSENBROCK>(a, grid, s, pdl, keys); return true;
+      default: return false;
+    }
+  }
+  return false;
+}
+
 template <typename T>
 static int pso_launch(const sp_pso_state* st, int it, int propose_only, cudaStream_t s, int chain = 0,
                       bool after_kernel = false) {
@@ -531,6 +578,7 @@ static int pso_launch(const sp_pso_state* st, int it, int propose_only, cudaStre
   const bool pdl = after_kernel || (a.chain & SP_CHAIN_IN) != 0;  // follows another kernel of the chain directly
 #define SP_CALL(TT, C, L)                                                                                    \
   do {                                                                                                       \
+    if (pso_launch_plain<TT, C, L>(a, grid, s, pdl, keys)) break;                                            \
     if (a.chain != 0)  /* pso_chainable(): fp32 only */                                                      \
       launch_chained<C, L>(a, grid, s, pdl, keys);                                                           \
     else if (philox)                                                                                         \

@@ -439,6 +439,13 @@ __device__ __forceinline__ void reduce1(double (&v)[K], const int (&op)[K], doub
 //     fp64 algebra between the reductions is replicated per warp, so few warps) and every dependent
 //     step is one combined block reduction.
 constexpr int kUpThreads = 256, kUpOut = kUpThreads / 8;
+// profiling hook: SM cycle counter at the stages of the update kernel's single-CTA phase (thread 0 of the last
+// CTA), read back with sp_debug_vd_clocks()
+__device__ long long g_vd_clk[16];
+#define VD_STAMP(i)                                    \
+  do {                                                 \
+    if (threadIdx.x == 0) g_vd_clk[i] = clock64();     \
+  } while (0)
 template <typename T, int kVdNpt>
 __global__ void __launch_bounds__(kUpThreads)
 vd_update_kernel(const VdPtrs<T> a) {
@@ -450,6 +457,7 @@ vd_update_kernel(const VdPtrs<T> a) {
   sp_es_ctrl* c = a.ctrl;
   if (!es_running(c)) return;
   const int N = a.N, tid = threadIdx.x, nt = blockDim.x;
+  const long long clk0 = clock64();
   {
     const int o = tid % kUpOut, g = tid / kUpOut;
     const int e = blockIdx.x * kUpOut + o;
@@ -498,6 +506,8 @@ vd_update_kernel(const VdPtrs<T> a) {
     if (!s_last) return;
     __threadfence();
   }
+  if (tid == 0) g_vd_clk[0] = clk0;
+  VD_STAMP(1);
   // ---- phase 2 -----------------------------------------------------------------------------------
   // Six dependent block reductions, one barrier each (reduce1), instead of a dozen three-barrier ones:
   //   L1 max vn^2, (pc/D).vn, H and everything the termination ladder needs   L2 vn.q   L3 ria, via
@@ -581,7 +591,9 @@ vd_update_kernel(const VdPtrs<T> a) {
   {
     const int op[15] = {RED_MAX, RED_SUM, RED_SUM, RED_SUM, RED_MAX, RED_MAX, RED_MAX, RED_MIN, RED_MIN, RED_MAX,
                         RED_MIN, RED_MAX, RED_MIN, RED_MAX, RED_MAX};
+    VD_STAMP(2);
     reduce1<15, kUpThreads / 32>(L1, op, s_r1, ph);
+    VD_STAMP(3);
   }
   const double vmax = L1[0], yv1 = L1[1], hmu = L1[2];
   const double best = L1[12];  // the row of rank 0 carries the minimum
@@ -635,7 +647,9 @@ vd_update_kernel(const VdPtrs<T> a) {
   for (int k = 0; k < kVdNpt; ++k) vv2[k] = vv[k], dv2[k] = dv[k];
   if (a.cmu + a.c1 > 0.0) {  // natural gradient, _vdcma.py:444-458
     const int sum1[1] = {RED_SUM};
+    VD_STAMP(4);
     reduce1<1, kUpThreads / 32>(vq, sum1, s_r1, ph);
+    VD_STAMP(5);
     T sv[kVdNpt];
     double red3[2] = {0.0, 0.0};  // ria, via
 #pragma unroll
@@ -651,6 +665,7 @@ vd_update_kernel(const VdPtrs<T> a) {
     {
       const int op[2] = {RED_SUM, RED_SUM};
       reduce1<2, kUpThreads / 32>(red3, op, s_r1, ph);
+      VD_STAMP(6);
     }
     const double ria = red3[0], via = red3[1];
     double svnn[1] = {0.0};
@@ -662,6 +677,7 @@ vd_update_kernel(const VdPtrs<T> a) {
       if (ok[k]) svnn[0] += sn * vnn;
     }
     reduce1<1, kUpThreads / 32>(svnn, sum1, s_r1, ph);
+    VD_STAMP(7);
     T ngv[kVdNpt], ngd[kVdNpt];
     double red4[2] = {0.0, inf};  // |ngv|^2, min D / |ngd|
 #pragma unroll
@@ -679,6 +695,7 @@ vd_update_kernel(const VdPtrs<T> a) {
     {
       const int op[2] = {RED_SUM, RED_MIN};
       reduce1<2, kUpThreads / 32>(red4, op, s_r1, ph);
+      VD_STAMP(8);
     }
     up = fmin(1.0, 0.7 * nv / sqrt(red4[0]));  // at most 70 % change, _vdcma.py:361-363
     up = fmin(up, 0.7 * red4[1]);
@@ -714,7 +731,9 @@ vd_update_kernel(const VdPtrs<T> a) {
   }
   {
     const int op[4] = {RED_SUM, RED_SUM, RED_SUM, RED_SUM};
+    VD_STAMP(9);
     reduce1<4, kUpThreads / 32>(L6, op, s_r1, ph);
+    VD_STAMP(10);
   }
   const double nv2n = L6[0], nvn = sqrt(nv2n);
   const T kinj = inject_next ? (T)(sqrt(L6[1]) / sqrt(L6[2] - L6[3] * L6[3] / (1.0 + nv2n))) : T(0);
@@ -744,6 +763,7 @@ vd_update_kernel(const VdPtrs<T> a) {
     c->base.nit = a.it;
     c->base.status = status;
   }
+  VD_STAMP(11);
 }
 
 template <typename T>
@@ -962,3 +982,8 @@ int sp_vd_run(const sp_vd_state* st, int it_first, int n, void* stream) {
 }
 
 }  // extern "C"
+
+// profiling hook (not part of the public header): the update kernel's stage clocks of the last generation
+extern "C" int sp_debug_vd_clocks(long long* out16) {
+  return cudaMemcpyFromSymbol(out16, sp::g_vd_clk, sizeof(long long) * 16) == cudaSuccess ? 0 : -1;
+}
