@@ -25,3 +25,5 @@ for dt in ("float32", "float64"):
     print(dt, "total cycles", v[11] - v[0], "= %.2f us" % ((v[11] - v[0]) / mhz))
     for i, n in enumerate(names):
         print("  %-20s %8d cycles  %6.2f us" % (n, v[i + 1] - v[i], (v[i + 1] - v[i]) / mhz))
+    print("  timeline of the last generation (globaltimer): sample + rank %.2f us, wsum %.2f us, update %.2f us"
+          % ((v[13] - v[12]) / 1e3, (v[14] - v[13]) / 1e3, (v[15] - v[14]) / 1e3))

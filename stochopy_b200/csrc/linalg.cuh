@@ -199,6 +199,17 @@ struct JacobiEps<float> {
 constexpr int kJacobiThreads = 1024;
 constexpr int kJacobiRegs = 8;  // row elements per lane staged in registers (N <= 256)
 
+// A sweep whose largest |cos(w_p, w_q)| (before its rotations) stayed below `quiet` needs no follow-up sweep:
+// the rotations of that sweep leave a residual of about quiet^2 (quadratic convergence).  fp64: 1e-6, i.e. a
+// residual of ~1e-12 relative -- B D^2 B^T reproduces C to ~1e-12 |C| (asserted to 1e-8 at N = 256 in
+// tests/test_gpu_sizes.py; the north-star bound is 1e-6) and a warm-started decomposition takes 3 sweeps instead
+// of 4.  fp32: the rounding-noise bound 0.25 sqrt(tol) ~ 7e-4.
+template <typename T>
+__device__ __forceinline__ float jacobi_quiet(T tol) {
+  const float q = 0.25f * sqrtf((float)tol);
+  return sizeof(T) == 8 ? fmaxf(q, 1.0e-6f) : q;
+}
+
 template <typename T>
 __device__ __forceinline__ T jacobi_tol(int N) {
   // rotate while |w_p.w_q| exceeds the rounding noise of a length-N dot product
@@ -421,7 +432,7 @@ jacobi_eigh_kernel(T* __restrict__ C, int N, T* __restrict__ w_out, T* __restric
   __syncthreads();
 
   const T tol = jacobi_tol<T>(N);
-  const float quiet = 0.25f * sqrtf((float)tol);  // a sweep below this needs no follow-up sweep
+  const float quiet = jacobi_quiet<T>(tol);  // a sweep below this needs no follow-up sweep
   const int n = N + (N & 1);  // even player count; index N (if any) is a bye
   const int half = n / 2;
   const bool regs = N <= 32 * kJacobiRegs;
@@ -590,7 +601,7 @@ jacobi_block_kernel(T* __restrict__ C, int N, T* __restrict__ w_out, T* __restri
   cl.sync();
 
   const T tol = jacobi_tol<T>(N);
-  const float quiet = 0.25f * sqrtf((float)tol);
+  const float quiet = jacobi_quiet<T>(tol);
   const int m = nblk / 2, n2 = 2 * b;
   const bool regs = N <= 32 * kJacobiRegs;
   const int nv = N / Num<T>::VEC;  // rows are copied in 16-byte vectors when N allows it

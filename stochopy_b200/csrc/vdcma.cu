@@ -18,7 +18,22 @@
 namespace sp {
 
 constexpr int kVdChunks = 256;
-constexpr int kVdUpMax = 512;  // CTAs of vd_update_kernel: 3 N / 32 outputs each, N <= 2048 -> <= 192
+constexpr int kVdUpOut = 32;   // outputs of the chunk reduction per CTA of vd_update_kernel (3 N / 32 CTAs)
+constexpr int kVdUpMax = 512;  // CTAs of vd_update_kernel: 3 N / 32, N <= 2048 -> <= 192
+
+// profiling hook, read back with sp_debug_vd_clocks(): [0..11] SM cycle counter at the stages of the update kernel's
+// single-CTA phase (thread 0 of the last CTA); [12..15] %globaltimer (ns) when CTA 0 of the sampling / weighted-sum /
+// update kernels passes its griddepcontrol.wait and when the update kernel ends -- the timeline of the last generation
+__device__ long long g_vd_clk[16];
+#define VD_STAMP(i)                                    \
+  do {                                                 \
+    if (threadIdx.x == 0) g_vd_clk[i] = clock64();     \
+  } while (0)
+__device__ __forceinline__ void vd_time_stamp(int i) {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  g_vd_clk[i] = (long long)t;
+}
 
 template <typename T>
 struct VdPtrs {
@@ -142,6 +157,7 @@ vd_sample_eval_kernel(const VdPtrs<T> a, const PhiloxKeys keys) {
   pdl_launch_dependents();
   pdl_wait();  // the previous generation's update kernel wrote everything read below
   if (!es_running(c)) return;
+  if (blockIdx.x == 0 && threadIdx.x == 0) vd_time_stamp(12);
   const int lane = threadIdx.x & 31, l = lane % LPR, sub = lane / LPR;
   const int64_t warp = (int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
   const int64_t nwarps = (int64_t)gridDim.x * (kThreads / 32);
@@ -294,6 +310,147 @@ vd_sample_eval_kernel(const VdPtrs<T> a, const PhiloxKeys keys) {
   }
 }
 
+// Wide rows (CH >= 4, i.e. more than 16 scalars per lane) of the device-resident loop (in-kernel draws, lean,
+// objective on the device, no Penalize): the same row algorithm as above with the row tile kept in a
+// WARP-PRIVATE SHARED-MEMORY ROW instead of registers.  Every lane only ever re-reads the 16-byte vectors it
+// wrote itself, so no synchronisation is needed -- the shared row is an explicitly managed spill area.  The
+// register-tile version holds CH * VEC scalars per lane across both passes: at CH = 8 ptxas spills ~100 MB per
+// launch to local memory under the 80-register cap (l1tex local sectors in profiles/r02_vd_sample_l2_metrics.csv)
+// and its fully unrolled row body is 20 KB of SASS per variant (13.5 k instructions in the kernel; 18 % of the
+// stall samples were instruction fetches).  Here the column loops are real loops (unrolled by 2), the live state
+// between passes is a handful of scalars, and only the objective sees a register tile (loaded from the shared row
+// at the end).  Rows 0 / 1 of an injecting generation branch warp-uniformly inside pass 2.
+template <typename T, int CH, bool FULL>
+__global__ void __launch_bounds__(kThreads, (CH * (int)sizeof(T) <= 32 ? 4 : 2))
+vd_sample_smem_kernel(const VdPtrs<T> a, const PhiloxKeys keys) {
+  using TL = Tile<T, CH, 32>;
+  using V = typename Num<T>::vec_t;
+  constexpr int VEC = Num<T>::VEC;
+  constexpr int COLS = TL::COLS;
+  extern __shared__ __align__(16) unsigned char vd_smem[];
+  T* s_vn = reinterpret_cast<T*>(vd_smem);
+  T* s_dv = s_vn + COLS;
+  T* s_fa = s_dv + COLS;
+  T* s_fb = s_fa + COLS;
+  T* srow = s_fb + COLS + (size_t)(threadIdx.x >> 5) * COLS;
+  const sp_es_ctrl* c = a.ctrl;
+  pdl_launch_dependents();
+  pdl_wait();  // the previous generation's update kernel wrote everything read below
+  if (!es_running(c)) return;
+  if (blockIdx.x == 0 && threadIdx.x == 0) vd_time_stamp(12);
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * (kThreads / 32);
+  const int ld = FULL ? COLS : (int)a.ld, N = FULL ? COLS : a.N;
+  const int64_t ldr = FULL ? (int64_t)COLS : a.ld;
+  for (int j = threadIdx.x; j < COLS; j += kThreads) {
+    const bool ok = FULL || j < N;
+    s_vn[j] = ok ? a.vn[j] : T(0);
+    s_dv[j] = ok ? a.dvec[j] : T(0);
+    s_fa[j] = ok ? a.fuse_a()[j] : T(0);
+    s_fb[j] = ok ? a.fuse_b()[j] : T(0);
+  }
+  const T fac = (T)(sqrt(1.0 + c->aux[0]) - 1.0);
+  const bool inject = c->inject != 0;
+  const bool stream = a.stream_stores != 0;
+  const uint32_t it = (uint32_t)a.it;
+  if (blockIdx.x == 0 && threadIdx.x == 0) const_cast<sp_es_ctrl*>(c)->sigma_gen = c->sigma;
+  __syncthreads();
+  auto lds = [&](const T* p, int j0, T (&o)[VEC]) {
+    const V t = *reinterpret_cast<const V*>(p + j0);
+    const T* q = reinterpret_cast<const T*>(&t);
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) o[e] = q[e];
+  };
+  auto sts = [&](T* p, int j0, const T (&val)[VEC]) {
+    V t;
+    T* q = reinterpret_cast<T*>(&t);
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) q[e] = val[e];
+    *reinterpret_cast<V*>(p + j0) = t;
+  };
+  for (int64_t row = warp; row < a.P; row += nwarps) {
+    // pass 1: z -> shared row, z . vn
+    T zv = 0;
+#pragma unroll 2
+    for (int cc = 0; cc < CH; ++cc) {
+      const int j0 = TL::col(cc, lane, 0);
+      T z[VEC], vn[VEC];
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) z[e] = T(0);
+      if (FULL || j0 < N) {
+        normal_block(philox4x32_keyed<kEsZRounds>((uint32_t)(j0 / VEC), (uint32_t)row, it, kEsZ, keys), z);
+        if (!FULL) {
+#pragma unroll
+          for (int e = 0; e < VEC; ++e) z[e] = (j0 + e < N) ? z[e] : T(0);
+        }
+      }
+      lds(s_vn, j0, vn);
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) zv += z[e] * vn[e];
+      sts(srow, j0, z);
+    }
+    zv = group_sum<32>(zv);
+    const T k = fac * zv;
+    const bool inj = inject && row < 2;  // warp-uniform: the pair +-dy of _vdcma.py:247-248
+    T yv = 0;
+    T* __restrict__ yrow = a.ary + row * ldr;
+#pragma unroll 2
+    for (int cc = 0; cc < CH; ++cc) {
+      const int j0 = TL::col(cc, lane, 0);
+      T z[VEC], vn[VEC], dv[VEC], yy[VEC], tt[VEC], fa[VEC], fb[VEC];
+      lds(srow, j0, z);
+      lds(s_vn, j0, vn);
+      lds(s_dv, j0, dv);
+      if (inj) {  // t = y / D
+        if (FULL || j0 < ld) {
+          const V t = __ldg(reinterpret_cast<const V*>(a.dy + j0));
+          const T* q = reinterpret_cast<const T*>(&t);
+#pragma unroll
+          for (int e = 0; e < VEC; ++e) {
+            yy[e] = row == 0 ? q[e] : -q[e];
+            tt[e] = (FULL || j0 + e < N) ? div_rn(yy[e], dv[e]) : T(0);
+          }
+        } else {
+#pragma unroll
+          for (int e = 0; e < VEC; ++e) yy[e] = tt[e] = T(0);
+        }
+      } else {
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) {
+          tt[e] = k * vn[e] + z[e];
+          yy[e] = dv[e] * tt[e];
+        }
+      }
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) yv += tt[e] * vn[e];
+      if (FULL || j0 < ld) {
+        V t;
+        T* q = reinterpret_cast<T*>(&t);
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) q[e] = yy[e];
+        if (stream) __stcs(reinterpret_cast<V*>(yrow + j0), t);
+        else *reinterpret_cast<V*>(yrow + j0) = t;
+      }
+      lds(s_fa, j0, fa);
+      lds(s_fb, j0, fb);
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) z[e] = tt[e] * fa[e] + fb[e];  // what the objective sees
+      sts(srow, j0, z);
+    }
+    yv = group_sum<32>(yv);
+    if (lane == 0) a.yvn[row] = yv;
+    // pass 3: the objective on a register tile loaded from the shared row
+    TL x;
+#pragma unroll
+    for (int cc = 0; cc < CH; ++cc) lds(srow, TL::col(cc, lane, 0), x.v[cc]);
+    const T f = evaluate_tile<T, CH, 32>(a.objective, x, lane, N);
+    if (lane == 0) a.arfit[row] = f;
+  }
+}
+template <int CH, typename T>
+constexpr size_t vd_smem_bytes() { return (size_t)(4 + kThreads / 32) * Tile<T, CH, 32>::COLS * sizeof(T); }
+
 // weighted sums over the mu best (_vdcma.py:291, 313, 426-441), factored so that a row costs four
 // instructions per element.  With yd = y / D, yn = yd . vn and h = (yn^2 + 1 + |v|^2) / 2 the reference needs
 //   S_y  = sum w y                                       (evolution path; and dx = sum w x - (sum w) xmean = sigma S_y)
@@ -314,6 +471,7 @@ vd_wsum_kernel(const VdPtrs<T> a) {
   pdl_launch_dependents();
   pdl_wait();
   if (!es_running(a.ctrl)) return;
+  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) vd_time_stamp(13);
   __shared__ int s_row[kWsTile];
   __shared__ T s_w[kWsTile], s_wyn[kWsTile];
   __shared__ int s_cnt[kWsThreads / 32];
@@ -418,12 +576,35 @@ __device__ __forceinline__ void reduce1(double (&v)[K], const int (&op)[K], doub
     for (int k = 0; k < K; ++k) buf[ph][k][warp] = v[k];
   }
   __syncthreads();
+  if constexpr (NW <= 8) {
 #pragma unroll
-  for (int k = 0; k < K; ++k) {
-    double x = buf[ph][k][0];
+    for (int k = 0; k < K; ++k) {
+      double x = buf[ph][k][0];
 #pragma unroll
-    for (int w = 1; w < NW; ++w) x = red_apply(x, buf[ph][k][w], op[k]);
-    v[k] = x;
+      for (int w = 1; w < NW; ++w) x = red_apply(x, buf[ph][k][w], op[k]);
+      v[k] = x;
+    }
+  } else {
+    // many warps: warp k folds value k with one more butterfly and leaves it in slot 0 (second barrier); a full
+    // second butterfly of all K values in every warp costs 5 x K fp64 shuffle steps per warp again (measured:
+    // 5.9 us for K = 15 with 32 warps)
+    static_assert(K <= NW, "one warp per value");
+    if (warp < K) {
+      double x = red_identity(RED_SUM);
+      int myop = RED_SUM;
+#pragma unroll
+      for (int k = 0; k < K; ++k)
+        if (k == warp) {
+          myop = op[k];
+          x = lane < NW ? buf[ph][k][lane < NW ? lane : 0] : red_identity(op[k]);
+        }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) x = red_apply(x, __shfl_xor_sync(0xffffffffu, x, o), myop);
+      if (lane == 0) buf[ph][warp][0] = x;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < K; ++k) v[k] = buf[ph][k][0];
   }
   ph ^= 1;
 }
@@ -438,19 +619,15 @@ __device__ __forceinline__ void reduce1(double (&v)[K], const int (&op)[K], doub
 //   phase 2 (that one CTA): the N-vectors live in registers (kVdNpt columns per thread; the scalar
 //     fp64 algebra between the reductions is replicated per warp, so few warps) and every dependent
 //     step is one combined block reduction.
-constexpr int kUpThreads = 256, kUpOut = kUpThreads / 8;
-// profiling hook: SM cycle counter at the stages of the update kernel's single-CTA phase (thread 0 of the last
-// CTA), read back with sp_debug_vd_clocks()
-__device__ long long g_vd_clk[16];
-#define VD_STAMP(i)                                    \
-  do {                                                 \
-    if (threadIdx.x == 0) g_vd_clk[i] = clock64();     \
-  } while (0)
-template <typename T, int kVdNpt>
+// UT threads per CTA (template parameter): one column per thread up to N = 1024 -- the single-CTA phase is a chain
+// of dependent fp64 operations (measured: ~14 cycles per instruction per warp with 8 warps; 26 us at N = 1024 with
+// four columns per thread), so it wants as many warps as there are columns, not registers per thread.
+template <typename T, int kVdNpt, int kUpThreads>
 __global__ void __launch_bounds__(kUpThreads)
 vd_update_kernel(const VdPtrs<T> a) {
+  constexpr int kUpOut = kVdUpOut, kGroups = kUpThreads / kUpOut;
   __shared__ double s_red[kRedDoubles];
-  __shared__ T s_p[8][kUpOut];
+  __shared__ T s_p[kGroups][kUpOut];
   __shared__ bool s_last;
   pdl_launch_dependents();
   pdl_wait();
@@ -458,18 +635,30 @@ vd_update_kernel(const VdPtrs<T> a) {
   if (!es_running(c)) return;
   const int N = a.N, tid = threadIdx.x, nt = blockDim.x;
   const long long clk0 = clock64();
+  if (blockIdx.x == 0 && tid == 0) vd_time_stamp(14);
+  // the N-vectors this generation did not touch yet: loaded by every CTA before the grid-wide hand-over, so the
+  // single-CTA phase does not start with a round of dependent L2 misses (only `sums` has to wait)
+  bool ok[kVdNpt];
+  T xm[kVdNpt], pc[kVdNpt], vnT[kVdNpt], dv[kVdNpt], vv[kVdNpt], dC[kVdNpt];
+#pragma unroll
+  for (int k = 0; k < kVdNpt; ++k) {
+    const int n = tid + k * nt;
+    ok[k] = n < N;
+    const int m = ok[k] ? n : 0;
+    xm[k] = a.xmean[m], pc[k] = a.pc[m], vnT[k] = a.vn[m], dv[k] = a.dvec[m], vv[k] = a.vvec[m], dC[k] = a.diagC[m];
+  }
   {
     const int o = tid % kUpOut, g = tid / kUpOut;
     const int e = blockIdx.x * kUpOut + o;
     T acc = 0;
     if (e < 3 * N) {
       const T* p = a.part() + e + (size_t)g * 3 * N;
-      const size_t step = (size_t)8 * 3 * N;
-      T v[kVdChunks / 8];
+      const size_t step = (size_t)kGroups * 3 * N;
+      T v[kVdChunks / kGroups];
 #pragma unroll
-      for (int k = 0; k < kVdChunks / 8; ++k) v[k] = (g + 8 * k < a.chunks) ? __ldcg(p + k * step) : T(0);
+      for (int k = 0; k < kVdChunks / kGroups; ++k) v[k] = (g + kGroups * k < a.chunks) ? __ldcg(p + k * step) : T(0);
 #pragma unroll
-      for (int k = 0; k < kVdChunks / 8; ++k) acc += v[k];
+      for (int k = 0; k < kVdChunks / kGroups; ++k) acc += v[k];
     }
     // this CTA's slice of the population: row of rank 0 (ties by index: the stable rank's first minimum)
     // and min / max fitness
@@ -491,7 +680,7 @@ vd_update_kernel(const VdPtrs<T> a) {
     if (g == 0 && e < 3 * N) {
       T tot = s_p[0][o];
 #pragma unroll
-      for (int k = 1; k < 8; ++k) tot += s_p[k][o];
+      for (int k = 1; k < kGroups; ++k) tot += s_p[k][o];
       a.sums()[e] = tot;
     }
     if (tid < 3) a.fpart()[3 * blockIdx.x + tid] = ext[tid];
@@ -515,16 +704,12 @@ vd_update_kernel(const VdPtrs<T> a) {
   __shared__ double s_r1[2][kRedMax][kUpThreads / 32];
   int ph = 0;
   const double nv2 = c->aux[0], nv = c->aux[1];
-  bool ok[kVdNpt];
-  T xm[kVdNpt], pc[kVdNpt], vnT[kVdNpt], dv[kVdNpt], vv[kVdNpt], Sy[kVdNpt], Sa[kVdNpt], Sb[kVdNpt], dC[kVdNpt];
+  T Sy[kVdNpt], Sa[kVdNpt], Sb[kVdNpt];
 #pragma unroll
   for (int k = 0; k < kVdNpt; ++k) {
-    const int n = tid + k * nt;
-    ok[k] = n < N;
-    const int m = ok[k] ? n : 0;
+    const int m = ok[k] ? tid + k * nt : 0;
     const T* p = a.sums();
     Sy[k] = __ldcg(p + m), Sa[k] = __ldcg(p + N + m), Sb[k] = __ldcg(p + 2 * N + m);
-    xm[k] = a.xmean[m], pc[k] = a.pc[m], vnT[k] = a.vn[m], dv[k] = a.dvec[m], vv[k] = a.vvec[m], dC[k] = a.diagC[m];
   }
   const int r0 = a.rank[0], r1 = a.P > 1 ? a.rank[1] : 0;
   const double inf = 1.0 / 0.0;
@@ -764,6 +949,7 @@ vd_update_kernel(const VdPtrs<T> a) {
     c->base.status = status;
   }
   VD_STAMP(11);
+  if (tid == 0) vd_time_stamp(15);
 }
 
 template <typename T>
@@ -838,6 +1024,40 @@ static VdPtrs<T> vd_ptrs(const sp_vd_state* st, int it, int evaluate) {
   return a;
 }
 
+// the device-resident loop on full-warp rows: register tiles up to 16 scalars per lane (compile-time configured
+// variants), the shared-memory row kernel above for wider rows
+template <typename T, int C>
+static void vd_sample_fast(const VdPtrs<T>& a, const PhiloxKeys& keys, int64_t P, bool full, int fast, int grid, bool pdl,
+                           cudaStream_t s) {
+  if constexpr (C >= 4) {
+    constexpr size_t smem = vd_smem_bytes<C, T>();
+    constexpr int per_sm = C * (int)sizeof(T) <= 32 ? 4 : 2;
+    auto kf = vd_sample_smem_kernel<T, C, true>;
+    auto kp = vd_sample_smem_kernel<T, C, false>;
+    static thread_local bool configured[64];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) dev = 0;
+    if (!configured[dev]) {
+      cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      cudaFuncSetAttribute(kp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      configured[dev] = true;
+    }
+    int64_t g = (P + kThreads / 32 - 1) / (kThreads / 32), cap = (int64_t)sm_count() * per_sm;
+    if (g > cap) g = cap;
+    if (full) launch_pdl(kf, dim3((unsigned)g), dim3(kThreads), smem, s, pdl, a, keys);
+    else launch_pdl(kp, dim3((unsigned)g), dim3(kThreads), smem, s, pdl, a, keys);
+  } else {
+    if (fast == 1) {
+      if (full) launch_pdl(vd_sample_eval_kernel<T, C, 32, true, false, 1>, dim3(grid), dim3(kThreads), 0, s, pdl, a, keys);
+      else launch_pdl(vd_sample_eval_kernel<T, C, 32, false, false, 1>, dim3(grid), dim3(kThreads), 0, s, pdl, a, keys);
+    } else {
+      if (full) launch_pdl(vd_sample_eval_kernel<T, C, 32, true, false, 2>, dim3(grid), dim3(kThreads), 0, s, pdl, a, keys);
+      else launch_pdl(vd_sample_eval_kernel<T, C, 32, false, false, 2>, dim3(grid), dim3(kThreads), 0, s, pdl, a, keys);
+    }
+  }
+}
+
 template <typename T>
 static int vd_sample(const sp_vd_state* st, int it, int evaluate, cudaStream_t s) {
   const VdPtrs<T> a = vd_ptrs<T>(st, it, evaluate);
@@ -863,12 +1083,8 @@ static int vd_sample(const sp_vd_state* st, int it, int evaluate, cudaStream_t s
 #define SP_GO(TT, C, L, F, CL, FA) launch_pdl(vd_sample_eval_kernel<TT, C, L, F, CL, FA>, dim3(grid), dim3(kThreads), 0, s, pdl, a, keys)
 #define SP_CALL(TT, C, L)                                                  \
   do {                                                                     \
-    if (L == 32 && fast == 1) {                                            \
-      if (full) SP_GO(TT, C, 32, true, false, 1);                          \
-      else SP_GO(TT, C, 32, false, false, 1);                              \
-    } else if (L == 32 && fast == 2) {                                     \
-      if (full) SP_GO(TT, C, 32, true, false, 2);                          \
-      else SP_GO(TT, C, 32, false, false, 2);                              \
+    if (L == 32 && fast != 0) {                                            \
+      vd_sample_fast<TT, C>(a, keys, st->P, full, fast, grid, pdl, s);     \
     } else if (L == 32 && full) {                                          \
       if (clip) SP_GO(TT, C, 32, true, true, 0);                           \
       else SP_GO(TT, C, 32, true, false, 0);                               \
@@ -905,12 +1121,12 @@ static int vd_update(const sp_vd_state* st, int it, cudaStream_t s) {
   SP_CHECK_LAUNCH();
   // chunk partials -> sums, then (last CTA) the update itself; also refreshes vn / diagC / fuse_a / fuse_b
   // (and dy) for the next generation
-  const int ups = cdiv(3 * (int64_t)N, kUpOut);
   cudaError_t le;
-  if (N <= 256) le = launch_pdl(vd_update_kernel<T, 1>, dim3(ups), dim3(kUpThreads), 0, s, true, a);
-  else if (N <= 512) le = launch_pdl(vd_update_kernel<T, 2>, dim3(ups), dim3(kUpThreads), 0, s, true, a);
-  else if (N <= 1024) le = launch_pdl(vd_update_kernel<T, 4>, dim3(ups), dim3(kUpThreads), 0, s, true, a);
-  else le = launch_pdl(vd_update_kernel<T, 8>, dim3(ups), dim3(kUpThreads), 0, s, true, a);
+  auto ups = [&](int) { return dim3((unsigned)cdiv(3 * (int64_t)N, kVdUpOut)); };
+  if (N <= 256) le = launch_pdl(vd_update_kernel<T, 1, 256>, ups(256), dim3(256), 0, s, true, a);
+  else if (N <= 512) le = launch_pdl(vd_update_kernel<T, 1, 512>, ups(512), dim3(512), 0, s, true, a);
+  else if (N <= 1024) le = launch_pdl(vd_update_kernel<T, 1, 1024>, ups(1024), dim3(1024), 0, s, true, a);
+  else le = launch_pdl(vd_update_kernel<T, 2, 1024>, ups(1024), dim3(1024), 0, s, true, a);
   (void)le;
   SP_CHECK_LAUNCH();
   return SP_OK;
