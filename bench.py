@@ -266,27 +266,32 @@ def sharded_swarm(sb, dist, world, popsize, gens=(100, 400), nccl=True):
     dev = torch.device("cuda", torch.cuda.current_device())
 
     def timed(exchange, it):
+        """(seconds of the whole call, max over ranks; device-timed generation loop in us per generation, max over
+        ranks; result)"""
         dist.barrier()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         r = parallel.cpso_sharded(sb.factory.styblinski_tang, b64, maxiter=it, exchange=exchange, **base)
         torch.cuda.synchronize()
-        t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        t = torch.tensor([time.perf_counter() - t0, r.loop_ms * 1e3 / max(1, r.loop_generations)], dtype=torch.float64,
+                         device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item()), r
+        return float(t[0].item()), float(t[1].item()), r
 
-    out = {"popsize": popsize, "ndim": 64, "rows_per_gpu": popsize // world}
+    out = {"popsize": popsize, "ndim": 64, "rows_per_gpu": popsize // world,
+           "timing": "generation loop between CUDA events on the launching stream (after the one-time IPC mailbox "
+                     "set-up), chunked enqueue + 64-byte status reads included; max over ranks"}
     res = None
     for exchange in (("peer", "nccl") if nccl else ("peer",)):
         timed(exchange, 8)
-        ta, _ = timed(exchange, gens[0])
-        tb, r = timed(exchange, gens[1])
-        per = (tb - ta) / (gens[1] - gens[0])
-        out[f"us_per_gen_{exchange}"] = per * 1e6
-        out[f"fixed_ms_{exchange}"] = (ta - gens[0] * per) * 1e3
+        _, us_a, _ = timed(exchange, gens[0])
+        tb, us_b, r = timed(exchange, gens[1])
+        out[f"us_per_gen_{exchange}"] = us_b
+        out[f"us_per_gen_{exchange}_short_run"] = us_a
+        out[f"call_seconds_{exchange}"] = tb
         if exchange == "peer":
             res = r
-            out["evals_per_s"] = popsize / per
+            out["evals_per_s"] = popsize / (us_b * 1e-6)
             out["evals_per_s_incl_setup"] = popsize * (gens[1] - 1) / tb
     # the same swarm on ONE GPU (every rank runs it on its own GPU: same work, no interference)
     def run1(it):
@@ -304,7 +309,7 @@ def sharded_swarm(sb, dist, world, popsize, gens=(100, 400), nccl=True):
     return out
 
 
-def vdcma_seeds(sb, dist, world, per_gpu=8, gens=40):
+def vdcma_seeds(sb, dist, world, per_gpu=8, gens=100):
     """BASELINE configs[4]: independent VD-CMA seeds, `per_gpu` per GPU, no collective in the loop."""
     import torch
 

@@ -275,7 +275,10 @@ int sp_jit_free(void* handle);
 
 /* ---- counter-based draws as a buffer: out[row][j] = U[0,1) (normal = 0) or N(0,1)
  * (normal = 1) of Philox counter (j / (16/sizeof(T)), row, it, purpose); the same
- * streams the generation kernels consume in place (csrc/philox.cuh). */
+ * streams the generation kernels consume in place (csrc/philox.cuh): LHS jitter (1), DE repair (4),
+ * PSO restart (7), ES draws (8, 9, 10, 11), NA walks (12).  The DE crossover decisions (2) and the
+ * PSO r1 / r2 coefficients (5, 6) are 16-bit pieces of differently keyed calls inside the kernels
+ * (csrc/philox.cuh) and are not available here: those purposes return SP_ERR_ARG. */
 int sp_random_fill(int dtype, void* d_out, int64_t P, int N, int64_t ld, int it, int purpose, uint64_t seed,
                    int normal, void* stream);
 

@@ -39,7 +39,10 @@ if which == "eigh_time":
             torch.cuda.synchronize(); t0 = time.perf_counter()
             L.call("sp_sym_eigh", eng.sp_dt, dC.data_ptr(), N, w.data_ptr(), B.data_ptr(), work.data_ptr(), warm, sw.data_ptr(), eng.stream)
             torch.cuda.synchronize(); dt = time.perf_counter() - t0
-            print(f"eigh N={N} warm={warm} pert={pert}: {dt*1e3:.3f} ms, sweeps={int(sw.item())}, per round {dt*1e6/max(1,int(sw.item()))/(N-1+N%2):.2f} us", flush=True)
+            nsw = int(sw.item())
+            offb = (2 * N * N + N) * 8  # per-sweep largest |cos| (fp32 bit patterns) sit behind W and lambda in `work`
+            worst = work.view(torch.uint8)[offb:offb + 4 * nsw].view(torch.float32).cpu().numpy()
+            print(f"eigh N={N} warm={warm} pert={pert}: {dt*1e3:.3f} ms, sweeps={nsw}, per round {dt*1e6/max(1,nsw)/(N-1+N%2):.2f} us, worst |cos| per sweep {['%.1e' % v for v in worst]}", flush=True)
 
 if which == "slopes":
     # per-generation device time in a real run (no profiler): slope between a short and a long run

@@ -274,6 +274,8 @@ int sp_random_fill(int dtype, void* out, int64_t P, int N, int64_t ld, int it, i
                    void* stream) {
   SP_CHECK_ARG(out && P >= 1 && N >= 1 && ld >= N, "null pointer or bad shape");
   SP_CHECK_ARG(dtype == SP_F32 || dtype == SP_F64, "dtype");
+  SP_CHECK_ARG(purpose != (int)kDeCross && purpose != (int)kPsoR1 && purpose != (int)kPsoR2,
+               "the DE crossover / PSO coefficient streams are 16-bit pieces drawn inside the kernels (philox.cuh)");
   cudaStream_t s = (cudaStream_t)stream;
   const int vec = dtype == SP_F32 ? 4 : 2;
   int64_t need = (P * (int64_t)((N + vec - 1) / vec) + 255) / 256, cap = (int64_t)sm_count() * 8;

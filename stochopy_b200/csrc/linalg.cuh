@@ -200,14 +200,20 @@ constexpr int kJacobiThreads = 1024;
 constexpr int kJacobiRegs = 8;  // row elements per lane staged in registers (N <= 256)
 
 // A sweep whose largest |cos(w_p, w_q)| (before its rotations) stayed below `quiet` needs no follow-up sweep:
-// the rotations of that sweep leave a residual of about quiet^2 (quadratic convergence).  fp64: 1e-6, i.e. a
-// residual of ~1e-12 relative -- B D^2 B^T reproduces C to ~1e-12 |C| (asserted to 1e-8 at N = 256 in
-// tests/test_gpu_sizes.py; the north-star bound is 1e-6) and a warm-started decomposition takes 3 sweeps instead
-// of 4.  fp32: the rounding-noise bound 0.25 sqrt(tol) ~ 7e-4.
+// the rotations of that sweep leave a residual of about quiet^2 (quadratic convergence; measured per-sweep maxima
+// of a warm-started N = 256 decomposition: 1.8e-2, 4.9e-3, 2.5e-5, 6.1e-10 -- profiles/r02_eigh_sweeps.txt).
+// fp64: 5e-5, i.e. a residual below 2.5e-9 relative -- B D^2 B^T reproduces C to that level (asserted to 1e-8 at
+// N = 256 in tests/test_gpu_sizes.py; the north-star bound is 1e-6), and a decomposition warm-started from the
+// previous generation's basis usually ends after 3 sweeps instead of 4.  SP_EIGH_QUIET overrides (profiling).
+// fp32: the rounding-noise bound 0.25 sqrt(tol) ~ 7e-4.
 template <typename T>
-__device__ __forceinline__ float jacobi_quiet(T tol) {
+__device__ __forceinline__ float jacobi_quiet(T tol, float q64) {
   const float q = 0.25f * sqrtf((float)tol);
-  return sizeof(T) == 8 ? fmaxf(q, 1.0e-6f) : q;
+  return sizeof(T) == 8 ? fmaxf(q, q64) : q;
+}
+inline float jacobi_quiet64() {
+  static const char* env = getenv("SP_EIGH_QUIET");
+  return env != nullptr ? (float)atof(env) : 5.0e-5f;
 }
 
 template <typename T>
@@ -414,7 +420,7 @@ template <typename T>
 __global__ void __launch_bounds__(kJacobiThreads, 1)
 jacobi_eigh_kernel(T* __restrict__ C, int N, T* __restrict__ w_out, T* __restrict__ B, T* __restrict__ lam_g,
                    int warm, const int* __restrict__ gate, const int* __restrict__ status_gate,
-                   int* __restrict__ sweeps_out) {
+                   int* __restrict__ sweeps_out, float q64) {
   extern __shared__ __align__(16) unsigned char jsm[];
   __shared__ unsigned int s_off;
   if (gate != nullptr && *gate == 0) return;
@@ -432,7 +438,7 @@ jacobi_eigh_kernel(T* __restrict__ C, int N, T* __restrict__ w_out, T* __restric
   __syncthreads();
 
   const T tol = jacobi_tol<T>(N);
-  const float quiet = jacobi_quiet<T>(tol);  // a sweep below this needs no follow-up sweep
+  const float quiet = jacobi_quiet<T>(tol, q64);  // a sweep below this needs no follow-up sweep
   const int n = N + (N & 1);  // even player count; index N (if any) is a bye
   const int half = n / 2;
   const bool regs = N <= 32 * kJacobiRegs;
@@ -580,7 +586,8 @@ template <typename T>
 __global__ void __launch_bounds__(512, 1)
 jacobi_block_kernel(T* __restrict__ C, int N, T* __restrict__ w_out, T* __restrict__ B, T* __restrict__ W,
                     T* __restrict__ lam, unsigned int* __restrict__ off, int warm, int b, int nblk,
-                    const int* __restrict__ gate, const int* __restrict__ status_gate, int* __restrict__ sweeps_out) {
+                    const int* __restrict__ gate, const int* __restrict__ status_gate, int* __restrict__ sweeps_out,
+                    float q64) {
   namespace cg = cooperative_groups;
   extern __shared__ __align__(16) unsigned char jbs[];
   if (gate != nullptr && *gate == 0) return;
@@ -601,7 +608,7 @@ jacobi_block_kernel(T* __restrict__ C, int N, T* __restrict__ w_out, T* __restri
   cl.sync();
 
   const T tol = jacobi_tol<T>(N);
-  const float quiet = jacobi_quiet<T>(tol);
+  const float quiet = jacobi_quiet<T>(tol, q64);
   const int m = nblk / 2, n2 = 2 * b;
   const bool regs = N <= 32 * kJacobiRegs;
   const int nv = N / Num<T>::VEC;  // rows are copied in 16-byte vectors when N allows it
@@ -712,7 +719,7 @@ inline cudaError_t jacobi_launch(T* C, int N, T* w, T* B, T* work, int warm, con
       if (e != cudaSuccess) return e;
       configured[dev] = true;
     }
-    kern<<<1, kJacobiThreads, need, s>>>(C, N, w, B, lam, warm, gate, status_gate, sweeps);
+    kern<<<1, kJacobiThreads, need, s>>>(C, N, w, B, lam, warm, gate, status_gate, sweeps, jacobi_quiet64());
     return cudaGetLastError();
   }
   static const char* env_b = getenv("SP_EIGH_BLOCK");  // profiling switch: rows per block
@@ -752,7 +759,7 @@ inline cudaError_t jacobi_launch(T* C, int N, T* w, T* B, T* work, int warm, con
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, kern, C, N, w, B, W, lam, off, warm, b, nblk, gate, status_gate, sweeps);
+  return cudaLaunchKernelEx(&cfg, kern, C, N, w, B, W, lam, off, warm, b, nblk, gate, status_gate, sweeps, jacobi_quiet64());
 }
 
 }  // namespace sp

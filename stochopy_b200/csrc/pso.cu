@@ -440,32 +440,50 @@ peer_gather_fit_kernel(const T* __restrict__ pbestfit, int64_t P, int64_t row0, 
 }
 
 // (4) reset the nw worst: V = 0, X = U(lower, upper), pbest = X, pbestfit = 1e30
+// A warp per row: one rank load decides for the whole row (most rows are left alone late in a run), the draws come
+// one Philox call per 16-byte vector (the element-per-thread version recomputed the call for each of its VEC
+// elements and divided every index by N: 10 us at P = 32768 x 64, 32 us per 131072 x 64 shard).
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
 restart_apply_kernel(T* X, T* V, T* pbest, T* pbestfit, const int32_t* __restrict__ rank, const T* __restrict__ lower,
                      const T* __restrict__ upper, int64_t P, int N, int64_t ld, int it, uint64_t seed,
                      const T* __restrict__ fresh, const sp_ctrl* ctrl, int64_t Ptot, int64_t row0) {
   constexpr int VEC = Num<T>::VEC;
+  using Vt = typename Num<T>::vec_t;
   const int nw = ctrl->flag;
   if (nw <= 0) return;
-  const int64_t total = P * (int64_t)N;
-  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t i = t / N;
-    const int j = (int)(t - i * N);
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * (kThreads / 32);
+  for (int64_t i = warp; i < P; i += nwarps) {
     const int64_t r = rank[i];
     if (r < Ptot - nw) continue;
-    T val;
-    if (fresh != nullptr) {
-      val = fresh[(Ptot - 1 - r) * ld + j];  // reset order: worst first (argsort()[:-nw-1:-1])
-    } else {
-      T blk[VEC];
-      uniform_block(philox4x32((uint32_t)(j / VEC), (uint32_t)(row0 + i), (uint32_t)it, kPsoRestart, seed), blk);
-      val = add_rn(lower[j], mul_rn(sub_rn(upper[j], lower[j]), blk[j % VEC]));
+    for (int j0 = lane * VEC; j0 < (int)ld; j0 += 32 * VEC) {  // ld is a multiple of VEC: whole vectors, padding stays 0
+      T val[VEC];
+      if (fresh != nullptr) {
+#pragma unroll
+        for (int e = 0; e < VEC; ++e)
+          val[e] = j0 + e < N ? fresh[(Ptot - 1 - r) * ld + j0 + e] : T(0);  // reset order: worst first (argsort()[:-nw-1:-1])
+      } else {
+        T blk[VEC];
+        uniform_block(philox4x32((uint32_t)(j0 / VEC), (uint32_t)(row0 + i), (uint32_t)it, kPsoRestart, seed), blk);
+#pragma unroll
+        for (int e = 0; e < VEC; ++e)
+          val[e] = j0 + e < N ? add_rn(lower[j0 + e], mul_rn(sub_rn(upper[j0 + e], lower[j0 + e]), blk[e])) : T(0);
+      }
+      Vt v, z;
+      T* pv = reinterpret_cast<T*>(&v);
+      T* pz = reinterpret_cast<T*>(&z);
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) {
+        pv[e] = val[e];
+        pz[e] = T(0);
+      }
+      *reinterpret_cast<Vt*>(X + i * ld + j0) = v;
+      *reinterpret_cast<Vt*>(pbest + i * ld + j0) = v;
+      *reinterpret_cast<Vt*>(V + i * ld + j0) = z;
     }
-    X[i * ld + j] = val;
-    pbest[i * ld + j] = val;
-    V[i * ld + j] = T(0);
-    if (j == 0) pbestfit[i] = T(1.0e30);
+    if (lane == 0) pbestfit[i] = T(1.0e30);
   }
 }
 
@@ -616,11 +634,15 @@ static int pso_check(const sp_pso_state* st, int it) {
 
 template <typename T>
 static int restart_plan_launch(const sp_pso_state* st, int it, int32_t* rank, cudaStream_t s) {
-  const int grid = grid_for_rows(st->P, 32, 8);
-  radius_kernel<T><<<grid, kThreads, 0, s>>>((const T*)st->X, (const T*)st->gbest, st->P, st->N, st->ld, st->ctrl);
-  SP_CHECK_LAUNCH();
-  restart_plan_kernel<<<1, 1, 0, s>>>(st->ctrl, st->P, st->N, it, st->maxiter, st->gamma, st->delta);
-  SP_CHECK_LAUNCH();
+  {  // radius + decision fused (the last CTA decides): one launch instead of two
+    const int vec = Num<T>::VEC;
+    int lpr = 1;
+    while (lpr < 32 && lpr * vec < st->ld) lpr <<= 1;
+    const int grid = grid_for_rows(st->P, lpr, 4);
+    radius_plan_kernel<T><<<grid, kThreads, 0, s>>>((const T*)st->X, (const T*)st->gbest, st->P, st->N, st->ld, st->ctrl, it,
+                                                  st->maxiter, st->gamma, st->delta, lpr, 0, st->P, PeerArgs{});
+    SP_CHECK_LAUNCH();
+  }
   if (rank_launch<T>((const T*)st->pbestfit, st->P, rank, &st->ctrl->flag, s) != cudaSuccess) return SP_ERR_CUDA;
   return SP_OK;
 }
@@ -628,9 +650,8 @@ static int restart_plan_launch(const sp_pso_state* st, int it, int32_t* rank, cu
 template <typename T>
 static int restart_apply_launch(const sp_pso_state* st, int it, const int32_t* rank, const void* fresh,
                                 cudaStream_t s) {
-  int64_t total = st->P * (int64_t)st->N;
-  int64_t need = (total + 255) / 256, cap = (int64_t)sm_count() * 8;
-  restart_apply_kernel<T><<<(int)(need < cap ? need : cap), 256, 0, s>>>(
+  int64_t need = (st->P + kThreads / 32 - 1) / (kThreads / 32), cap = (int64_t)sm_count() * 8;
+  restart_apply_kernel<T><<<(int)(need < cap ? need : cap), kThreads, 0, s>>>(
       (T*)st->X, (T*)st->V, (T*)st->pbest, (T*)st->pbestfit, rank, (const T*)st->lower, (const T*)st->upper, st->P,
       st->N, st->ld, it, st->seed, (const T*)fresh, st->ctrl, st->shard ? st->P_total : st->P, st->shard ? st->row0 : 0);
   SP_CHECK_LAUNCH();
@@ -641,21 +662,40 @@ template <typename T>
 static int pso_run_sharded(const sp_pso_state* st, int it_first, int n, int32_t* rank_all, cudaStream_t s) {
   const PeerArgs p = peer_args<T>(st);
   const T* fit_all = reinterpret_cast<const T*>(static_cast<const unsigned char*>(st->mailbox) + p.L.fit);
+  // profiling switch (results are then wrong, timing only): bit 0 skips radius + decision, 1 the pbestfit
+  // all-gather, 2 the ranking, 3 the reset
+  static const int skip = getenv("SP_SHARD_SKIP") != nullptr ? atoi(getenv("SP_SHARD_SKIP")) : 0;
   for (int g = 0; g < n; ++g) {
     const int it = it_first + g;
     int rc = pso_launch<T>(st, it, 0, s);
     if (rc) return rc;
     if (st->gamma < 0.0) continue;
-    const int grid = grid_for_rows(st->P, 32, 8);
-    radius_kernel<T><<<grid, kThreads, 0, s>>>((const T*)st->X, (const T*)st->gbest, st->P, st->N, st->ld, st->ctrl);
-    SP_CHECK_LAUNCH();
-    restart_plan_peer_kernel<<<1, 64, 0, s>>>(st->ctrl, st->P_total, st->N, it, st->maxiter, st->gamma, st->delta, p);
-    SP_CHECK_LAUNCH();
-    peer_gather_fit_kernel<T><<<1, 1024, 0, s>>>((const T*)st->pbestfit, st->P, st->row0, st->ctrl, it, p);
-    SP_CHECK_LAUNCH();
-    if (rank_launch<T>(fit_all, st->P_total, rank_all, &st->ctrl->flag, s) != cudaSuccess) return SP_ERR_CUDA;
-    rc = restart_apply_launch<T>(st, it, rank_all + st->row0, nullptr, s);
-    if (rc) return rc;
+    if (!(skip & 1)) {  // radius + max-reduce over the ranks + decision in ONE kernel (the last CTA exchanges), launched programmatically
+      const int vec = Num<T>::VEC;
+      int lpr = 1;
+      while (lpr < 32 && lpr * vec < st->ld) lpr <<= 1;
+      const int grid = grid_for_rows(st->P, lpr, 4);
+      cudaError_t e = launch_pdl(radius_plan_kernel<T>, dim3(grid), dim3(kThreads), 0, s, true, (const T*)st->X,
+                                 (const T*)st->gbest, st->P, st->N, st->ld, st->ctrl, it, st->maxiter, st->gamma,
+                                 st->delta, lpr, 0, st->P_total, p);
+      if (e != cudaSuccess) {
+        set_error("sp_pso_run_sharded: %s", cudaGetErrorString(e));
+        return SP_ERR_CUDA;
+      }
+      g_launches.fetch_add(1, std::memory_order_relaxed);
+    }
+    if (!(skip & 2)) {
+      peer_gather_fit_kernel<T><<<1, 1024, 0, s>>>((const T*)st->pbestfit, st->P, st->row0, st->ctrl, it, p);
+      SP_CHECK_LAUNCH();
+    }
+    // every rank sorts all chunks of the all-gathered fitness but merges only the chunks of its own rows
+    if (!(skip & 4) &&
+        rank_launch<T>(fit_all, st->P_total, rank_all, &st->ctrl->flag, s, nullptr, st->row0, st->P) != cudaSuccess)
+      return SP_ERR_CUDA;
+    if (!(skip & 8)) {
+      rc = restart_apply_launch<T>(st, it, rank_all + st->row0, nullptr, s);
+      if (rc) return rc;
+    }
   }
   return SP_OK;
 }
@@ -688,7 +728,8 @@ static int restart_resume(const sp_pso_state* st, int it, int32_t* rank, cudaStr
     n = st->P_total;
     mine = rank + st->row0;
   }
-  if (rank_launch<T>(fit, n, rank, &st->ctrl->flag, s) != cudaSuccess) {
+  if (rank_launch<T>(fit, n, rank, &st->ctrl->flag, s, nullptr, st->shard == 2 ? st->row0 : 0, st->shard == 2 ? st->P : -1) !=
+      cudaSuccess) {
     set_error("sp_cpso_restart_resume: ranking failed");
     return SP_ERR_CUDA;
   }

@@ -142,7 +142,7 @@ rank_sort_kernel(const T* __restrict__ fit, int64_t P, int n, typename RankItem<
 template <typename T>
 __global__ void __launch_bounds__(kRankChunk)
 rank_merge_kernel(const typename RankItem<T>::type* __restrict__ sorted, int64_t P, int C,
-                  int32_t* __restrict__ rank, const int32_t* gate, const int32_t* live = nullptr) {
+                  int32_t* __restrict__ rank, const int32_t* gate, const int32_t* live = nullptr, int ab0 = 0) {
   using R = RankItem<T>;
   using I = typename R::type;
   constexpr int n = kRankChunk;
@@ -151,7 +151,7 @@ rank_merge_kernel(const typename RankItem<T>::type* __restrict__ sorted, int64_t
   if (gate != nullptr && *gate <= 0) return;
   if (live != nullptr && *reinterpret_cast<const volatile int32_t*>(live) != SP_RUNNING) return;
   __shared__ I s[2][n];
-  const int ab = blockIdx.x, G = gridDim.y, t = threadIdx.x;
+  const int ab = ab0 + blockIdx.x, G = gridDim.y, t = threadIdx.x;  // ab0: first chunk whose items are ranked
   const I me = sorted[(int64_t)ab * n + t];
   const uint32_t idx = R::index(me);
   const bool real = idx < (uint64_t)P;
@@ -220,12 +220,16 @@ inline cudaError_t rank_launch_ws(const T* fit, int64_t P, int32_t* rank, void* 
   int G = (3 * sm_count() + C - 1) / C;  // about three CTAs per SM in all
   G = G < 1 ? 1 : (G > C ? C : G);
   g_launches.fetch_add(2, std::memory_order_relaxed);
-  return launch_pdl(rank_merge_kernel<T>, dim3((unsigned)C, (unsigned)G), dim3(n), 0, s, true, (const I*)ws, P, C, rank, gate, live);
+  return launch_pdl(rank_merge_kernel<T>, dim3((unsigned)C, (unsigned)G), dim3(n), 0, s, true, (const I*)ws, P, C, rank, gate, live, 0);
 }
 
+// first / count (optional): only the items first .. first + count - 1 need their rank (a rank of a row-sharded
+// swarm ranks its own rows against the whole all-gathered vector): every chunk is sorted, but only the chunks
+// that overlap the range are merged against the others -- 1 / world of the merge work.  rank[] of the other
+// items is left incomplete.
 template <typename T>
 inline cudaError_t rank_launch(const T* fit, int64_t P, int32_t* rank, const int32_t* gate, cudaStream_t s,
-                               const int32_t* live = nullptr) {
+                               const int32_t* live = nullptr, int64_t first = 0, int64_t count = -1) {
   using I = typename RankItem<T>::type;
   if (P <= kRankChunk) {
     int n = 2;
@@ -242,9 +246,15 @@ inline cudaError_t rank_launch(const T* fit, int64_t P, int32_t* rank, const int
   cudaError_t e = rank_scratch(&ws, (size_t)C * n * sizeof(I), s);
   if (e != cudaSuccess) return e;
   rank_sort_kernel<T><<<C, n / 2, 0, s>>>(fit, P, n, (I*)ws, rank, gate, 0, live);
-  int G = (3 * sm_count() + C - 1) / C;  // about three CTAs per SM in all
+  int ab0 = 0, Cm = C;
+  if (count >= 0) {
+    ab0 = (int)(first / n);
+    Cm = (int)((first + (count > 0 ? count : 1) - 1) / n) - ab0 + 1;
+    if (ab0 + Cm > C) Cm = C - ab0;
+  }
+  int G = (3 * sm_count() + Cm - 1) / Cm;  // about three CTAs per SM in all
   G = G < 1 ? 1 : (G > C ? C : G);
-  rank_merge_kernel<T><<<dim3((unsigned)C, (unsigned)G), n, 0, s>>>((const I*)ws, P, C, rank, gate, live);
+  rank_merge_kernel<T><<<dim3((unsigned)Cm, (unsigned)G), n, 0, s>>>((const I*)ws, P, C, rank, gate, live, ab0);
   e = cudaGetLastError();
   g_launches.fetch_add(2, std::memory_order_relaxed);
   cudaError_t f = cudaFreeAsync(ws, s);

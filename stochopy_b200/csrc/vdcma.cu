@@ -18,6 +18,7 @@
 namespace sp {
 
 constexpr int kVdChunks = 256;
+constexpr int kVdAuxZgen = 15;  // ctrl->aux slot: generation whose z draws sit in arx (vd_zgen_rows), 0 = none
 constexpr int kVdUpOut = 32;   // outputs of the chunk reduction per CTA of vd_update_kernel (3 N / 32 CTAs)
 constexpr int kVdUpMax = 512;  // CTAs of vd_update_kernel: 3 N / 32, N <= 2048 -> <= 192
 
@@ -354,7 +355,13 @@ vd_sample_smem_kernel(const VdPtrs<T> a, const PhiloxKeys keys) {
   const bool inject = c->inject != 0;
   const bool stream = a.stream_stores != 0;
   const uint32_t it = (uint32_t)a.it;
-  if (blockIdx.x == 0 && threadIdx.x == 0) const_cast<sp_es_ctrl*>(c)->sigma_gen = c->sigma;
+  // z of this generation may already sit in the (otherwise unused, lean) arx buffer: the previous generation's
+  // update kernel draws it on the SMs its single-CTA phase leaves idle (vd_zgen_rows) and says so in aux[15]
+  const bool zpre = c->aux[kVdAuxZgen] == (double)a.it;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    const_cast<sp_es_ctrl*>(c)->sigma_gen = c->sigma;
+    const_cast<sp_es_ctrl*>(c)->pad_ = 0;  // row-claim counter of the next vd_zgen_rows
+  }
   __syncthreads();
   auto lds = [&](const T* p, int j0, T (&o)[VEC]) {
     const V t = *reinterpret_cast<const V*>(p + j0);
@@ -378,7 +385,14 @@ vd_sample_smem_kernel(const VdPtrs<T> a, const PhiloxKeys keys) {
       T z[VEC], vn[VEC];
 #pragma unroll
       for (int e = 0; e < VEC; ++e) z[e] = T(0);
-      if (FULL || j0 < N) {
+      if (zpre) {
+        if (FULL || j0 < ld) {
+          const V t = __ldcs(reinterpret_cast<const V*>(a.arx + row * ldr + j0));  // read once
+          const T* q = reinterpret_cast<const T*>(&t);
+#pragma unroll
+          for (int e = 0; e < VEC; ++e) z[e] = q[e];
+        }
+      } else if (FULL || j0 < N) {
         normal_block(philox4x32_keyed<kEsZRounds>((uint32_t)(j0 / VEC), (uint32_t)row, it, kEsZ, keys), z);
         if (!FULL) {
 #pragma unroll
@@ -563,6 +577,49 @@ vd_wsum_kernel(const VdPtrs<T> a) {
     }
 }
 
+// ---- z of the NEXT generation, drawn while the update kernel's single-CTA phase runs (experiment, off by default:
+// measured slower, see vd_update) ---------------------------------------------------------------------------------
+// The N(0,1) draws depend only on (seed, row, generation): nothing of the update is needed for them, and they are 45 %
+// of the sampling kernel's instructions.  The update kernel therefore runs with one CTA per SM; the CTAs that are not
+// (or no longer) needed by the update claim rows from a device counter (ctrl->pad_) and store z of generation it + 1
+// into arx -- unused in the lean device-resident loop -- and the sampling kernel of it + 1 reads it (aux[15] holds the
+// generation the buffer is valid for).  Same Philox counters as the in-kernel draws: bitwise the same run.
+constexpr int kVdZgenBatch = 4;  // rows per claim
+template <typename T>
+__device__ __forceinline__ void vd_zgen_rows(const VdPtrs<T>& a, const PhiloxKeys& keys) {
+  using V = typename Num<T>::vec_t;
+  constexpr int VEC = Num<T>::VEC;
+  const int lane = threadIdx.x & 31;
+  const uint32_t it = (uint32_t)(a.it + 1);
+  int32_t* counter = &a.ctrl->pad_;
+  for (;;) {
+    int r0 = 0;
+    if (lane == 0) r0 = atomicAdd(counter, kVdZgenBatch);
+    r0 = __shfl_sync(0xffffffffu, r0, 0);
+    if (r0 >= a.P) break;
+#pragma unroll 1
+    for (int r = r0; r < r0 + kVdZgenBatch && r < a.P; ++r) {
+      T* __restrict__ zrow = a.arx + (int64_t)r * a.ld;
+#pragma unroll 2
+      for (int j0 = lane * VEC; j0 < (int)a.ld; j0 += 32 * VEC) {
+        T z[VEC];
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) z[e] = T(0);
+        if (j0 < a.N) {
+          normal_block(philox4x32_keyed<kEsZRounds>((uint32_t)(j0 / VEC), (uint32_t)r, it, kEsZ, keys), z);
+#pragma unroll
+          for (int e = 0; e < VEC; ++e) z[e] = (j0 + e < a.N) ? z[e] : T(0);
+        }
+        V t;
+        T* q = reinterpret_cast<T*>(&t);
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) q[e] = z[e];
+        *reinterpret_cast<V*>(zrow + j0) = t;
+      }
+    }
+  }
+}
+
 // Block reduction with ONE barrier: warp butterflies, one shared slot per (value, warp), then every thread
 // folds the NW warp results itself, in warp order (deterministic).  Two slot sets alternate (`ph`), so a
 // thread may start the next reduction while others still read this one's slots.
@@ -622,9 +679,11 @@ __device__ __forceinline__ void reduce1(double (&v)[K], const int (&op)[K], doub
 // UT threads per CTA (template parameter): one column per thread up to N = 1024 -- the single-CTA phase is a chain
 // of dependent fp64 operations (measured: ~14 cycles per instruction per warp with 8 warps; 26 us at N = 1024 with
 // four columns per thread), so it wants as many warps as there are columns, not registers per thread.
+// n1: CTAs of phase 1 (the first n1 of the grid); zgen != 0: the grid has one CTA per SM and every CTA that is not
+// (or no longer) busy with the update draws z of the next generation (vd_zgen_rows).
 template <typename T, int kVdNpt, int kUpThreads>
 __global__ void __launch_bounds__(kUpThreads)
-vd_update_kernel(const VdPtrs<T> a) {
+vd_update_kernel(const VdPtrs<T> a, const int n1, const int zgen, const PhiloxKeys keys) {
   constexpr int kUpOut = kVdUpOut, kGroups = kUpThreads / kUpOut;
   __shared__ double s_red[kRedDoubles];
   __shared__ T s_p[kGroups][kUpOut];
@@ -634,6 +693,11 @@ vd_update_kernel(const VdPtrs<T> a) {
   sp_es_ctrl* c = a.ctrl;
   if (!es_running(c)) return;
   const int N = a.N, tid = threadIdx.x, nt = blockDim.x;
+  const bool draw_next = zgen != 0 && a.it < a.maxiter;
+  if ((int)blockIdx.x >= n1) {  // not part of the update: straight to the draws
+    if (draw_next) vd_zgen_rows<T>(a, keys);
+    return;
+  }
   const long long clk0 = clock64();
   if (blockIdx.x == 0 && tid == 0) vd_time_stamp(14);
   // the N-vectors this generation did not touch yet: loaded by every CTA before the grid-wide hand-over, so the
@@ -662,7 +726,7 @@ vd_update_kernel(const VdPtrs<T> a) {
     }
     // this CTA's slice of the population: row of rank 0 (ties by index: the stable rank's first minimum)
     // and min / max fitness
-    const int64_t per = (a.P + gridDim.x - 1) / gridDim.x;
+    const int64_t per = (a.P + n1 - 1) / n1;
     const int64_t i0 = blockIdx.x * per, i1 = (i0 + per < a.P) ? i0 + per : a.P;
     double ext[3] = {1.0 / 0.0, -1.0 / 0.0, -1.0};  // min f, max f, best row (or -1)
     for (int64_t i = i0 + tid; i < i1; i += nt) {
@@ -688,11 +752,14 @@ vd_update_kernel(const VdPtrs<T> a) {
     __syncthreads();
     if (tid == 0) {
       const unsigned prev = atomicAdd(&c->base.done_blocks, 1u);
-      s_last = prev == gridDim.x - 1;
+      s_last = prev == (unsigned)n1 - 1u;
       if (s_last) c->base.done_blocks = 0;  // ready for the next launch
     }
     __syncthreads();
-    if (!s_last) return;
+    if (!s_last) {
+      if (draw_next) vd_zgen_rows<T>(a, keys);
+      return;
+    }
     __threadfence();
   }
   if (tid == 0) g_vd_clk[0] = clk0;
@@ -719,7 +786,7 @@ vd_update_kernel(const VdPtrs<T> a) {
   // [12] min f  [13] max f  [14] row of rank 0
   double L1[15] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 1.0, inf, -inf, inf, -inf, inf, -inf, -1.0};
   if (tid < a.chunks) L1[2] = (double)__ldcg(a.hpart() + tid);
-  for (int b = tid; b < (int)gridDim.x; b += nt) {  // the per-CTA scan results of phase 1
+  for (int b = tid; b < n1; b += nt) {  // the per-CTA scan results of phase 1
     const double* fp = a.fpart() + 3 * b;
     L1[12] = fmin(L1[12], __ldcg(fp));
     L1[13] = fmax(L1[13], __ldcg(fp + 1));
@@ -947,9 +1014,11 @@ vd_update_kernel(const VdPtrs<T> a) {
     c->aux[2] = up;
     c->base.nit = a.it;
     c->base.status = status;
+    c->aux[kVdAuxZgen] = (draw_next && status == SP_RUNNING) ? (double)(a.it + 1) : 0.0;
   }
   VD_STAMP(11);
   if (tid == 0) vd_time_stamp(15);
+  if (draw_next) vd_zgen_rows<T>(a, keys);  // whatever rows are left
 }
 
 template <typename T>
@@ -1122,11 +1191,23 @@ static int vd_update(const sp_vd_state* st, int it, cudaStream_t s) {
   // chunk partials -> sums, then (last CTA) the update itself; also refreshes vn / diagC / fuse_a / fuse_b
   // (and dy) for the next generation
   cudaError_t le;
-  auto ups = [&](int) { return dim3((unsigned)cdiv(3 * (int64_t)N, kVdUpOut)); };
-  if (N <= 256) le = launch_pdl(vd_update_kernel<T, 1, 256>, ups(256), dim3(256), 0, s, true, a);
-  else if (N <= 512) le = launch_pdl(vd_update_kernel<T, 1, 512>, ups(512), dim3(512), 0, s, true, a);
-  else if (N <= 1024) le = launch_pdl(vd_update_kernel<T, 1, 1024>, ups(1024), dim3(1024), 0, s, true, a);
-  else le = launch_pdl(vd_update_kernel<T, 2, 1024>, ups(1024), dim3(1024), 0, s, true, a);
+  const int n1 = (int)cdiv(3 * (int64_t)N, kVdUpOut);
+  // z of the next generation CAN be drawn inside this kernel (on the SMs its single-CTA phase leaves idle) when the
+  // next sampling launch is the shared-memory-row kernel of the lean device-resident loop (vd_sample_fast with
+  // CH >= 4).  Measured on B200 (C5 fp32, profiles/r02_vd_zgen_experiment.txt): SLOWER, 101.1 vs 90.3 us per
+  // generation -- the draws take longer than the single-CTA phase they hide behind (update 20 -> 25.5 us) and the
+  // sampling kernel gains nothing from reading z back (64 MB of z + 64 MB of y no longer fit the L2 together;
+  // sample + rank 50.7 -> 55.1 us).  Off unless SP_VD_ZGEN=1.
+  static const bool no_zgen = getenv("SP_VD_ZGEN") == nullptr;
+  Shape sh;
+  const bool wide = pick_shape(N, Num<T>::VEC, &sh) && sh.lpr == 32 && sh.ch >= 4;
+  const int zgen = (!no_zgen && st->lean && !st->host_z && st->constraint != SP_CONS_PENALIZE && wide) ? 1 : 0;
+  const int grid = zgen && sm_count() > n1 ? sm_count() : n1;
+  const PhiloxKeys keys = philox_keys(st->seed);
+  if (N <= 256) le = launch_pdl(vd_update_kernel<T, 1, 256>, dim3(grid), dim3(256), 0, s, true, a, n1, zgen, keys);
+  else if (N <= 512) le = launch_pdl(vd_update_kernel<T, 1, 512>, dim3(grid), dim3(512), 0, s, true, a, n1, zgen, keys);
+  else if (N <= 1024) le = launch_pdl(vd_update_kernel<T, 1, 1024>, dim3(grid), dim3(1024), 0, s, true, a, n1, zgen, keys);
+  else le = launch_pdl(vd_update_kernel<T, 2, 1024>, dim3(grid), dim3(1024), 0, s, true, a, n1, zgen, keys);
   (void)le;
   SP_CHECK_LAUNCH();
   return SP_OK;

@@ -77,6 +77,13 @@ def minimize(
     d_shift = eng.upload_vec(np.where(span_mask, lower, upper), ld)
     d_mask = torch.from_numpy(span_mask.astype(np.int32)).to(eng.device)
     ctrl, scratch = eng.new_ctrl()
+    # the per-walker distance scratch is P x cap scalars and the transposed archive N x cap (cap = popsize * maxiter):
+    # quadratic in popsize -- fail early and clearly instead of running the device out of memory
+    need = (P * cap + (N + 2) * cap) * eng.np_dt.itemsize
+    free, _total = torch.cuda.mem_get_info(eng.device)
+    if need > 0.9 * free:
+        raise MemoryError(f"na: popsize={P}, maxiter={maxiter} needs {need / 2**30:.1f} GiB of device scratch "
+                          f"(popsize^2 * maxiter scalars); {free / 2**30:.1f} GiB are free -- use a smaller popsize or maxiter")
     archT = eng.zeros(N, cap)
     archfit = eng.zeros(cap)
     rank = eng.zeros(cap, dtype=torch.int32)

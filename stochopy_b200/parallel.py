@@ -19,6 +19,8 @@ plumbing; the collectives carry device tensors.
 """
 import ctypes as C
 
+import os
+
 import numpy as np
 import torch
 import torch.distributed as dist
@@ -278,12 +280,22 @@ def cpso_sharded(fun, bounds, maxiter=100, popsize=10, inertia=0.7298, cognitivi
     ctrl64 = ctrl.view(torch.float64)  # aux[0] (local max squared radius) sits at byte 40
     it = 1
     c = eng.read_ctrl(ctrl)
+    # the generation loop timed on the device (CUDA events on the launching stream): the IPC mailbox set-up in
+    # front of it is a fixed cost of tens to hundreds of milliseconds that a wall clock would mix into the rate
+    ev_loop = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+    it_loop0, started = 1, False
     if mode == "peer":
         box = PeerMailboxes(L.load().sp_peer_bytes(eng.sp_dt, world, ld, Ptot), group, eng.device)
         st.shard, st.world, st.rank = 2, world, rank
         st.mailbox, st.peers = box.own, box.table.data_ptr()
         try:
             eager_left, last_restart = 0, -(1 << 30)
+            if os.environ.get("SP_SHARD_EAGER"):  # profiling switch: gated in-chunk restarts from the first generation on
+                eager_left = 1 << 30
+            if world > 1:
+                dist.barrier(group=group)  # every rank has mapped every mailbox and is about to enqueue
+            ev_loop[0].record()
+            started = True
             while c.status == L.SP_RUNNING:
                 n = min(32 if it < 64 else 128, max(int(maxiter), 2) - it)
                 if restart and eager_left <= 0:
@@ -307,6 +319,8 @@ def cpso_sharded(fun, bounds, maxiter=100, popsize=10, inertia=0.7298, cognitivi
             box.close()
         if c.status == L.SP_STATUS_PEER_TIMEOUT:
             raise L.EngineError("cpso_sharded: a peer did not answer within the exchange timeout")
+    if not started:
+        ev_loop[0].record()
     while c.status == L.SP_RUNNING:
         it += 1
         L.call("sp_pso_generation", C.byref(st), it, eng.stream)
@@ -332,6 +346,8 @@ def cpso_sharded(fun, bounds, maxiter=100, popsize=10, inertia=0.7298, cognitivi
                 L.call("sp_cpso_restart_apply", C.byref(st), it, rank_all[row0:].data_ptr(), None, eng.stream)
 
     it = c.nit
+    ev_loop[1].record()
+    ev_loop[1].synchronize()
     return OptimizeResult(
         x=gbest[:N].to("cpu").numpy().astype(np.float64),
         success=c.status >= 0,
@@ -340,4 +356,6 @@ def cpso_sharded(fun, bounds, maxiter=100, popsize=10, inertia=0.7298, cognitivi
         fun=float(c.gfit),
         nfev=it * Ptot,
         nit=it,
+        loop_ms=float(ev_loop[0].elapsed_time(ev_loop[1])),  # generations 2..nit on this rank (device time)
+        loop_generations=int(it - it_loop0),
     )
