@@ -1,3 +1,5 @@
+import signal
+signal.signal(signal.SIGPIPE, signal.SIG_DFL)  # `| head` closes the pipe early
 #!/usr/bin/env python
 """Aggregate an ncu launch list (csv from `ncu --metrics gpu__time_duration.sum[,more] --csv`) by kernel.
 Only rows of the metric gpu__time_duration.sum are summed (a csv captured with several metrics has one row

@@ -128,8 +128,8 @@ pso_generation_kernel(const PsoArgs<T> a, const PhiloxKeys keys) {
   int64_t mine_row = 0x7fffffffffffffffLL;
   // measured on B200 (C3, fp32 N=64): prefetching one group ahead costs 26 registers and a resident
   // CTA per SM and is slower (21.3 vs 17.0 us per generation) -- the state is L2 resident; keep it off
-  constexpr bool kPrefetch = false;
-  if (kPrefetch && warp < groups) fetch(warp);
+  constexpr bool kPrefetch = PLAIN;
+  if (kPrefetch && warp < groups && !(CHAIN && have_first)) fetch(warp);
   for (int64_t g = warp; g < groups; g += nwarps) {
     int64_t row = g * TL::RPW + sub;
     const bool live = PLAIN || row < a.P;
