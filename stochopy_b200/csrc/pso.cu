@@ -128,7 +128,8 @@ pso_generation_kernel(const PsoArgs<T> a, const PhiloxKeys keys) {
   int64_t mine_row = 0x7fffffffffffffffLL;
   // measured on B200 (C3, fp32 N=64): prefetching one group ahead costs 26 registers and a resident
   // CTA per SM and is slower (21.3 vs 17.0 us per generation) -- the state is L2 resident; keep it off
-  constexpr bool kPrefetch = PLAIN;
+  // (round 2, PLAIN variant, 48 / 63 registers with the prefetch: 11.2 vs 11.1 us per generation, no gain)
+  constexpr bool kPrefetch = false;
   if (kPrefetch && warp < groups && !(CHAIN && have_first)) fetch(warp);
   for (int64_t g = warp; g < groups; g += nwarps) {
     int64_t row = g * TL::RPW + sub;
