@@ -201,11 +201,8 @@ inline size_t rank_ws_bytes(int64_t P) { return (size_t)((P + kRankChunk - 1) / 
 
 // the same with caller-provided scratch and programmatic dependent launches: no pool traffic between
 // the kernels of a generation chain, and each kernel is scheduled while its predecessor drains
-// merge == false: only the chunk sort runs -- rank[] then holds the position of every item inside its own sorted
-// chunk and the caller adds the lower bounds in the other chunks itself (vd_wsum_kernel does, for its own rows)
 template <typename T>
-inline cudaError_t rank_launch_ws(const T* fit, int64_t P, int32_t* rank, void* ws, cudaStream_t s, const int32_t* live,
-                                  bool merge = true) {
+inline cudaError_t rank_launch_ws(const T* fit, int64_t P, int32_t* rank, void* ws, cudaStream_t s, const int32_t* live) {
   using I = typename RankItem<T>::type;
   const int32_t* gate = nullptr;
   if (P <= kRankChunk) {
@@ -220,10 +217,6 @@ inline cudaError_t rank_launch_ws(const T* fit, int64_t P, int32_t* rank, void* 
   const int C = (int)((P + n - 1) / n);
   cudaError_t e = launch_pdl(rank_sort_kernel<T>, dim3(C), dim3(n / 2), 0, s, true, fit, P, n, (I*)ws, rank, gate, 0, live);
   if (e != cudaSuccess) return e;
-  if (!merge) {
-    g_launches.fetch_add(1, std::memory_order_relaxed);
-    return cudaSuccess;
-  }
   int G = (3 * sm_count() + C - 1) / C;  // about three CTAs per SM in all
   G = G < 1 ? 1 : (G > C ? C : G);
   g_launches.fetch_add(2, std::memory_order_relaxed);

@@ -477,24 +477,16 @@ constexpr size_t vd_smem_bytes() { return (size_t)(4 + kThreads / 32) * Tile<T, 
 // time with 16-byte loads by two thread groups that take alternate batches and are folded in a fixed
 // order.  Only y is read: x is never needed.
 constexpr int kWsTile = 512, kWsUnroll = 8, kWsThreads = 512;
-// fuse_c > 0 (small populations: at most kWsFuseChunks sorted chunks, one column tile): the ranking kernel pair
-// stopped after the chunk sort -- rank[] holds positions inside the own chunk -- and this kernel completes the ranks
-// of ITS rows (own position + lower bound in each of the other fuse_c sorted chunks, four binary searches in flight
-// per thread, straight from the L2) and writes them back for vd_update: one launch and its gap less per generation.
-constexpr int kWsFuseChunks = 32;
 template <typename T>
 __global__ void __launch_bounds__(kWsThreads, 2)
-vd_wsum_kernel(const VdPtrs<T> a, const int fuse_c) {
+vd_wsum_kernel(const VdPtrs<T> a) {
   using V = typename Num<T>::vec_t;
-  using RI = RankItem<T>;
-  using I = typename RI::type;
   constexpr int VEC = Num<T>::VEC;
   pdl_launch_dependents();
   pdl_wait();
   if (!es_running(a.ctrl)) return;
   if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) vd_time_stamp(13);
   __shared__ int s_row[kWsTile];
-  __shared__ int s_cross[kWsTile];  // fused ranking: items of the other chunks that sort before the row
   __shared__ T s_w[kWsTile], s_wyn[kWsTile];
   __shared__ int s_cnt[kWsThreads / 32];
   __shared__ T s_h[kWsThreads / 32];
@@ -512,49 +504,7 @@ vd_wsum_kernel(const VdPtrs<T> a, const int fuse_c) {
   for (int64_t t0 = i0; t0 < i1; t0 += kWsTile) {
     __syncthreads();
     const int64_t i = t0 + tid;
-    if (fuse_c > 0) {
-      s_cross[tid] = 0;
-      __syncthreads();
-      const I* __restrict__ sorted = reinterpret_cast<const I*>(a.rank_ws());
-      const int rows_here = (int)((i1 - t0) < kWsTile ? (i1 - t0) : kWsTile);
-      const int total = rows_here * fuse_c;
-      // task q -> (row = q % rows_here, chunk = q / rows_here): neighbouring threads search the same chunk
-      for (int q0 = tid; q0 < total; q0 += 4 * kWsThreads) {
-        int lo[4], row[4];
-        const I* ch[4];
-        I key[4];
-        bool on[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int q = q0 + u * kWsThreads;
-          on[u] = q < total;
-          const int qq = on[u] ? q : 0;
-          row[u] = qq % rows_here;
-          const int c = qq / rows_here;
-          const int64_t gi = t0 + row[u];
-          on[u] = on[u] && c != (int)(gi / kRankChunk);  // the own chunk's share is what rank_sort_kernel left in rank[]
-          key[u] = RI::make(a.arfit[gi], (uint32_t)gi);
-          ch[u] = sorted + (size_t)c * kRankChunk;
-          lo[u] = 0;
-        }
-#pragma unroll
-        for (int h = kRankChunk >> 1; h > 0; h >>= 1) {
-#pragma unroll
-          for (int u = 0; u < 4; ++u) lo[u] += RI::less(ch[u][lo[u] + h - 1], key[u]) ? h : 0;
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          lo[u] += RI::less(ch[u][lo[u]], key[u]) ? 1 : 0;
-          if (on[u] && lo[u]) atomicAdd(&s_cross[row[u]], lo[u]);
-        }
-      }
-      __syncthreads();
-    }
-    int r = i < i1 ? a.rank[i] : a.mu;
-    if (fuse_c > 0 && i < i1) {
-      r += s_cross[tid];
-      a.rank[i] = r;  // complete rank for vd_update (one column tile in this mode: nobody else reads the partial one)
-    }
+    const int r = i < i1 ? a.rank[i] : a.mu;
     const T yn = i < i1 ? a.yvn[i] : T(0);  // in flight together with the rank
     const bool sel = r < a.mu;
     const T w = sel ? a.weights[r] : T(0);
@@ -1235,14 +1185,8 @@ static int vd_update(const sp_vd_state* st, int it, cudaStream_t s) {
         a.arx, a.coef(), a.arfit, P, N, st->ld, st->ctrl);
     SP_CHECK_LAUNCH();
   }
-  // small populations: the merge half of the ranking rides vd_wsum_kernel (SP_VD_NO_FUSED_RANK=1: profiling switch)
-  static const bool no_fuse = getenv("SP_VD_NO_FUSED_RANK") != nullptr;
-  const int col_tiles = (int)cdiv(st->ld, 256 * Num<T>::VEC);
-  const int rchunks = (int)cdiv(P, kRankChunk);
-  const int fuse_c = (!no_fuse && col_tiles == 1 && rchunks > 1 && rchunks <= kWsFuseChunks) ? rchunks : 0;
-  if (rank_launch_ws<T>(a.arfit, P, a.rank, a.rank_ws(), s, &st->ctrl->base.status, fuse_c == 0) != cudaSuccess)
-    return SP_ERR_CUDA;
-  launch_pdl(vd_wsum_kernel<T>, dim3(col_tiles, a.chunks), dim3(kWsThreads), 0, s, true, a, fuse_c);
+  if (rank_launch_ws<T>(a.arfit, P, a.rank, a.rank_ws(), s, &st->ctrl->base.status) != cudaSuccess) return SP_ERR_CUDA;
+  launch_pdl(vd_wsum_kernel<T>, dim3(cdiv(st->ld, 256 * Num<T>::VEC), a.chunks), dim3(kWsThreads), 0, s, true, a);
   SP_CHECK_LAUNCH();
   // chunk partials -> sums, then (last CTA) the update itself; also refreshes vn / diagC / fuse_a / fuse_b
   // (and dy) for the next generation
