@@ -221,12 +221,16 @@ int sp_cpso_radius(const sp_pso_state* st, int it, void* stream);
 int sp_cpso_decide(const sp_pso_state* st, int it, void* stream);
 /* enqueue generations it_first .. it_first+n-1 (+ restart when gamma >= 0) */
 int sp_pso_run(const sp_pso_state* st, int it_first, int n, int32_t* d_rank, void* stream);
-/* CPSO with the restart taken out of the common path: per generation only the generation
- * kernel and a fused radius + decision kernel are enqueued.  When a restart fires
- * (_cpso.py:405-426, rare while the swarm is wide) the decision kernel parks the run with
- * ctrl.status = SP_STATUS_RESTART_PENDING (nit = the generation whose restart is due, ctrl.flag =
- * nw) and the rest of the chunk returns at once; the host then calls sp_cpso_restart_resume
- * (ranking, reset of the nw worst, status back to SP_RUNNING) and continues at nit + 1. */
+/* CPSO with the restart taken out of the common path.  Whole swarm (shard == 0): per generation ONLY the
+ * generation kernel is enqueued; its epilogue takes the reference's decision `radius < delta`
+ * (_cpso.py:405-412) from a bound on the radius that needs no second pass over the swarm (the maximum
+ * distance to the PREVIOUS gbest, accumulated in the row loop, +- the distance the gbest moved), which is
+ * exact whenever the interval lies on one side of delta.  Peer-sharded swarm: generation kernel + a fused
+ * radius + max-reduce + decision kernel.  When a restart fires (_cpso.py:405-426) the run parks with
+ * ctrl.status = SP_STATUS_RESTART_PENDING (nit = the generation whose restart is due, ctrl.flag = nw, or
+ * -1 if the bound could not decide) and the rest of the chunk returns at once; the host then calls
+ * sp_cpso_restart_resume (exact radius decision if flag == -1, ranking, reset of the nw worst, status back
+ * to SP_RUNNING) and continues at nit + 1. */
 #define SP_STATUS_RESTART_PENDING (-901)
 int sp_pso_run_lazy(const sp_pso_state* st, int it_first, int n, void* stream);
 int sp_cpso_restart_resume(const sp_pso_state* st, int it, int32_t* d_rank, void* stream);

@@ -38,7 +38,47 @@ struct PsoArgs {
   PeerArgs peer;           // shard == 2: exchange inside the kernel over the peer mailboxes
   int chain;               // SP_CHAIN_IN / SP_CHAIN_OUT (plain PSO, whole swarm)
   T* chain_rows;           // [2 parities][kChainRegion][ld]: the best row of every CTA
+  int rbound;              // CPSO, whole swarm, lazy run: the restart decision is taken in this kernel's epilogue (below)
+  double gamma, delta;
 };
+
+// CPSO restart decision without a second pass over the swarm (rbound).  The reference tests
+//   radius(g) = max_i |X_i - gbest(g)| / sqrt(4 N) < delta            (cpso/_cpso.py:405-412)
+// with the gbest of THIS generation, which only exists once every CTA has finished.  But every CTA knows
+// gbest(g-1) while it moves its rows, and for every i  | |X_i - gbest(g)| - |X_i - gbest(g-1)| | <= dist with
+// dist = |gbest(g) - gbest(g-1)| -- which the epilogue computes anyway (it is selection_sync's x-tolerance test).
+// So with M = max_i |X_i - gbest(g-1)| (accumulated in the row loop, 4 subtractions + 4 FMAs + a group reduce per
+// row) the radius lies in [M - dist, M + dist] / sqrt(4 N): if the whole interval is on one side of delta the
+// decision is the reference's exactly; dist = 0 (gbest did not move) makes it exact always.  Otherwise the run parks
+// with ctrl->flag = -1 and sp_cpso_restart_resume takes the exact decision with the radius kernel.  eps covers the
+// rounding of the working-precision sums.
+template <typename T>
+__device__ __forceinline__ void restart_decide_bound(sp_ctrl* ctrl, double m2, int N, int64_t Ptot, int it, int maxiter,
+                                                     double gamma, double delta) {
+  if (ctrl->status != SP_RUNNING) {  // the generation terminated the run: no restart (_cpso.py:304)
+    ctrl->flag = 0;
+    return;
+  }
+  const double eps = sizeof(T) == 4 ? 1.0e-4 : 1.0e-10;
+  const double dist = ctrl->dist, M = sqrt(m2), s4n = sqrt(4.0 * (double)N);
+  const double hi = (M * (1.0 + eps) + dist) / s4n, lo = (M * (1.0 - eps) - dist) / s4n;
+  ctrl->aux[1] = M / s4n;
+  if (lo >= delta) {  // certainly no restart
+    ctrl->flag = 0;
+    return;
+  }
+  int nw = -1;        // -1: cannot tell from the bound
+  if (hi < delta) {   // certainly a restart: nw of _cpso.py:415-416
+    const double inorm = (double)it / (double)maxiter;
+    nw = (int)(((double)Ptot - 1.0) / (1.0 + exp(1.0 / 0.09 * (inorm - gamma + 0.5))));
+    if (nw <= 0) {
+      ctrl->flag = 0;
+      return;
+    }
+  }
+  ctrl->flag = nw;
+  ctrl->status = SP_STATUS_RESTART_PENDING;
+}
 
 // shard == 2, last CTA of the generation kernel: local best -> every peer's mailbox (NVLink
 // stores), flags, wait, then selection_sync's reduction over the `world` records on every rank.
@@ -126,6 +166,7 @@ pso_generation_kernel(const PsoArgs<T> a, const PhiloxKeys keys) {
   Best mine{1.0 / 0.0, 0x7fffffffffffffffLL};
   T mine_f = Num<T>::inf();  // PLAIN: the lane's minimum in T (rows ascend, strict < keeps the first = np.argmin's tie rule)
   int64_t mine_row = 0x7fffffffffffffffLL;
+  T dmax = 0;  // rbound: max over this thread's rows of |X_i - gbest(g-1)|^2
   // measured on B200 (C3, fp32 N=64): prefetching one group ahead costs 26 registers and a resident
   // CTA per SM and is slower (21.3 vs 17.0 us per generation) -- the state is L2 resident; keep it off
   // (round 2, PLAIN variant, 48 / 63 registers with the prefetch: 11.2 vs 11.1 us per generation, no gain)
@@ -199,6 +240,18 @@ pso_generation_kernel(const PsoArgs<T> a, const PhiloxKeys keys) {
       x.store(a.X + row * ldr, l, ld);
       v.store(a.V + row * ldr, l, ld);
     }
+    if (!CHAIN && a.rbound) {  // (padding columns are zero in both; the chained kernels never take this decision)
+      T d2 = 0;
+#pragma unroll
+      for (int c = 0; c < CH; ++c)
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) {
+          const T t = x.v[c][e] - gb.v[c][e];
+          d2 += t * t;
+        }
+      d2 = group_sum<LPR>(d2);
+      if (live && d2 > dmax) dmax = d2;
+    }
     if (!PLAIN && a.propose_only) continue;  // SP_OBJ_HOST: caller evaluates X, then sp_select_sync(copy_when=1)
 
     const T f = evaluate_tile<T, CH, LPR>(OBJ >= 0 ? OBJ : a.objective, x, l, N);
@@ -239,6 +292,18 @@ pso_generation_kernel(const PsoArgs<T> a, const PhiloxKeys keys) {
     }
     return;
   }
+  __shared__ double s_dmax[kThreads / 32];
+  if (!CHAIN && a.rbound) {  // the CTA's maximum goes to scratch region 1 (the chained kernels' region; this one is not chained)
+    double d = (double)dmax;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) d = fmax(d, __shfl_xor_sync(0xffffffffu, d, o));
+    if ((threadIdx.x & 31) == 0) s_dmax[threadIdx.x >> 5] = d;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      for (int w = 1; w < kThreads / 32; ++w) d = fmax(d, s_dmax[w]);
+      chain_region(a.scratch, 1)[blockIdx.x].f = d;  // published by grid_best's fence + arrival counter
+    }
+  }
   Best top;
   if (grid_best(mine, a.scratch, a.ctrl, &top)) {
     if (a.shard == 2) {
@@ -249,16 +314,35 @@ pso_generation_kernel(const PsoArgs<T> a, const PhiloxKeys keys) {
       if (threadIdx.x == 0) a.xch[0] = (T)top.f;
     } else {
       finalize_generation<T>(top, a.pbest, a.ld, a.N, a.gbest, a.ctrl, a.it, a.maxiter, a.xtol, a.ftol);
+      if (!CHAIN && a.rbound) {  // (thread 0 wrote ctrl->dist / status in finalize_generation; it also decides)
+        double d = 0.0;
+        for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x) d = fmax(d, __ldcg(&chain_region(a.scratch, 1)[i].f));
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) d = fmax(d, __shfl_xor_sync(0xffffffffu, d, o));
+        __syncthreads();
+        if ((threadIdx.x & 31) == 0) s_dmax[threadIdx.x >> 5] = d;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+          for (int w = 1; w < kThreads / 32; ++w) d = fmax(d, s_dmax[w]);
+          restart_decide_bound<T>(a.ctrl, d, a.N, a.P, a.it, a.maxiter, a.gamma, a.delta);
+        }
+      }
     }
   }
 }
 
 // ---- competitive restart, _cpso.py:405-426 ------------------------------------
 // (1) max_i |X_i - gbest|^2 -> ctrl->aux[0] (bit pattern, atomicMax on non-negative doubles)
+// parked != 0: runs only for a run parked by the bound decision with ctrl->flag == -1 (radius undecided)
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
-radius_kernel(const T* __restrict__ X, const T* __restrict__ gbest, int64_t P, int N, int64_t ld, sp_ctrl* ctrl) {
-  if (!running(ctrl)) return;
+radius_kernel(const T* __restrict__ X, const T* __restrict__ gbest, int64_t P, int N, int64_t ld, sp_ctrl* ctrl,
+              int parked = 0) {
+  if (parked) {
+    if (ctrl->status != SP_STATUS_RESTART_PENDING || ctrl->flag != -1) return;
+  } else if (!running(ctrl)) {
+    return;
+  }
   const int lane = threadIdx.x & 31;
   const int64_t warp = (int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
   const int64_t nwarps = (int64_t)gridDim.x * (kThreads / 32);
@@ -375,8 +459,11 @@ __global__ void restart_resume_kernel(sp_ctrl* ctrl) {
 }
 
 // (2) decision: radius < delta -> nw rows to reset (ctrl->flag), ctrl->aux[1] = radius
-__global__ void restart_plan_kernel(sp_ctrl* ctrl, int64_t P, int N, int it, int maxiter, double gamma, double delta) {  // P = whole swarm
-  if (!running(ctrl)) {
+__global__ void restart_plan_kernel(sp_ctrl* ctrl, int64_t P, int N, int it, int maxiter, double gamma, double delta,
+                                    int parked = 0) {  // P = whole swarm
+  if (parked) {  // exact decision for a run the bound could not decide (flag == -1); a decided one keeps its nw
+    if (ctrl->status != SP_STATUS_RESTART_PENDING || ctrl->flag != -1) return;
+  } else if (!running(ctrl)) {
     ctrl->flag = 0;
     return;
   }
@@ -550,7 +637,7 @@ static bool pso_launch_plain(const PsoArgs<T>& a, int grid, cudaStream_t s, bool
 
 template <typename T>
 static int pso_launch(const sp_pso_state* st, int it, int propose_only, cudaStream_t s, int chain = 0,
-                      bool after_kernel = false) {
+                      bool after_kernel = false, bool rbound = false) {
   Shape sh;
   if (!pick_shape(st->N, Num<T>::VEC, &sh)) {
     set_error("sp_pso_generation: ndim %d exceeds the compiled row shapes", st->N);
@@ -590,6 +677,9 @@ static int pso_launch(const sp_pso_state* st, int it, int propose_only, cudaStre
   a.peer = peer_args<T>(st);
   a.chain = propose_only ? 0 : chain;
   a.chain_rows = (T*)st->chain_rows;
+  a.rbound = rbound ? 1 : 0;
+  a.gamma = st->gamma;
+  a.delta = st->delta;
   const bool philox = st->r1 == nullptr;
   const PhiloxKeys keys = philox_keys(st->seed);
   int grid = grid_for_rows(st->P, sh.lpr, sh.ch >= 4 ? 2 : 4);
@@ -721,6 +811,13 @@ static int restart_resume(const sp_pso_state* st, int it, int32_t* rank, cudaStr
   const T* fit = (const T*)st->pbestfit;
   int64_t n = st->P;
   const int32_t* mine = rank;
+  if (st->shard == 0) {  // a run parked by the bound decision with flag == -1: the exact radius decides (no-ops otherwise)
+    const int grid = grid_for_rows(st->P, 32, 8);
+    radius_kernel<T><<<grid, kThreads, 0, s>>>((const T*)st->X, (const T*)st->gbest, st->P, st->N, st->ld, st->ctrl, 1);
+    SP_CHECK_LAUNCH();
+    restart_plan_kernel<<<1, 1, 0, s>>>(st->ctrl, st->P, st->N, it, st->maxiter, st->gamma, st->delta, 1);
+    SP_CHECK_LAUNCH();
+  }
   if (st->shard == 2) {
     const PeerArgs p = peer_args<T>(st);
     peer_gather_fit_kernel<T><<<1, 1024, 0, s>>>((const T*)st->pbestfit, st->P, st->row0, st->ctrl, it, p);
@@ -743,10 +840,15 @@ static int pso_run_lazy(const sp_pso_state* st, int it_first, int n, cudaStream_
   int lpr = 1;
   while (lpr < 32 && lpr * vec < st->ld) lpr <<= 1;
   const int grid = grid_for_rows(st->P, lpr, 4);
+  // whole swarm: the restart decision rides the generation kernel's epilogue (restart_decide_bound): ONE launch per
+  // generation; SP_CPSO_EXACT_RADIUS=1 keeps the separate radius + decision kernel (profiling / parity switch)
+  static const bool exact = getenv("SP_CPSO_EXACT_RADIUS") != nullptr;
+  const bool bound = st->shard == 0 && !exact;
   for (int g = 0; g < n; ++g) {
     const int it = it_first + g;
-    int rc = pso_launch<T>(st, it, 0, s, 0, g > 0);
+    int rc = pso_launch<T>(st, it, 0, s, 0, g > 0, bound);
     if (rc) return rc;
+    if (bound) continue;
     cudaError_t e = launch_pdl(radius_plan_kernel<T>, dim3(grid), dim3(kThreads), 0, s, true, (const T*)st->X,
                                (const T*)st->gbest, st->P, st->N, st->ld, st->ctrl, it, st->maxiter, st->gamma,
                                st->delta, lpr, 1, st->shard ? st->P_total : st->P, peer_args<T>(st));

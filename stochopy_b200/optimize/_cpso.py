@@ -162,16 +162,20 @@ def minimize(
                 c = eng.read_ctrl(ctrl)
                 if c.status == L.SP_STATUS_RESTART_PENDING:
                     L.call("sp_cpso_restart_resume", C.byref(st), c.nit, rank_ptr, eng.stream)
-                    if c.nit - last_restart < 16:  # restarts come in runs once the swarm has collapsed: the
-                        eager_left = 64            # gated in-chunk kernels are then cheaper than parking
+                    if c.nit - last_restart < 16:  # restarts come in runs (at large popsize: every generation of the
+                        eager_left = 32            # first part of a run): the gated in-chunk kernels are then cheaper
                     last_restart = c.nit
                     c.status = L.SP_RUNNING
                 it = c.nit
                 continue
+            n = min(n, 32)
             L.call("sp_pso_run", C.byref(st), it + 1, n, rank_ptr, eng.stream)
             eager_left -= n
             c = eng.read_ctrl(ctrl)
             it = c.nit
+            if c.flag > 0:  # the last generation of the window still restarted: stay with the eager sequence
+                eager_left = max(eager_left, 32)
+                last_restart = c.nit
             continue
         if streamer is not None:  # return_all: snapshots leave through a side stream, no per-generation sync
             for _ in range(min(64, last - it)):

@@ -44,3 +44,24 @@ def test_de_cross_uniform_pieces(dtype):
     # no visible structure along rows or columns
     assert abs(np.corrcoef(u[:, :-1].ravel(), u[:, 1:].ravel())[0, 1]) < 0.02
     assert abs(np.corrcoef(u[:-1].ravel(), u[1:].ravel())[0, 1]) < 0.02
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_pso_uniform_pieces(dtype):
+    """r1 / r2 of the PSO velocity update: 16-bit pieces of one Philox4x32-10 call per 4 columns -- multiples of
+    2^-16 in [0, 1), the same numbers in fp32 and fp64, r1 and r2 uncorrelated, mean 1/2."""
+    rows = np.arange(300, 812)
+    r1, r2 = px.pso_uniforms(rows, 70, 9, 4321, dtype)
+    for r in (r1, r2):
+        assert r.shape == (512, 70) and r.dtype == np.dtype(dtype)
+        k = r.astype(np.float64) * 65536.0
+        assert np.array_equal(k, np.round(k)) and k.min() >= 0 and k.max() <= 65535
+        assert abs(float(r.mean()) - 0.5) < 4.0 / np.sqrt(12.0 * r.size) + 2.0**-16
+    a1, a2 = px.pso_uniforms(rows, 70, 9, 4321, np.float64)
+    assert np.array_equal(r1.astype(np.float64), a1) and np.array_equal(r2.astype(np.float64), a2)
+    assert abs(np.corrcoef(r1.ravel(), r2.ravel())[0, 1]) < 0.02
+    b1, _ = px.pso_uniforms(rows, 70, 10, 4321, dtype)
+    assert not np.array_equal(r1, b1)
+    # a draw depends on (row, column, generation), not on which rows are asked for (sharded swarm)
+    c1, c2 = px.pso_uniforms(rows[100:200], 70, 9, 4321, dtype)
+    assert np.array_equal(c1, r1[100:200]) and np.array_equal(c2, r2[100:200])
