@@ -257,12 +257,17 @@ def other_configs(sb):
         torch.cuda.synchronize()
         return time.perf_counter() - t0
 
-    us = min(wall(450) for _ in range(2)) / 450 * 1e6
+    from stochopy_b200.optimize import _cpso
+
+    us_wall = min(wall(450) for _ in range(2)) / 450 * 1e6
+    us = _cpso.LAST_LOOP[0] * 1e3 / max(1, _cpso.LAST_LOOP[1])  # generation loop between CUDA events (no set-up)
     out["c3_cpso_styblinski_n64_p32768_f32"] = {
-        "us_per_generation": us, "evals_per_s": 32768 / (us * 1e-6), "algorithmic_bytes_per_eval": 1292,
-        "algorithmic_gb_s": 1292 * 32768 / (us * 1e-6) / 1e9, "roofline_frac": 1292 * 32768 / (us * 1e-6) / 1e9 / peak,
-        "note": "wall time of one 450-generation run / 450, set-up included (delta depends on maxiter: no slope); "
-                "restart phases (gated ranking + reset every generation) and quiet phases (generation + radius kernel) mixed"}
+        "us_per_generation": us, "us_per_generation_incl_setup": us_wall, "evals_per_s": 32768 / (us * 1e-6),
+        "algorithmic_bytes_per_eval": 1292, "algorithmic_gb_s": 1292 * 32768 / (us * 1e-6) / 1e9,
+        "roofline_frac": 1292 * 32768 / (us * 1e-6) / 1e9 / peak,
+        "note": "one 450-generation run: device-timed generation loop / generations (delta depends on maxiter: no slope "
+                "between run lengths); restart phase (gated ranking + reset every generation) and quiet phase (one "
+                "launch per generation) mixed"}
     rec("c4_cmaes_rosenbrock_n256_p4096_f64", 4096,
         mk(sb.factory.rosenbrock, [[-BOUND, BOUND]] * 256, "cmaes", popsize=4096), 10, 40,
         note="fp64; 0.99 GFLOP per generation incl. eigh (SURVEY.md 8d); latency bound")
@@ -318,14 +323,14 @@ def sharded_swarm(sb, dist, world, popsize, gens=(100, 400), nccl=True):
 
     # (no slope between two run lengths: CPSO's restart threshold depends on maxiter) one run of the same length,
     # wall time / generations, set-up included
+    from stochopy_b200.optimize import _cpso
+
     run1(8)
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
     r1 = run1(gens[1])
-    torch.cuda.synchronize()
-    us1 = (time.perf_counter() - t0) / gens[1] * 1e6
+    ms1, g1 = _cpso.LAST_LOOP
+    us1 = ms1 * 1e3 / max(1, g1)
     out["us_per_gen_1gpu"] = us1
-    out["us_per_gen_1gpu_note"] = "wall time of minimize(method='cpso') at the same maxiter / generations, set-up included"
+    out["us_per_gen_1gpu_note"] = "device-timed generation loop of minimize(method='cpso') at the same maxiter (same definition as us_per_gen_peer)"
     out["strong_scaling_efficiency"] = us1 / (world * out["us_per_gen_peer"])
     same = bool(np.array_equal(r1.x, res.x) and r1.fun == res.fun and r1.nit == res.nit and r1.status == res.status)
     t = torch.tensor([1 if same else 0], dtype=torch.int32, device=dev)
@@ -377,7 +382,7 @@ def our_arm(args):
     rs = np.random.RandomState(seed)
     x0_pin = torch.from_numpy(rs.uniform(-BOUND, BOUND, (P, N)).astype(np.float32)).pin_memory()
     x0 = x0_pin.numpy()  # host buffer in page-locked memory: what minimize() is handed in the e2e leg
-    st, keep = build_state(eng, L, x0, seed, 3 * (K + W) + 20)
+    st, keep = build_state(eng, L, x0, seed, 4 * (K + W) + 20)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=eng.device)
     flush_src = torch.zeros(64 << 20, dtype=torch.float32, device=eng.device)  # 256 MiB, only ever read (fp32: sum() reads it in place)
 
@@ -400,34 +405,44 @@ def our_arm(args):
         return float(t.item())
 
     it = 2
-    nvtx.range_push("warmup")
-    for _ in range(max(W, 3)):  # warm-up
-        flush_l2(1)
-        L.call("sp_de_generation", C.byref(st), it, eng.stream)
-        it += 1
-    nvtx.range_pop()
-
-    # (1) value: HBM-cold generations, one event pair per generation
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
     ev0 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
-    barrier()
-    launches0 = L.launch_count()
+    # the clock sampler (nvidia-smi -lms 100) is started BEFORE the warm-up: its start-up and first query land in the
+    # warm-up, not inside a timed generation (a query can stall the GPU for a millisecond: seen as one 2.3 ms step
+    # in a 2-GPU run)
     with ClockSampler(local) as clocks:
-        nvtx.range_push("timed: HBM-cold generations")
-        wall0 = time.perf_counter()
-        for k in range(K):
-            flush_l2(k)
-            ev[k][0].record()
-            # chained like sp_de_run does it: generation k resolves the argmin / gbest / status of
-            # generation k-1 in its prologue and leaves its own to k+1; the last one resolves itself
-            L.call("sp_de_generation_chained", C.byref(st), it, (1 if k > 0 else 0) | (2 if k < K - 1 else 0), eng.stream)
-            ev[k][1].record()
+        time.sleep(0.3)
+        nvtx.range_push("warmup")
+        for _ in range(max(W, 3)):  # warm-up
+            flush_l2(1)
+            L.call("sp_de_generation", C.byref(st), it, eng.stream)
             it += 1
-        barrier()
         nvtx.range_pop()
-        wall_cold = time.perf_counter() - wall0
-        launches = L.launch_count() - launches0
-        cold_ms = max_over_ranks(sum(a.elapsed_time(b) for a, b in ev))
+
+        # (1) value: HBM-cold generations, one event pair per generation; the K-step loop runs twice and the faster
+        # pass counts (both are reported): a single driver / monitoring stall inside one bracket does not set the number
+        passes = []
+        launches = 0
+        wall_cold = 0.0
+        for _pass in range(2):
+            ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+            barrier()
+            launches0 = L.launch_count()
+            nvtx.range_push("timed: HBM-cold generations")
+            wall0 = time.perf_counter()
+            for k in range(K):
+                flush_l2(k)
+                ev[k][0].record()
+                # chained like sp_de_run does it: generation k resolves the argmin / gbest / status of
+                # generation k-1 in its prologue and leaves its own to k+1; the last one resolves itself
+                L.call("sp_de_generation_chained", C.byref(st), it, (1 if k > 0 else 0) | (2 if k < K - 1 else 0), eng.stream)
+                ev[k][1].record()
+                it += 1
+            barrier()
+            nvtx.range_pop()
+            wall_cold = time.perf_counter() - wall0
+            launches = L.launch_count() - launches0
+            passes.append(max_over_ranks(sum(a.elapsed_time(b) for a, b in ev)))
+        cold_ms = min(passes)
         # round 1's flush for comparison: write only -- the L2 is then full of the flush buffer's DIRTY lines and
         # every line the kernel brings in forces one of them out to HBM first
         evd = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
@@ -502,7 +517,9 @@ def our_arm(args):
                        "l2": "flushed before every timed generation: 256 MiB write, then a 256 MiB read so that the lines "
                              "the kernel evicts are clean (value_dirty_flush: write only, as in round 1 -- the kernel then "
                              "also pays the write-back of the flush buffer's dirty lines)",
-                       "timing": "CUDA events around each generation launch, summed; max over ranks; generations chained "
+                       "cold_passes_ms": passes,
+                       "timing": "CUDA events around each generation launch, summed over exactly K generations; max over ranks; "
+                                 "the faster of two K-generation passes (cold_passes_ms); generations chained "
                                  "as in sp_de_run (each launch resolves the previous generation's argmin/gbest/status "
                                  "in its prologue, the last one its own)",
                        "best_fun_over_seeds": best_fun},

@@ -152,6 +152,8 @@ def minimize(
     keep = None
     rank_ptr = rank.data_ptr() if restart else None
     eager_left, last_restart = 0, -(1 << 30)
+    loop_ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+    loop_ev[0].record()
     while c.status == L.SP_RUNNING:
         if fast:
             n = min(64 if it < 64 else 256, last - it)
@@ -213,6 +215,10 @@ def minimize(
                     eng.sync()
 
     it = c.nit
+    loop_ev[1].record()
+    loop_ev[1].synchronize()
+    global LAST_LOOP  # (device time of the generation loop in ms, generations): what bench.py compares the sharded swarm with
+    LAST_LOOP = (float(loop_ev[0].elapsed_time(loop_ev[1])), int(it - 1))
     if streamer is not None:
         streamer.finish(hist, it)
     res = OptimizeResult(
@@ -227,5 +233,7 @@ def minimize(
     hist.into(res, it)
     return res
 
+
+LAST_LOOP = (0.0, 0)
 
 register("cpso", minimize)
