@@ -348,16 +348,24 @@ def vdcma_seeds(sb, dist, world, per_gpu=8, gens=100):
     b = [[-BOUND, BOUND]] * 1024
     o = dict(popsize=16384, dtype="float32", **OFF)
     parallel.minimize_seeds(sb.factory.ackley, b, list(range(world)), method="vdcma", options=dict(o, maxiter=3))
-    dist.barrier()
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
     seeds = list(range(per_gpu * world))
-    r = parallel.minimize_seeds(sb.factory.ackley, b, seeds, method="vdcma", options=dict(o, maxiter=gens))
-    torch.cuda.synchronize()
-    dist.barrier()
-    dt = time.perf_counter() - t0
-    return {"seeds": len(seeds), "generations": gens, "popsize": 16384, "ndim": 1024, "seconds": dt,
-            "evals_per_s": len(seeds) * gens * 16384 / dt, "best_fun": float(r["fun"])}
+    out = {"seeds": len(seeds), "generations": gens, "popsize": 16384, "ndim": 1024}
+    for conc, tag in ((1, "_sequential"), (4, "")):  # one run at a time, then four at a time on their own streams
+        parallel.minimize_seeds(sb.factory.ackley, b, list(range(conc * world)), method="vdcma", options=dict(o, maxiter=3),
+                                concurrent=conc)
+        dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        r = parallel.minimize_seeds(sb.factory.ackley, b, seeds, method="vdcma", options=dict(o, maxiter=gens), concurrent=conc)
+        torch.cuda.synchronize()
+        dist.barrier()
+        dt = time.perf_counter() - t0
+        out["seconds" + tag] = dt
+        out["evals_per_s" + tag] = len(seeds) * gens * 16384 / dt
+        out["best_fun" + tag] = float(r["fun"])
+    out["concurrent_runs_per_gpu"] = 4
+    out["same_best_as_sequential"] = bool(out["best_fun"] == out["best_fun_sequential"])
+    return out
 
 
 def our_arm(args):

@@ -16,8 +16,8 @@ for dt in ("float32", "float64"):
     torch.cuda.synchronize()
     out = (C.c_longlong * 16)()
     lib = L.load()
-    lib.sp_debug_vd_clocks.argtypes = [C.POINTER(C.c_longlong)]
-    lib.sp_debug_vd_clocks(out)
+    lib.sp_debug_vd_clocks.argtypes = [C.POINTER(C.c_longlong), C.c_int]
+    lib.sp_debug_vd_clocks(out, 0 if dt == "float32" else 1)
     v = list(out)
     names = ["phase1", "loads+pre", "L1 reduce", "p/q vectors", "vq reduce", "ria/via (+reduce)", "svnn (+reduce)",
              "ngv/ngd (+reduce)", "apply + L6 pre", "L6 reduce", "tail stores"]

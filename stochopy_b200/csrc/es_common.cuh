@@ -29,6 +29,10 @@ __global__ void normal_fill_kernel(T* __restrict__ Z, int64_t P, int N, int64_t 
   }
 }
 
+// VD-CMA work-buffer layout (vdcma_impl.cuh; sp_vd_work_scalars in vdcma.cu)
+constexpr int kVdChunks = 256;  // row chunks of the weighted sums
+constexpr int kVdUpMax = 512;   // CTAs of vd_update_kernel's chunk reduction: 3 N / 32, N <= 2048 -> <= 192
+
 // Block reductions through shared memory.  s_red must hold kRedDoubles doubles.
 constexpr int kRedMax = 16;                       // values per combined reduction
 constexpr int kRedDoubles = kRedMax * 32 + kRedMax;

@@ -9,6 +9,7 @@ PyTorch is used for device buffers and streams only.
 """
 import ctypes as C
 import functools
+import threading
 import os
 
 import numpy as np
@@ -31,7 +32,7 @@ messages = {
 }
 
 _TORCH_DT = {"float32": torch.float32, "float64": torch.float64}
-_PINNED = {}  # one pinned 64-byte landing pad for the control block per device
+_PINNED = {}  # one pinned landing pad for the control block per (device, host thread): concurrent runs do not share it
 
 
 def resolve_dtype(dtype):
@@ -100,7 +101,7 @@ class Engine:
         # device, so the front-ends run under `device_scope` which makes this device current
         self.device = torch.device("cuda", torch.cuda.current_device() if dev.index is None else dev.index)
         self.vec = 16 // self.np_dt.itemsize
-        key = (self.device.type, self.device.index)
+        key = (self.device.type, self.device.index, threading.get_ident())
         if key not in _PINNED:
             _PINNED[key] = torch.empty(512, dtype=torch.uint8, pin_memory=True)
         self._ctrl_host = _PINNED[key]

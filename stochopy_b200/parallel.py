@@ -177,15 +177,41 @@ def reduce_best(funs, xs, group=None, device=None):
     return float(rows[b, 0]), rows[b, 1:].copy(), rows[:, 0].copy()
 
 
-def minimize_seeds(fun, bounds, seeds, method="de", options=None, group=None, runner=None):
+def minimize_seeds(fun, bounds, seeds, method="de", options=None, group=None, runner=None, concurrent=1):
     """Run one optimisation per seed, seeds sharded over the ranks; returns the best
-    OptimizeResult-like dict plus every seed's final value (identical on all ranks)."""
+    OptimizeResult-like dict plus every seed's final value (identical on all ranks).
+
+    concurrent > 1: this rank's seeds run on that many host threads, each on its own CUDA stream, so the
+    latency-bound stages of one run (ranking, single-CTA updates, status reads) overlap the wide kernels of the
+    others (seeds batched per GPU).  Results do not depend on it (every run has its own buffers,
+    control block and Philox key)."""
     from .optimize import minimize
 
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     runner = runner or (lambda seed: minimize(fun, bounds, method=method, options=dict(options or {}, seed=seed)))
-    mine = [runner(s) for s in shard_seeds(seeds, rank, world)]
+    local_seeds = shard_seeds(seeds, rank, world)
+    if concurrent > 1 and len(local_seeds) > 1 and torch.cuda.is_available():
+        from concurrent.futures import ThreadPoolExecutor
+
+        dev = torch.cuda.current_device()
+        main = torch.cuda.current_stream(dev)
+        ready = torch.cuda.Event()
+        ready.record(main)
+
+        def on_stream(seed):
+            torch.cuda.set_device(dev)  # a new host thread starts on device 0
+            st = torch.cuda.Stream(device=dev)
+            st.wait_event(ready)
+            with torch.cuda.stream(st):
+                r = runner(seed)
+                st.synchronize()
+            return r
+
+        with ThreadPoolExecutor(max_workers=int(concurrent)) as pool:
+            mine = list(pool.map(on_stream, local_seeds))
+    else:
+        mine = [runner(s) for s in local_seeds]
     n = len(bounds)
     funs = [r["fun"] for r in mine]
     xs = [r["x"] for r in mine] if mine else np.empty((0, n))
