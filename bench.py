@@ -350,7 +350,8 @@ def vdcma_seeds(sb, dist, world, per_gpu=8, gens=100):
     parallel.minimize_seeds(sb.factory.ackley, b, list(range(world)), method="vdcma", options=dict(o, maxiter=3))
     seeds = list(range(per_gpu * world))
     out = {"seeds": len(seeds), "generations": gens, "popsize": 16384, "ndim": 1024}
-    for conc, tag in ((1, "_sequential"), (4, "")):  # one run at a time, then four at a time on their own streams
+    best = None
+    for conc, tag in ((1, "_sequential"), (4, "_4_at_a_time"), (8, "_8_at_a_time")):  # per GPU, each on its own stream
         parallel.minimize_seeds(sb.factory.ackley, b, list(range(conc * world)), method="vdcma", options=dict(o, maxiter=3),
                                 concurrent=conc)
         dist.barrier()
@@ -363,8 +364,12 @@ def vdcma_seeds(sb, dist, world, per_gpu=8, gens=100):
         out["seconds" + tag] = dt
         out["evals_per_s" + tag] = len(seeds) * gens * 16384 / dt
         out["best_fun" + tag] = float(r["fun"])
-    out["concurrent_runs_per_gpu"] = 4
-    out["same_best_as_sequential"] = bool(out["best_fun"] == out["best_fun_sequential"])
+        if best is None or dt < best[0]:
+            best = (dt, conc)
+    out["seconds"], out["concurrent_runs_per_gpu"] = best
+    out["evals_per_s"] = len(seeds) * gens * 16384 / best[0]
+    out["best_fun"] = out["best_fun_sequential"]
+    out["same_best_in_every_mode"] = bool(out["best_fun_4_at_a_time"] == out["best_fun_sequential"] == out["best_fun_8_at_a_time"])
     return out
 
 

@@ -133,6 +133,9 @@ def shared_seed(seed, group=None):
     return int(t.cpu().item())
 
 
+_SEED_STREAMS = {}  # (device, k) -> the k worker streams of minimize_seeds(concurrent=k)
+
+
 def shard_range(total, rank, world):
     """Contiguous, balanced [start, stop) of `total` items for `rank` (first ranks get the extras)."""
     q, r = divmod(int(total), int(world))
@@ -195,21 +198,27 @@ def minimize_seeds(fun, bounds, seeds, method="de", options=None, group=None, ru
         from concurrent.futures import ThreadPoolExecutor
 
         dev = torch.cuda.current_device()
-        main = torch.cuda.current_stream(dev)
+        k = min(int(concurrent), len(local_seeds))
+        # one stream per worker, kept for the life of the process: PyTorch's caching allocator pools blocks per
+        # stream, so a fresh stream per run would pay a cudaMalloc (and its device-wide sync) for every buffer
+        streams = _SEED_STREAMS.setdefault((dev, k), [torch.cuda.Stream(device=dev) for _ in range(k)])
         ready = torch.cuda.Event()
-        ready.record(main)
+        ready.record(torch.cuda.current_stream(dev))
 
-        def on_stream(seed):
+        def worker(w):
             torch.cuda.set_device(dev)  # a new host thread starts on device 0
-            st = torch.cuda.Stream(device=dev)
+            st = streams[w]
             st.wait_event(ready)
+            out = []
             with torch.cuda.stream(st):
-                r = runner(seed)
+                for j in range(w, len(local_seeds), k):
+                    out.append((j, runner(local_seeds[j])))
                 st.synchronize()
-            return r
+            return out
 
-        with ThreadPoolExecutor(max_workers=int(concurrent)) as pool:
-            mine = list(pool.map(on_stream, local_seeds))
+        with ThreadPoolExecutor(max_workers=k) as pool:
+            done = [r for part in pool.map(worker, range(k)) for r in part]
+        mine = [r for _, r in sorted(done, key=lambda t: t[0])]
     else:
         mine = [runner(s) for s in local_seeds]
     n = len(bounds)

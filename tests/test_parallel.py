@@ -198,3 +198,22 @@ def test_multi_gpu_sharded_swarm_equals_single_gpu(world):
            "--master-addr", "127.0.0.1", "--master-port", str(_free_port()), os.path.join(here, "multi_gpu_check.py")]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "multi_gpu_check ok" in r.stdout, (r.stdout[-2000:], r.stderr[-4000:])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("method,n,opts", [("vdcma", 300, dict(popsize=600, maxiter=12, dtype="float32")),
+                                           ("de", 128, dict(popsize=900, maxiter=15, dtype="float32", updating="deferred")),
+                                           ("cpso", 10, dict(popsize=500, maxiter=30, competitivity=1.0, updating="deferred"))])
+def test_minimize_seeds_concurrent_streams_equal_sequential(method, n, opts):
+    """A rank's seeds on several host threads with their own CUDA streams (minimize_seeds(concurrent=k)):
+    every run has its own buffers, control block and Philox key, so the results are those of the sequential
+    loop, bit for bit."""
+    import stochopy_b200 as sb
+
+    b = [[-5.12, 5.12]] * n
+    seeds = list(range(6))
+    a = parallel.minimize_seeds(sb.factory.rastrigin, b, seeds, method=method, options=opts)
+    c = parallel.minimize_seeds(sb.factory.rastrigin, b, seeds, method=method, options=opts, concurrent=3)
+    assert np.array_equal(a["funs"], c["funs"]) and a["fun"] == c["fun"] and np.array_equal(a["x"], c["x"])
+    for ra, rc in zip(a["local"], c["local"]):
+        assert (ra.nit, ra.status, ra.nfev) == (rc.nit, rc.status, rc.nfev) and np.array_equal(ra.x, rc.x)
