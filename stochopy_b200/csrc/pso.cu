@@ -54,7 +54,7 @@ struct PsoArgs {
 // rounding of the working-precision sums.
 template <typename T>
 __device__ __forceinline__ void restart_decide_bound(sp_ctrl* ctrl, double m2, int N, int64_t Ptot, int it, int maxiter,
-                                                     double gamma, double delta) {
+                                                     double gamma, double delta, bool force_undecided) {
   if (ctrl->status != SP_RUNNING) {  // the generation terminated the run: no restart (_cpso.py:304)
     ctrl->flag = 0;
     return;
@@ -63,6 +63,11 @@ __device__ __forceinline__ void restart_decide_bound(sp_ctrl* ctrl, double m2, i
   const double dist = ctrl->dist, M = sqrt(m2), s4n = sqrt(4.0 * (double)N);
   const double hi = (M * (1.0 + eps) + dist) / s4n, lo = (M * (1.0 - eps) - dist) / s4n;
   ctrl->aux[1] = M / s4n;
+  if (force_undecided) {  // test hook (SP_CPSO_FORCE_AMBIGUOUS): every generation goes through the exact path
+    ctrl->flag = -1;
+    ctrl->status = SP_STATUS_RESTART_PENDING;
+    return;
+  }
   if (lo >= delta) {  // certainly no restart
     ctrl->flag = 0;
     return;
@@ -324,7 +329,7 @@ pso_generation_kernel(const PsoArgs<T> a, const PhiloxKeys keys) {
         __syncthreads();
         if (threadIdx.x == 0) {
           for (int w = 1; w < kThreads / 32; ++w) d = fmax(d, s_dmax[w]);
-          restart_decide_bound<T>(a.ctrl, d, a.N, a.P, a.it, a.maxiter, a.gamma, a.delta);
+          restart_decide_bound<T>(a.ctrl, d, a.N, a.P, a.it, a.maxiter, a.gamma, a.delta, a.rbound == 2);
         }
       }
     }
@@ -677,7 +682,7 @@ static int pso_launch(const sp_pso_state* st, int it, int propose_only, cudaStre
   a.peer = peer_args<T>(st);
   a.chain = propose_only ? 0 : chain;
   a.chain_rows = (T*)st->chain_rows;
-  a.rbound = rbound ? 1 : 0;
+  a.rbound = rbound ? (getenv("SP_CPSO_FORCE_AMBIGUOUS") != nullptr ? 2 : 1) : 0;  // 2: test hook, see restart_decide_bound
   a.gamma = st->gamma;
   a.delta = st->delta;
   const bool philox = st->r1 == nullptr;

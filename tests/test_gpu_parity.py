@@ -592,3 +592,19 @@ def test_return_all_streaming_window_wraps(method, opts, monkeypatch):
         d = sb.optimize.minimize(sb.factory.sphere, b, method=method, options=dict(o), callback=lambda X, s: None)
         assert (a.nit, a.status) == (d.nit, d.status)
         assert np.array_equal(a.xall, d.xall) and np.array_equal(a.funall, d.funall)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_cpso_undecided_bound_takes_the_exact_radius_path(dtype, monkeypatch):
+    """The lazy CPSO run decides the restart from a bound on the swarm radius inside the generation kernel and parks
+    with flag = -1 when the bound cannot tell; sp_cpso_restart_resume then decides with the exact radius kernel.
+    SP_CPSO_FORCE_AMBIGUOUS sends EVERY generation down that path: the trajectory must still be the eager one's."""
+    import stochopy_b200 as sb
+
+    b = [[-5.12, 5.12]] * 6
+    o = dict(maxiter=60, popsize=200, seed=8, dtype=dtype, competitivity=1.0, updating="deferred", xtol=-1.0, ftol=-1.0e300)
+    d = sb.optimize.minimize(sb.factory.rastrigin, b, method="cpso", options=dict(o), callback=lambda X, s: None)
+    monkeypatch.setenv("SP_CPSO_FORCE_AMBIGUOUS", "1")
+    a = sb.optimize.minimize(sb.factory.rastrigin, b, method="cpso", options=dict(o))
+    assert (a.nit, a.status, a.nfev) == (d.nit, d.status, d.nfev) == (60, -1, 60 * 200)
+    assert np.array_equal(a.x, d.x) and a.fun == d.fun
