@@ -1,20 +1,26 @@
-// DE generation kernel for full-warp rows (32 lanes per row): a per-SM row pool
-// drained by warp-private TMA pipelines.
+// DE generation kernel for full-warp rows (32 lanes per row): a per-SM row pool.
 //
 // One CTA per SM owns a contiguous slice of the population (about P/148 rows):
 //   phase 0  every thread draws the donors + forced crossover column of one row of
-//            the slice (one Philox call per row) into shared-memory tables and
-//            stages pbestfit for the slice;
-//   phase 1  warps claim rows one at a time from a shared counter -- fast warps
-//            take more rows, so the whole SM stays busy until the slice is empty --
-//            and keep S claimed rows in flight in a warp-private ring: a stage is
-//            the individual's own row + its K donor rows, fetched by cp.async.bulk
-//            (1-D TMA, SASS UBLKCP) onto the stage's mbarrier;
-//            mutant -> crossover (test on the raw Philox words, crossover_cut) ->
-//            repair -> objective -> strict-< selection -> 16-byte row store;
+//            the slice (one Philox call per row) into a per-row record table in shared
+//            memory (fixed offset: every access in the row loop is [row * stride + imm])
+//            and stages pbestfit for the slice;
+//   phase 1  warps claim rows from a shared counter -- fast warps take more rows, so the
+//            whole SM stays busy until the slice is empty.  Two ways to move the rows:
+//            * register pipeline (CH == 1, K <= 3; the headline shape): rows are claimed in
+//              PAIRS; while row A is processed, the own row + K donor rows of row B travel
+//              into a second register set with plain 16-byte loads;
+//            * TMA ring (wider rows, 4 / 5 donors): S claimed rows in flight in a
+//              warp-private ring, a stage = the K donor rows fetched by cp.async.bulk
+//              (1-D TMA, SASS UBLKCP) onto the stage's mbarrier, the own row one row ahead
+//              through registers;
+//            mutant -> crossover (16-bit pieces of one Philox2x32-10 call per 4 columns,
+//            philox.cuh) -> repair -> objective -> strict-< selection -> 16-byte row store;
 //   phase 2  pbestfit / pfit of the slice are written back coalesced, the CTA's
-//            (fitness, row) minimum goes to scratch and the last CTA finalises.
-// Strategy is a template parameter (donor count, mutant formula static).
+//            (fitness, row) minimum goes to scratch and the last CTA finalises (or, chained,
+//            the next launch's prologue does).
+// Strategy is a template parameter (donor count, mutant formula static); for the register
+// pipeline's FULL + PLAIN variant the objective can be one too (Rosenbrock, Rastrigin).
 // FULL: ndim == 32 * VEC * CH == ld, so no padding masks are needed.
 #pragma once
 #include "de_common.cuh"
